@@ -1,0 +1,313 @@
+"""Benchmark of the per-tile raster compute path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+
+Workload at every N: BASELINE.json configs[1] -- Reclassify + Clip + Step +
+IsData on a 16384 x 16384 int16 / float32 MemorySource pair -- one such raster
+pair per GPU (weak scaling, no data-path collective: pixels are independent).
+A step is one pass of the fused chain over the whole raster pair.
+
+  value     Gpixel/s with the inputs resident in HBM (CUDA events around K launches)
+  e2e       the same metric through ``view.get_data(**request)`` with host NumPy
+            inputs: pinned H2D of both rasters and D2H of the result in every step
+  roofline  algorithmic bytes (2 + 4 in, 1 out = 7 B/px) / measured kernel time
+            against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle port of the same chain (NumPy, all host threads)
+            on a bounded row-stripe sample of the same inputs
+
+``--impl reference`` times that CPU port as the reference arm (the reference is
+pure NumPy/SciPy; its own package cannot be imported without GDAL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fused raster chain throughput (Reclassify+Clip+Step+IsData)"
+UNIT = "Gpixel/s"
+BYTES_PER_PIXEL = 7  # int16 + float32 in, bool out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=16384, help="raster edge in pixels")
+    ap.add_argument("--cpu-sample-rows", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline (oracle port, threaded over row tiles)
+# ----------------------------------------------------------------------------
+
+
+def cpu_chain_throughput(ints, floats, rows, repeats, threads):
+    """Gpixel/s of the oracle chain on the first ``rows`` rows, tiled over threads."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from dask_geomodeling_b200.workloads import CFG2_PAIRS
+    from oracle import workloads as ow
+
+    rows = min(rows, ints.shape[1])
+    tile = max(rows // (threads * 2), 64)
+    bounds = [(r, min(r + tile, rows)) for r in range(0, rows, tile)]
+
+    def work(b):
+        r0, r1 = b
+        (isdata, _), _ = ow.cfg2(ints[:, r0:r1], floats[:, r0:r1], CFG2_PAIRS)
+        return int(isdata.sum())
+
+    best = None
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(work, bounds[: threads]))  # warm-up
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            list(pool.map(work, bounds))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    pixels = rows * ints.shape[2]
+    return pixels / best / 1e9, pixels, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size = args.size
+    threads = os.cpu_count() or 1
+    rows = min(args.cpu_sample_rows, size)
+    # only the sampled stripe is generated: same generator, same seed, first rows
+    ints, floats = _stripe(size, rows)
+    times = []
+    for step in range(args.warmup + args.steps):
+        gpx, pixels, dt = cpu_chain_throughput(ints, floats, rows, 1, threads)
+        if step >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = pixels / (ms / 1e3) / 1e9
+    sample = "first {} rows x {} cols of the {}x{} workload per step".format(rows, size, size, size)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16/float32->bool", "data": "synthetic",
+        "config": {"workload": "cfg2 Reclassify+Clip+Step+IsData {}x{} int16/float32".format(size, size),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def _stripe(size, rows):
+    from dask_geomodeling_b200 import workloads
+
+    rng = np.random.default_rng(43)
+    shape = (1, rows, size)
+    ints = workloads._with_nodata(rng, rng.integers(0, 50, shape, dtype=np.int16), 32767, 0.05)
+    floats = workloads._with_nodata(rng, rng.uniform(0, 100, shape).astype(np.float32),
+                                    workloads.F32_MAX, 0.05)
+    return ints, floats
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+
+
+class ClockSampler(object):
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, sm_max, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max = float(parts[1])
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("GM_DEVICE", str(local_rank))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from dask_geomodeling_b200 import _native, workloads
+    from dask_geomodeling_b200.core import fusion
+    from dask_geomodeling_b200.raster import _program
+
+    size = args.size
+    pixels = size * size
+    ints, floats = workloads.cfg2_arrays(size, seed=43 + rank)
+    view, _ = workloads.cfg2_views(ints, floats)
+    request = workloads.request(size, size)
+
+    # ---- kernel-resident measurement: compile once, launch K times -------------
+    graph, name = view.get_compute_graph(**request)
+    fused = fusion.optimize(graph, name)
+    task = fused[name]
+    assert task[0] is fusion.fused_process, "the chain did not fuse into one task"
+    plan, leaf_keys = task[1], task[2:]
+    stream = torch.cuda.current_stream()
+    with _native.use_stream(stream.cuda_stream), fusion.device_resident():
+        leaf_payloads = [fused[k][0](*fused[k][1:]) for k in leaf_keys]  # H2D, once
+        inputs = [p["values"] for p in leaf_payloads]
+        leaf_types = [(p["values"].dtype, p["no_data_value"]) for p in leaf_payloads]
+        compiled = _program.CompiledProgram([fusion.build_expression(plan)], leaf_types)
+        out = _native.DeviceArray((1, size, size), compiled.results[0].dtype)
+        for _ in range(max(args.warmup, 3)):
+            compiled.launch(inputs, [out])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        launches_before = _native.launch_count()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        for _ in range(args.steps):
+            compiled.launch(inputs, [out])
+        stop.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches = _native.launch_count() - launches_before
+        elapsed_ms = start.elapsed_time(stop)
+        clocks = sampler.stop() if sampler else None
+        checksum = int(np.asarray(out.to_host()).sum())
+        del inputs, leaf_payloads, out
+
+    # ---- end to end through the Block API: host arrays in, host array out ----------
+    with _native.use_stream(stream.cuda_stream):
+        view.get_data(**request)  # warm-up: tokens, pinning, pool
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            result = view.get_data(**request)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    assert int(result["values"].sum()) == checksum, "e2e result differs from the resident result"
+    h2d = ints.nbytes + floats.nbytes
+    d2h = result["values"].nbytes
+
+    t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_per_step = elapsed_ms / args.steps
+        value = world * pixels / (ms_per_step / 1e3) / 1e9
+        e2e_value = world * pixels * args.e2e_steps / e2e_s / 1e9
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
+        else:
+            peak, peak_kind = 6650.0, "fallback"
+        achieved = BYTES_PER_PIXEL * pixels / (ms_per_step / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16/float32->bool",
+            "data": "synthetic",
+            "config": {
+                "workload": "cfg2 Reclassify+Clip+Step+IsData {0}x{0} int16/float32 per GPU".format(size),
+                "l2": "inputs {:.2f} GiB per step >> 126 MB L2, no flush needed".format(h2d / 2 ** 30),
+                "parallelism": "row stripes, one raster pair per GPU, no collective",
+                "checksum_true_pixels": checksum,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "bytes_per_pixel": BYTES_PER_PIXEL, "kernel": "eval_kernel<4,2>"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1:
+            threads = os.cpu_count() or 1
+            rows = min(args.cpu_sample_rows, size)
+            gpx, cpu_pixels, best = cpu_chain_throughput(ints, floats, rows, 3, threads)
+            line["cpu_baseline"] = {
+                "value": gpx, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "first {} rows x {} cols of the same inputs, best of 3 ({:.2f} s)".format(
+                    rows, size, best),
+            }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,675 @@
+"""Compiler from element-wise block expressions to evaluator bytecode.
+
+An expression is a DAG of ``Node`` objects over ``Leaf`` inputs (rasters that
+are already materialised) and python/numpy scalars.  ``evaluate`` infers the
+NumPy result dtypes and no data sentinels exactly as the reference blocks do
+(raster/elemwise.py:134-152, :235-299; raster/misc.py),
+lowers the DAG to the accumulator machine of include/geokernels.h and runs it
+in ONE CUDA launch through ``gm_eval_program``.
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _native
+from ..utils import get_dtype_max, get_uint_dtype, get_int_dtype
+
+C_I32, C_I64, C_F32, C_F64 = 0, 1, 2, 3
+_WIDE = (C_I64, C_F64)
+
+# GmOp (order matters: it is the enum in include/geokernels.h)
+_OPS = [
+    "LOAD", "ST", "OUT", "CVT", "ADD", "SUB", "RSUB", "MUL", "DIV", "RDIV", "POW", "RPOW",
+    "EXP", "LOG", "LOG10", "EQ", "NE", "GT", "GE", "LT", "LE", "AND", "OR", "XOR", "NOT",
+    "ISDATA", "ISNODATA", "OVERLAY", "CLIP", "MASK", "MASKBELOW", "STEP", "CLASSIFY", "RECLASS",
+]
+OP = {name: i for i, name in enumerate(_OPS)}
+SRC_NONE, SRC_REG, SRC_INPUT, SRC_IMM = 0, 1, 2, 3
+F_ND_A, F_ND_B, F_CLOSE, F_ND_FINITE, F_B_BOOL, F_RIGHT, F_SELECT, F_ND_T = 1, 2, 4, 8, 16, 32, 64, 128
+
+DENSE_TABLE_LIMIT = 4096
+
+
+class FusionLimit(Exception):
+    """The expression does not fit one program (registers, inputs, length)."""
+
+
+class Leaf(object):
+    def __init__(self, index):
+        self.index = index
+
+
+class Node(object):
+    """``op`` applied to ``children`` (Leaf | Node | scalar) with literal ``params``."""
+
+    def __init__(self, op, children, **params):
+        self.op = op
+        self.children = list(children)
+        self.params = params
+
+
+def dtype_class(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return C_F32
+    if dtype == np.float64:
+        return C_F64
+    if dtype in (np.dtype("u4"), np.dtype("i8")):
+        return C_I64
+    if dtype == bool or (dtype.kind in "iu" and dtype.itemsize <= 4):
+        return C_I32
+    raise TypeError("dtype '{}' is not supported by the CUDA raster path".format(dtype))
+
+
+def _bits(value, cls):
+    """Raw 64-bit pattern of ``value`` in class ``cls``."""
+    if cls == C_I32:
+        return int(value) & 0xFFFFFFFF
+    if cls == C_I64:
+        return int(value) & 0xFFFFFFFFFFFFFFFF
+    with np.errstate(over="ignore"):
+        if cls == C_F32:
+            return int(np.array(value, dtype=np.float32).view(np.uint32))
+        return int(np.array(value, dtype=np.float64).view(np.uint64))
+
+
+def _is_scalar(x):
+    return isinstance(x, (bool, int, float, np.generic))
+
+
+def sentinel(dtype, nodata):
+    """Value ``v`` such that ``values == nodata`` (NumPy semantics) is exactly
+    ``values == v`` in ``dtype``; None when the comparison can never be true."""
+    if nodata is None:
+        return None
+    dtype = np.dtype(dtype)
+    try:
+        if dtype == bool:
+            return None
+        if dtype.kind in "iu":
+            if isinstance(nodata, (float, np.floating)) and not float(nodata).is_integer():
+                return None
+            v = int(nodata)
+            info = np.iinfo(dtype)
+            return v if info.min <= v <= info.max else None
+        with np.errstate(over="ignore"):
+            v = dtype.type(nodata)
+        if np.isnan(v) or float(v) != float(nodata):
+            return None
+        return v
+    except (TypeError, ValueError, OverflowError):
+        return None
+
+
+def _isclose_terms(dtype, nodata):
+    """(compare dtype, y, tol, isfinite(y)) reproducing ``np.isclose(values, nodata)``
+    term by term (numpy/_core/numeric.py isclose): ``abs(x - y) <= atol + rtol*abs(y)``."""
+    y = nodata
+    if isinstance(y, (bool, int)) and not isinstance(y, np.generic):
+        y = float(y)
+    elif isinstance(y, np.generic):
+        y = np.asarray(y, dtype=np.result_type(y, 1.0))[()]
+    probe = np.zeros(1, dtype=dtype)
+    with np.errstate(all="ignore"):
+        cmp_dtype = (probe - y).dtype
+        rhs = 1e-8 + 1e-5 * abs(y)
+        if isinstance(rhs, np.generic):
+            cmp_dtype = np.result_type(cmp_dtype, rhs)
+        tol = np.asarray(rhs).astype(cmp_dtype)[()]
+        yy = np.asarray(y).astype(cmp_dtype)[()]
+    return np.dtype(cmp_dtype), yy, tol, bool(np.isfinite(y))
+
+
+def _cast_into(value, dtype):
+    """What ``array[index] = value`` stores in an array of ``dtype``."""
+    with np.errstate(all="ignore"):
+        return np.asarray(value).astype(dtype)[()]
+
+
+def _compare_dtype(dtypes_and_scalars):
+    return np.result_type(*dtypes_and_scalars)
+
+
+class _Typed(object):
+    __slots__ = ("dtype", "nodata")
+
+    def __init__(self, dtype, nodata):
+        self.dtype = np.dtype(dtype)
+        self.nodata = nodata
+
+    @property
+    def cls(self):
+        return dtype_class(self.dtype)
+
+
+_MATH = {"add": "ADD", "subtract": "SUB", "multiply": "MUL", "divide": "DIV", "power": "POW"}
+_REVERSED = {"SUB": "RSUB", "DIV": "RDIV", "POW": "RPOW", "ADD": "ADD", "MUL": "MUL",
+             "EQ": "EQ", "NE": "NE", "GT": "LT", "LT": "GT", "GE": "LE", "LE": "GE",
+             "AND": "AND", "OR": "OR", "XOR": "XOR"}
+_COMPARE = {"equal": "EQ", "not_equal": "NE", "greater": "GT", "greater_equal": "GE",
+            "less": "LT", "less_equal": "LE"}
+_LOGIC = {"logical_and": "AND", "logical_or": "OR", "logical_xor": "XOR"}
+_UNARY_MATH = {"exp": "EXP", "log": "LOG", "log10": "LOG10"}
+
+
+class _Compiler(object):
+    def __init__(self, leaves):
+        self.leaves = leaves  # list of _Typed for every input
+        self.instr = []
+        self.tables = []      # dicts with numpy arrays (kept alive until launch)
+        self.free_regs = list(range(_native.GM_NREG))
+        self.uses = {}
+        self.in_reg = {}      # id(node) -> (reg, _Typed)
+        self.wide = False
+
+    # -- helpers ---------------------------------------------------------------
+    def emit(self, op, cls=C_I32, cls_a=C_I32, cls_b=C_I32, cls_out=C_I32, src=(SRC_NONE, 0),
+             flags=0, aux=0, k=()):
+        if len(self.instr) >= _native.GM_MAX_INSTR:
+            raise FusionLimit("program too long")
+        kk = [0] * 6
+        for i, v in enumerate(k):
+            kk[i] = v
+        for c in (cls, cls_a, cls_out) + ((cls_b,) if src[0] != SRC_NONE else ()):
+            if c in _WIDE:
+                self.wide = True
+        self.instr.append(dict(op=OP[op], cls=cls, cls_a=cls_a, cls_b=cls_b, cls_out=cls_out,
+                               src_kind=src[0], src=src[1], flags=flags, aux=aux, k=kk))
+
+    def count_uses(self, node):
+        if not isinstance(node, Node):
+            return
+        self.uses[id(node)] = self.uses.get(id(node), 0) + 1
+        if self.uses[id(node)] == 1:
+            for c in node.children:
+                self.count_uses(c)
+
+    def alloc_reg(self):
+        if not self.free_regs:
+            raise FusionLimit("out of registers")
+        return self.free_regs.pop(0)
+
+    def type_of(self, x):
+        """_Typed of an operand without emitting code (leaves and cached nodes)."""
+        if isinstance(x, Leaf):
+            return self.leaves[x.index]
+        return None
+
+    def operand(self, x):
+        """Make ``x`` available as the b operand.  Returns (src tuple, _Typed|None, k0)
+        where _Typed is None for scalars."""
+        if isinstance(x, Leaf):
+            return (SRC_INPUT, x.index), self.leaves[x.index], 0
+        if isinstance(x, Node):
+            reg, typed = self.in_reg[id(x)]
+            return (SRC_REG, reg), typed, 0
+        return (SRC_IMM, 0), None, x
+
+    def release(self, x):
+        """Called once per consumed use of a node that lives in a register."""
+        if isinstance(x, Node) and id(x) in self.in_reg:
+            self.uses[id(x)] -= 1
+            if self.uses[id(x)] <= 0:
+                reg, _ = self.in_reg.pop(id(x))
+                self.free_regs.append(reg)
+                self.free_regs.sort()
+
+    def to_acc(self, x):
+        """Bring ``x`` into the accumulator; returns its _Typed."""
+        if isinstance(x, Leaf):
+            t = self.leaves[x.index]
+            self.emit("LOAD", cls_b=t.cls, cls_out=t.cls, src=(SRC_INPUT, x.index))
+            return t
+        if isinstance(x, Node):
+            if id(x) in self.in_reg:
+                reg, t = self.in_reg[id(x)]
+                self.emit("LOAD", cls_b=t.cls, cls_out=t.cls, src=(SRC_REG, reg))
+                self.release(x)
+                return t
+            t = self.node(x)
+            if self.uses.get(id(x), 1) > 1:
+                reg = self.alloc_reg()
+                self.emit("ST", cls_a=t.cls, cls_out=t.cls, aux=reg)
+                self.in_reg[id(x)] = (reg, t)
+                self.release(x)
+            return t
+        raise TypeError("scalar cannot be the accumulator operand")
+
+    def spill_to_reg(self, x):
+        """Evaluate node ``x`` and park it in a register (if not there yet)."""
+        if id(x) in self.in_reg:
+            return
+        t = self.node(x)
+        reg = self.alloc_reg()
+        self.emit("ST", cls_a=t.cls, cls_out=t.cls, aux=reg)
+        self.in_reg[id(x)] = (reg, t)
+        if self.uses.get(id(x), 1) <= 1:
+            self.uses[id(x)] = 1
+
+    def binary_operands(self, a, b):
+        """Decide which operand is accumulated; returns (typed_a, typed_b|None,
+        src, k0, swapped) with the accumulator operand loaded."""
+        a_complex = isinstance(a, Node) and id(a) not in self.in_reg
+        b_complex = isinstance(b, Node) and id(b) not in self.in_reg
+        if _is_scalar(a) and _is_scalar(b):
+            raise TypeError("at least one operand must be a raster")
+        swapped = False
+        if b_complex and a_complex:
+            self.spill_to_reg(b)
+        elif b_complex or _is_scalar(a):
+            a, b, swapped = b, a, True
+        ta = self.to_acc(a)
+        src, tb, k0 = self.operand(b)
+        return ta, tb, src, k0, swapped, b
+
+    # -- per-op lowering -----------------------------------------------------------
+    def node(self, n):
+        handler = getattr(self, "op_" + n.op, None)
+        if handler is None:
+            if n.op in _MATH:
+                return self.math(n)
+            if n.op in _COMPARE:
+                return self.compare(n)
+            if n.op in _LOGIC:
+                return self.logic(n)
+            if n.op in _UNARY_MATH:
+                return self.unary_math(n)
+            raise NotImplementedError(n.op)
+        return handler(n)
+
+    def _nd_flags(self, ta, tb):
+        flags, k1, k2 = 0, 0, 0
+        if ta is not None:
+            s = sentinel(ta.dtype, ta.nodata)
+            if s is not None:
+                flags |= F_ND_A
+                k1 = _bits(s, ta.cls)
+        if tb is not None:
+            s = sentinel(tb.dtype, tb.nodata)
+            if s is not None:
+                flags |= F_ND_B
+                k2 = _bits(s, tb.cls)
+        return flags, k1, k2
+
+    def math(self, n):
+        dtype = np.dtype(n.params["dtype"])
+        fill = n.params["fillvalue"]
+        T = dtype_class(dtype)
+        a, b = n.children
+        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
+        op = _MATH[n.op]
+        if swapped:
+            op = _REVERSED[op]
+        flags, k1, k2 = self._nd_flags(ta, tb)
+        cls_b = T
+        if tb is None:
+            with np.errstate(all="ignore"):
+                k0 = _bits(np.asarray(k0).astype(dtype)[()], T)
+        else:
+            cls_b = tb.cls
+        self.emit(op, cls=T, cls_a=ta.cls, cls_b=cls_b, cls_out=T, src=src, flags=flags,
+                  k=(k0, k1, k2, _bits(fill, T)))
+        self.release(b_used)
+        return _Typed(dtype, fill)
+
+    def unary_math(self, n):
+        dtype = np.dtype(n.params["dtype"])
+        fill = n.params["fillvalue"]
+        T = dtype_class(dtype)
+        ta = self.to_acc(n.children[0])
+        flags, k1, _ = self._nd_flags(ta, None)
+        self.emit(_UNARY_MATH[n.op], cls=T, cls_a=ta.cls, cls_out=T, flags=flags,
+                  k=(0, k1, 0, _bits(fill, T)))
+        return _Typed(dtype, fill)
+
+    def compare(self, n):
+        a, b = n.children
+        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
+        op = _COMPARE[n.op]
+        if swapped:
+            op = _REVERSED[op]
+        terms = [ta.dtype, tb.dtype if tb is not None else k0]
+        cmp_dtype = _compare_dtype(terms)
+        T = dtype_class(cmp_dtype)
+        cls_b = tb.cls if tb is not None else T
+        if tb is None:
+            if T in (C_I32, C_I64):
+                v = int(k0)
+                if T == C_I32 and not (-2 ** 31 <= v < 2 ** 31):
+                    T = cls_b = C_I64
+                if T == C_I64 and ta.cls == C_I32 and -2 ** 31 <= v < 2 ** 31:
+                    T = cls_b = C_I32   # exact in 32 bits, keeps the program narrow
+                k0 = _bits(v, T)
+            else:
+                k0 = _bits(k0, T)
+        elif T == C_I64 and ta.cls == C_I32 and tb.cls == C_I32:
+            T = C_I32
+        flags, k1, k2 = self._nd_flags(ta, tb)
+        fill = 1 if n.op == "not_equal" else 0
+        self.emit(op, cls=T, cls_a=ta.cls, cls_b=cls_b, cls_out=C_I32, src=src, flags=flags,
+                  k=(k0, k1, k2, fill))
+        self.release(b_used)
+        return _Typed(bool, None)
+
+    def logic(self, n):
+        a, b = n.children
+        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
+        if tb is None:
+            k0 = 1 if k0 else 0
+        self.emit(_LOGIC[n.op], cls_a=ta.cls, cls_b=C_I32, src=src, k=(k0,))
+        self.release(b_used)
+        return _Typed(bool, None)
+
+    def op_invert(self, n):
+        self.to_acc(n.children[0])
+        self.emit("NOT")
+        return _Typed(bool, None)
+
+    def _is_data(self, n, op):
+        child = n.children[0]
+        if isinstance(child, Node) and child.op == "reclassify" and self.uses.get(id(child), 1) <= 1:
+            self.op_reclassify(child, nd_only=True)   # acc = "has data" boolean
+            if op == "ISNODATA":
+                self.emit("NOT")
+            return _Typed(bool, None)
+        ta = self.to_acc(child)
+        flags, k1, _ = self._nd_flags(ta, None)
+        self.emit(op, cls_a=ta.cls, flags=flags, k=(0, k1))
+        return _Typed(bool, None)
+
+    def op_isdata(self, n):
+        return self._is_data(n, "ISDATA")
+
+    def op_isnodata(self, n):
+        return self._is_data(n, "ISNODATA")
+
+    def op_fillnodata(self, n):
+        dtype = np.dtype(n.params["dtype"])
+        fill = get_dtype_max(dtype)
+        T = dtype_class(dtype)
+        complex_children = [c for c in n.children if isinstance(c, Node) and id(c) not in self.in_reg]
+        for c in complex_children:
+            self.spill_to_reg(c)
+        self.emit("LOAD", cls_b=T, cls_out=T, src=(SRC_IMM, 0), k=(_bits(fill, T),))
+        for c in n.children:
+            src, tc, _ = self.operand(c)
+            flags, cmp_cls, k2, k4 = 0, tc.cls, 0, 0
+            if tc.nodata is not None:
+                if tc.dtype.kind == "f":
+                    cmp_dtype, y, tol, fin = _isclose_terms(tc.dtype, tc.nodata)
+                    cmp_cls = dtype_class(cmp_dtype)
+                    flags = F_ND_T | F_CLOSE | (F_ND_FINITE if fin else 0)
+                    k2, k4 = _bits(y, cmp_cls), _bits(tol, cmp_cls)
+                else:
+                    s = sentinel(tc.dtype, tc.nodata)
+                    if s is not None:
+                        flags, k2 = F_ND_T, _bits(s, cmp_cls)
+            self.emit("OVERLAY", cls=cmp_cls, cls_a=T, cls_b=tc.cls, cls_out=T, src=src, flags=flags,
+                      k=(0, 0, k2, 0, k4))
+            self.release(c)
+        return _Typed(dtype, fill)
+
+    def op_clip(self, n):
+        store, mask = n.children
+        mask_is_reclass = (isinstance(mask, Node) and mask.op == "reclassify"
+                           and self.uses.get(id(mask), 1) <= 1 and id(mask) not in self.in_reg)
+        tm_bool = None
+        if mask_is_reclass:
+            self.op_reclassify(mask, nd_only=True)
+            reg = self.alloc_reg()
+            self.emit("ST", aux=reg)
+            tm_bool = _Typed(bool, None)
+            self.in_reg[id(mask)] = (reg, tm_bool)
+            self.uses[id(mask)] = 1
+        elif isinstance(mask, Node) and id(mask) not in self.in_reg:
+            self.spill_to_reg(mask)
+        ts = self.to_acc(store)
+        src, tm, _ = self.operand(mask)
+        flags, k2 = 0, 0
+        if tm.dtype == bool:
+            flags = F_B_BOOL
+        else:
+            s = sentinel(tm.dtype, tm.nodata)
+            if s is not None:
+                flags, k2 = F_ND_B, _bits(s, tm.cls)
+        nd = _cast_into(ts.nodata, ts.dtype) if ts.nodata is not None else 0
+        self.emit("CLIP", cls_a=ts.cls, cls_b=tm.cls, cls_out=ts.cls, src=src, flags=flags,
+                  k=(0, _bits(nd, ts.cls), k2))
+        self.release(mask)
+        return _Typed(ts.dtype, ts.nodata)
+
+    def op_mask(self, n):
+        value = n.params["value"]
+        if isinstance(value, float):
+            out_dtype = np.dtype("float32")
+        elif value >= 0:
+            out_dtype = get_uint_dtype(value)
+        else:
+            out_dtype = get_int_dtype(value)
+        fill = 1 if value == 0 else 0
+        out_cls = dtype_class(out_dtype)
+        ta = self.to_acc(n.children[0])
+        flags, cmp_cls, k1, k4 = 0, ta.cls, 0, 0
+        if ta.nodata is not None:
+            if ta.dtype.kind == "f":
+                cmp_dtype, y, tol, fin = _isclose_terms(ta.dtype, ta.nodata)
+                cmp_cls = dtype_class(cmp_dtype)
+                flags = F_ND_T | F_CLOSE | (F_ND_FINITE if fin else 0)
+                k1, k4 = _bits(y, cmp_cls), _bits(tol, cmp_cls)
+            else:
+                s = sentinel(ta.dtype, ta.nodata)
+                if s is not None:
+                    flags, k1 = F_ND_T, _bits(s, cmp_cls)
+        self.emit("MASK", cls=cmp_cls, cls_a=ta.cls, cls_out=out_cls, flags=flags,
+                  k=(_bits(_cast_into(value, out_dtype), out_cls), k1, 0,
+                     _bits(_cast_into(fill, out_dtype), out_cls), k4))
+        return _Typed(out_dtype, fill)
+
+    def _scalar_compare_class(self, ta, value):
+        T = dtype_class(_compare_dtype([ta.dtype, value]))
+        if T == C_I32 and not (-2 ** 31 <= int(value) < 2 ** 31):
+            T = C_I64
+        return T
+
+    def op_maskbelow(self, n):
+        value = n.params["value"]
+        ta = self.to_acc(n.children[0])
+        T = self._scalar_compare_class(ta, value)
+        nd = _cast_into(ta.nodata, ta.dtype)
+        self.emit("MASKBELOW", cls=T, cls_a=ta.cls, cls_out=ta.cls,
+                  k=(_bits(value, T), 0, 0, 0, 0, _bits(nd, ta.cls)))
+        return _Typed(ta.dtype, ta.nodata)
+
+    def op_step(self, n):
+        p = n.params
+        ta = self.to_acc(n.children[0])
+        T = self._scalar_compare_class(ta, p["value"])
+        flags, k1, _ = self._nd_flags(ta, None)
+        cast = lambda v: _bits(_cast_into(v, ta.dtype), ta.cls)  # noqa: E731
+        self.emit("STEP", cls=T, cls_a=ta.cls, cls_out=ta.cls, flags=flags,
+                  k=(_bits(p["value"], T), k1, cast(p["left"]), cast(p["at"]), cast(p["right"])))
+        return _Typed(ta.dtype, ta.nodata)
+
+    def op_classify(self, n):
+        bins = np.asarray(n.params["bins"])
+        out_dtype = get_uint_dtype(len(bins) + 2)
+        fill = get_dtype_max(out_dtype)
+        ta = self.to_acc(n.children[0])
+        small = ta.dtype == bool or (ta.dtype.kind in "iu" and ta.dtype.itemsize <= 2)
+        if bins.dtype.kind in "iu" and ta.dtype.kind in "iub":
+            fits = len(bins) == 0 or (bins.min() >= -2 ** 31 and bins.max() < 2 ** 31)
+            T = C_I32 if (ta.cls == C_I32 and fits) else C_I64
+            keys = bins.astype(np.int64)
+            if T == C_I32:
+                keys = keys.astype(np.int32).view(np.uint32).astype(np.uint64).view(np.int64)
+        else:
+            as32 = bins.astype(np.float32)
+            exact32 = bool(np.all(as32.astype(np.float64) == bins.astype(np.float64)))
+            if exact32 and (ta.dtype == np.float32 or small):
+                T = C_F32   # identical ordering to the float64 comparison NumPy performs
+                keys = as32.view(np.uint32).astype(np.uint64).view(np.int64)
+            else:
+                T = C_F64
+                keys = bins.astype(np.float64).view(np.int64)
+        table = dict(keys=np.ascontiguousarray(keys), vals=None, hit=None, base=0, n=len(bins), kind=0)
+        self.tables.append(table)
+        if len(self.tables) > _native.GM_MAX_TABLES:
+            raise FusionLimit("too many tables")
+        flags, k1, _ = self._nd_flags(ta, None)
+        if n.params["right"]:
+            flags |= F_RIGHT
+        self.emit("CLASSIFY", cls=T, cls_a=ta.cls, cls_out=C_I32, flags=flags, aux=len(self.tables) - 1,
+                  k=(0, k1, 0, _bits(fill, C_I32)))
+        return _Typed(out_dtype, fill)
+
+    def op_reclassify(self, n, nd_only=False):
+        p = n.params
+        dtype = np.dtype(p["dtype"])
+        fill = p["fillvalue"]
+        pairs = p["data"]
+        source = np.asarray([s for s, _ in pairs])
+        target = np.asarray([t for _, t in pairs])
+        ta = self.to_acc(n.children[0])
+        nd = ta.nodata
+        if nd is not None and not np.any(source == nd):
+            source = np.append(source, nd)
+            target = np.append(target, fill)
+        order = np.argsort(source)
+        source = source[order].astype(np.int64)
+        target = target[order].astype(dtype)
+        T = dtype_class(dtype)
+        with np.errstate(all="ignore"):
+            is_fill = target == dtype.type(fill)
+        hit = np.where(is_fill, 2, 1).astype(np.uint8)
+        vals = target.view(np.uint64)
+        span = int(source[-1] - source[0]) + 1 if len(source) else 0
+        if 0 < span <= DENSE_TABLE_LIMIT:
+            base = int(source[0])
+            dense_vals = np.zeros(span, dtype=np.uint64)
+            dense_hit = np.zeros(span, dtype=np.uint8)
+            dense_vals[source - base] = vals
+            dense_hit[source - base] = hit
+            table = dict(keys=None, vals=None if nd_only else dense_vals, hit=dense_hit, base=base,
+                         n=span, kind=1)
+        else:
+            table = dict(keys=np.ascontiguousarray(source), vals=np.ascontiguousarray(vals),
+                         hit=np.ascontiguousarray(hit), base=0, n=len(source), kind=0)
+        self.tables.append(table)
+        if len(self.tables) > _native.GM_MAX_TABLES:
+            raise FusionLimit("too many tables")
+        flags = (F_SELECT if p["select"] else 0) | (F_ND_T if nd_only else 0)
+        out_cls = C_I32 if nd_only else T
+        if not nd_only:
+            self.wide = True
+        self.emit("RECLASS", cls=C_I32 if nd_only else C_I64, cls_a=ta.cls, cls_out=out_cls, flags=flags,
+                  aux=len(self.tables) - 1, k=(0, 0, 0, _bits(fill, T) if not nd_only else 0))
+        return _Typed(bool, None) if nd_only else _Typed(dtype, fill)
+
+
+_STORE_CODE = {}
+
+
+def _build_program(compiler, n_inputs, n_outputs):
+    prog = _native.GmProgram()
+    prog.n_instr = len(compiler.instr)
+    prog.n_inputs = n_inputs
+    prog.n_outputs = n_outputs
+    prog.word = 8 if compiler.wide else 4
+    prog.n_tables = len(compiler.tables)
+    for dst, src in zip(prog.instr, compiler.instr):
+        for name in ("op", "cls", "cls_a", "cls_b", "cls_out", "src_kind", "src", "flags", "aux"):
+            setattr(dst, name, src[name])
+        for i in range(6):
+            dst.k[i] = src["k"][i]
+    for dst, t in zip(prog.tables, compiler.tables):
+        dst.keys = t["keys"].ctypes.data if t["keys"] is not None else None
+        dst.vals = t["vals"].ctypes.data if t["vals"] is not None else None
+        dst.hit = t["hit"].ctypes.data if t["hit"] is not None else None
+        dst.base, dst.n, dst.kind = t["base"], t["n"], t["kind"]
+    return prog
+
+
+def compile_expression(roots, leaf_types):
+    """Lower ``roots`` (list of Node) to a GmProgram with one output per root.
+
+    Returns (program, compiler, [result _Typed per root])."""
+    comp = _Compiler([_Typed(d, nd) for d, nd in leaf_types])
+    for r in roots:
+        comp.count_uses(r)
+    results = []
+    for i, r in enumerate(roots):
+        if isinstance(r, Leaf):
+            t = comp.to_acc(r)
+        else:
+            t = comp.to_acc(r)
+        results.append(t)
+        comp.emit("OUT", cls_a=t.cls, cls_out=t.cls, aux=i)
+    if len(leaf_types) > _native.GM_MAX_INPUTS or len(roots) > _native.GM_MAX_OUTPUTS:
+        raise FusionLimit("too many inputs/outputs")
+    # inputs whose natural class is wide force the 64-bit machine
+    if any(dtype_class(d) in _WIDE for d, _ in leaf_types):
+        comp.wide = True
+    return _build_program(comp, len(leaf_types), len(roots)), comp, results
+
+
+def run_program(prog, inputs, out_dtypes, shape, keep_on_device):
+    """Launch ``prog`` over ``inputs`` (numpy or DeviceArray); returns the outputs."""
+    lib = _native.lib()
+    n = int(np.prod(shape, dtype=np.int64))
+    in_desc = (_native.GmArray * max(len(inputs), 1))()
+    staged = []
+    any_device = keep_on_device or any(_native.is_device(a) for a in inputs)
+    for i, a in enumerate(inputs):
+        if not _native.is_device(a):
+            a = np.ascontiguousarray(a)
+            if any_device:
+                a = _native.DeviceArray.from_host(a)
+        staged.append(a)
+        in_desc[i] = _native.as_gm_array(a, (1, 1, n))
+    outputs = []
+    out_desc = (_native.GmArray * len(out_dtypes))()
+    for i, dt in enumerate(out_dtypes):
+        out = _native.DeviceArray(shape, dt) if any_device else _native.pinned_empty(shape, dt)
+        outputs.append(out)
+        out_desc[i] = _native.as_gm_array(out, (1, 1, n))
+    _native.check(lib.gm_eval_program(ctypes.byref(prog), in_desc, out_desc, n, _native.current_stream()))
+    if any_device and not keep_on_device:
+        outputs = [o.to_host() for o in outputs]
+    return outputs
+
+
+def evaluate(roots, leaves, keep_on_device=False):
+    """Evaluate expression roots over ``leaves`` = [(values, no_data_value), ...].
+
+    Returns [(values, dtype, no_data_value), ...] per root.
+    """
+    shapes = [tuple(v.shape) for v, _ in leaves]
+    shape = shapes[0]
+    arrays = [v for v, _ in leaves]
+    if any(s != shape for s in shapes):
+        shape = np.broadcast_shapes(*shapes)
+        arrays = [np.ascontiguousarray(np.broadcast_to(np.asarray(a), shape)) for a in arrays]
+    prog, comp, results = compile_expression(roots, [(v.dtype, nd) for v, nd in leaves])
+    outs = run_program(prog, arrays, [t.dtype for t in results], shape, keep_on_device)
+    del comp  # tables stay alive until the (synchronous) upload inside the call is done
+    return [(o, t.dtype, t.nodata) for o, t in zip(outs, results)]
+
+
+class CompiledProgram(object):
+    """A program compiled once and launched many times on device-resident
+    arrays (what ``bench.py`` times; no host work besides the launch)."""
+
+    def __init__(self, roots, leaf_types):
+        self.program, self._compiler, self.results = compile_expression(roots, leaf_types)
+
+    def launch(self, inputs, outputs):
+        lib = _native.lib()
+        n = inputs[0].size if inputs else outputs[0].size
+        in_desc = (_native.GmArray * max(len(inputs), 1))()
+        for i, a in enumerate(inputs):
+            in_desc[i] = _native.as_gm_array(a, (1, 1, n))
+        out_desc = (_native.GmArray * len(outputs))()
+        for i, a in enumerate(outputs):
+            out_desc[i] = _native.as_gm_array(a, (1, 1, n))
+        _native.check(lib.gm_eval_program(ctypes.byref(self.program), in_desc, out_desc, n,
+                                          _native.current_stream()))

@@ -1,0 +1,68 @@
+"""Fused chains through ``get_data`` (graph -> fusion -> one CUDA launch) against
+the oracle applied block by block; configs 1 and 2 of BASELINE.json at test
+sizes, plus the fusion bookkeeping (root key kept, one launch)."""
+import numpy as np
+import pytest
+
+from dask_geomodeling_b200 import _native, workloads
+from dask_geomodeling_b200.core import fusion
+from dask_geomodeling_b200._compat import config
+from oracle import workloads as oracle_workloads
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("size", [64, 257, 1024])
+def test_cfg1_chain(size):
+    a, b = workloads.cfg1_arrays(size)
+    view = workloads.cfg1_view(a, b)
+    before = _native.launch_count()
+    got = view.get_data(**workloads.request(size, size))
+    launches = _native.launch_count() - before
+    values, nodata = oracle_workloads.cfg1(a, b)
+    assert got["values"].dtype == values.dtype == np.uint8
+    np.testing.assert_array_equal(got["values"], values)
+    assert got["no_data_value"] == nodata
+    # two resample kernels (float sources) + ONE fused evaluator launch
+    assert launches == 3
+
+
+@pytest.mark.parametrize("size", [96, 1000])
+def test_cfg2_chain(size):
+    ints, floats = workloads.cfg2_arrays(size, chunk=256)
+    isdata, step = workloads.cfg2_views(ints, floats)
+    (e_isdata, _), (e_step, e_nodata) = oracle_workloads.cfg2(ints, floats, workloads.CFG2_PAIRS)
+    got = isdata.get_data(**workloads.request(size, size))
+    assert got["values"].dtype == np.bool_
+    np.testing.assert_array_equal(got["values"], e_isdata)
+    assert got["no_data_value"] is None
+    got = step.get_data(**workloads.request(size, size))
+    assert got["values"].dtype == np.float32
+    np.testing.assert_array_equal(got["values"], e_step)
+    assert got["no_data_value"] == e_nodata
+
+
+def test_fusion_keeps_root_key_and_matches_unfused():
+    a, b = workloads.cfg1_arrays(128)
+    view = workloads.cfg1_view(a, b)
+    req = workloads.request(128, 128)
+    graph, name = view.get_compute_graph(**req)
+    fused = fusion.optimize(graph, name)
+    assert name in fused
+    assert fused[name][0] is fusion.fused_process
+    assert len(fused) < len(graph)
+    with config.set({"geomodeling.fuse": False}):
+        unfused = view.get_data(**req)
+    np.testing.assert_array_equal(view.get_data(**req)["values"], unfused["values"])
+
+
+def test_window_requests_crop_and_pad():
+    a, b = workloads.cfg1_arrays(64)
+    view = workloads.cfg1_view(a, b)
+    full = oracle_workloads.cfg1(a, b)[0]
+    # window partly outside the source: outside cells are no data -> Mask fill (0)
+    got = view.get_data(mode="vals", bbox=(-8, 40, 24, 72), width=32, height=32,
+                        projection=workloads.PROJECTION)
+    expected = np.zeros((1, 32, 32), dtype=np.uint8)
+    expected[:, 8:, 8:] = full[:, 0:24, 0:24]
+    np.testing.assert_array_equal(got["values"], expected)
