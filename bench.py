@@ -39,12 +39,14 @@ BYTES_PER_PIXEL = 7  # int16 + float32 in, bool out
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=16384, help="raster edge in pixels")
     ap.add_argument("--cpu-sample-rows", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--profile", action="store_true",
+                    help="kernel-resident loop only (for ncu): no e2e, no CPU baseline")
     return ap.parse_args()
 
 
@@ -124,6 +126,59 @@ def _stripe(size, rows):
 # ----------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------
+
+
+class NvmlSampler(object):
+    """SM clock and throttle reasons sampled through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        import pynvml
+
+        self.nvml = pynvml
+        pynvml.nvmlInit()
+        self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.period = period
+        self.sm, self.reasons = [], set()
+        self.running = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def _loop(self):
+        n = self.nvml
+        flags = {
+            "hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+            "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+        }
+        while self.running:
+            try:
+                self.sm.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for name, bit in flags.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self.running = False
+        self.thread.join(timeout=2)
+        try:
+            sm_max = self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)
+        except Exception:
+            sm_max = None
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+
+
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
 
 
 class ClockSampler(object):
@@ -208,7 +263,11 @@ def run_b200(args):
     task = fused[name]
     assert task[0] is fusion.fused_process, "the chain did not fuse into one task"
     plan, leaf_keys = task[1], task[2:]
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the kernels, the CUDA events that time them
+    # and torch's allocator all use this one stream handle
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     with _native.use_stream(stream.cuda_stream), fusion.device_resident():
         leaf_payloads = [fused[k][0](*fused[k][1:]) for k in leaf_keys]  # H2D, once
         inputs = [p["values"] for p in leaf_payloads]
@@ -221,7 +280,7 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = make_sampler(local_rank) if rank == 0 else None
         launches_before = _native.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
@@ -239,19 +298,22 @@ def run_b200(args):
         del inputs, leaf_payloads, out
 
     # ---- end to end through the Block API: host arrays in, host array out ----------
-    with _native.use_stream(stream.cuda_stream):
-        view.get_data(**request)  # warm-up: tokens, pinning, pool
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            result = view.get_data(**request)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-    assert int(result["values"].sum()) == checksum, "e2e result differs from the resident result"
     h2d = ints.nbytes + floats.nbytes
-    d2h = result["values"].nbytes
+    d2h = pixels  # one bool per pixel
+    e2e_s = float("nan")
+    if not args.profile:
+        with _native.use_stream(stream.cuda_stream):
+            view.get_data(**request)  # warm-up: tokens, pinning, pool
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                result = view.get_data(**request)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+        assert int(result["values"].sum()) == checksum, "e2e result differs from the resident result"
+        d2h = result["values"].nbytes
 
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -287,7 +349,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if world == 1:
+        if world == 1 and not args.profile:
             threads = os.cpu_count() or 1
             rows = min(args.cpu_sample_rows, size)
             gpx, cpu_pixels, best = cpu_chain_throughput(ints, floats, rows, 3, threads)

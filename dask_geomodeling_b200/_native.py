@@ -224,9 +224,10 @@ def launch_count():
     return int(load_library().gm_launch_count())
 
 
-def _free_device(ptr):
+def _free_device(ptr, stream):
+    # stream-ordered free on the stream the block was allocated (and used) on
     if _lib is not None and ptr:
-        _lib.gm_free(ptr, None)
+        _lib.gm_free(ptr, stream)
 
 
 def _free_pinned(ptr):
@@ -248,9 +249,10 @@ class DeviceArray:
         self._owner = owner  # keeps foreign memory (e.g. a torch tensor) alive
         if ptr is None:
             p = ctypes.c_void_p()
-            check(lib().gm_malloc(ctypes.byref(p), self.nbytes, current_stream()))
+            stream = current_stream()
+            check(lib().gm_malloc(ctypes.byref(p), self.nbytes, stream))
             self.ptr = p.value
-            self._finalizer = weakref.finalize(self, _free_device, self.ptr)
+            self._finalizer = weakref.finalize(self, _free_device, self.ptr, stream)
         else:
             self.ptr = int(ptr)
             self._finalizer = None
@@ -290,18 +292,46 @@ class DeviceArray:
         return "DeviceArray(shape={}, dtype={})".format(self.shape, self.dtype)
 
 
+_pinned_free = {}          # nbytes -> [ptr, ...] page-locked blocks ready for reuse
+_pinned_cached_bytes = 0
+PINNED_CACHE_LIMIT = int(os.environ.get("GM_PINNED_CACHE_BYTES", 8 << 30))
+
+
+def _recycle_pinned(ptr, nbytes):
+    """Finalizer of a pinned result array: keep the block for the next result of
+    the same size (cudaHostAlloc costs ~0.1 s/GB), free it beyond the cache limit."""
+    global _pinned_cached_bytes
+    if _lib is None or not ptr:
+        return
+    with _lib_lock:
+        if _pinned_cached_bytes + nbytes <= PINNED_CACHE_LIMIT:
+            _pinned_free.setdefault(nbytes, []).append(ptr)
+            _pinned_cached_bytes += nbytes
+            return
+    _lib.gm_host_free(ptr)
+
+
 def pinned_empty(shape, dtype):
-    """numpy array backed by page-locked host memory (freed with the array)."""
+    """numpy array backed by page-locked host memory (recycled with the array)."""
+    global _pinned_cached_bytes
     dtype = np.dtype(dtype)
     shape = tuple(int(s) for s in shape)
     nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
     if nbytes == 0:
         return np.empty(shape, dtype)
-    p = ctypes.c_void_p()
-    check(lib().gm_host_alloc(ctypes.byref(p), nbytes))
-    buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+    ptr = None
+    with _lib_lock:
+        blocks = _pinned_free.get(nbytes)
+        if blocks:
+            ptr = blocks.pop()
+            _pinned_cached_bytes -= nbytes
+    if ptr is None:
+        p = ctypes.c_void_p()
+        check(lib().gm_host_alloc(ctypes.byref(p), nbytes))
+        ptr = p.value
+    buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    weakref.finalize(buf, _free_pinned, p.value)
+    weakref.finalize(buf, _recycle_pinned, ptr, nbytes)
     return arr
 
 

@@ -1,0 +1,310 @@
+// Temporal reductions and scans over the band axis
+// (raster/temporal.py:722-768 TemporalAggregate, :959-1005 Cumulative).
+//
+// One thread per pixel; consecutive threads own consecutive x so every frame is
+// read with fully coalesced accesses and the whole (T, H, W) stack is streamed
+// exactly once.  Accumulation is sequential in t in the reference's working
+// dtype (float32 or float64 = result_type(float32, out dtype)), which is what
+// NumPy's axis-0 reductions do, so sums are bit-identical.
+#include "gm_common.cuh"
+#include <cfloat>
+#include <limits>
+
+namespace gm {
+
+constexpr int TMP_MAX_SORT = 1024;  // frames per bin for median / percentile
+
+template <typename W> __device__ __forceinline__ W nan_();
+template <> __device__ __forceinline__ float nan_<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double nan_<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+template <typename D> struct DMax { static __host__ __device__ D value() { return std::numeric_limits<D>::max(); } };
+
+template <typename W, typename D> __device__ __forceinline__ D cast_out(W v) { return (D)v; }
+
+// np.nanpercentile(method="linear") on a sorted sample
+template <typename W>
+__device__ __forceinline__ W lerp_percentile(const W* sorted, int n, double q) {
+  const double virt = (q / 100.0) * (double)(n - 1);
+  int lo = (int)floor(virt);
+  if (lo < 0) lo = 0;
+  if (lo > n - 1) lo = n - 1;
+  const int hi = lo + 1 < n ? lo + 1 : n - 1;
+  const W t = (W)(virt - (double)lo);
+  const W a = sorted[lo], b = sorted[hi];
+  const W diff = b - a;
+  W r = a + diff * t;
+  if (t >= (W)0.5) r = b - diff * ((W)1 - t);
+  return r;
+}
+
+template <typename S, typename W, typename D>
+__global__ void __launch_bounds__(256)
+temporal_aggregate_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                          int stat, double q, const int* __restrict__ bin_offsets,
+                          const int* __restrict__ frame_index, int n_bins, int64_t plane,
+                          W* __restrict__ scratch) {
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pix >= plane) return;
+  const bool extensive = stat == GM_STAT_SUM || stat == GM_STAT_COUNT;
+  const D fill = extensive ? (D)0 : DMax<D>::value();
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
+    D out = fill;
+    if (f1 > f0) {
+      W result = nan_<W>();
+      if (stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE) {
+        // gather the valid samples of this pixel (column of the scratch matrix), sort, pick
+        W* col = scratch + pix;
+        int n = 0;
+        for (int f = f0; f < f1; ++f) {
+          const S v = src[(int64_t)frame_index[f] * plane + pix];
+          if (has_nodata && v == nodata) continue;
+          const W w = (W)v;
+          if (w != w) continue;
+          int j = n++;
+          while (j > 0 && col[(int64_t)(j - 1) * plane] > w) {
+            col[(int64_t)j * plane] = col[(int64_t)(j - 1) * plane];
+            --j;
+          }
+          col[(int64_t)j * plane] = w;
+        }
+        if (n > 0) {
+          if (stat == GM_STAT_MEDIAN) {
+            const W a = col[(int64_t)((n - 1) / 2) * plane], b = col[(int64_t)(n / 2) * plane];
+            result = (n & 1) ? a : (a + b) / (W)2;
+          } else {
+            // strided column -> tiny local copy of the two neighbours via the same formula
+            const double virt = (q / 100.0) * (double)(n - 1);
+            int lo = (int)floor(virt);
+            if (lo < 0) lo = 0;
+            if (lo > n - 1) lo = n - 1;
+            const int hi = lo + 1 < n ? lo + 1 : n - 1;
+            W pair[2] = {col[(int64_t)lo * plane], col[(int64_t)hi * plane]};
+            const W t = (W)(virt - (double)lo);
+            const W diff = pair[1] - pair[0];
+            result = pair[0] + diff * t;
+            if (t >= (W)0.5) result = pair[1] - diff * ((W)1 - t);
+          }
+        }
+      } else {
+        W acc = (W)0;
+        W lo = nan_<W>(), hi = nan_<W>();
+        int64_t cnt = 0;
+#pragma unroll 4
+        for (int f = f0; f < f1; ++f) {
+          const S v = __ldcs(src + (int64_t)frame_index[f] * plane + pix);
+          const W w = (W)v;
+          const bool valid = !(has_nodata && v == nodata) && (w == w);
+          if (valid) {
+            acc += w;
+            ++cnt;
+            lo = (lo != lo || w < lo) ? w : lo;
+            hi = (hi != hi || w > hi) ? w : hi;
+          }
+        }
+        switch (stat) {
+          case GM_STAT_SUM: result = acc; break;
+          case GM_STAT_COUNT: result = (W)cnt; break;
+          case GM_STAT_MIN: result = lo; break;
+          case GM_STAT_MAX: result = hi; break;
+          case GM_STAT_MEAN: result = (W)((double)acc / (double)cnt); break;
+          default: {  // STD / VAR: second pass over the deviations (np.nanvar)
+            const W avg = (W)((double)acc / (double)cnt);
+            W ss = (W)0;
+            for (int f = f0; f < f1; ++f) {
+              const S v = src[(int64_t)frame_index[f] * plane + pix];
+              const W w = (W)v;
+              const bool valid = !(has_nodata && v == nodata) && (w == w);
+              if (valid) { const W d = w - avg; ss += d * d; }
+            }
+            W var = cnt > 0 ? (W)((double)ss / (double)cnt) : nan_<W>();
+            result = stat == GM_STAT_VAR ? var : (W)sqrt((double)var);
+            if (stat == GM_STAT_STD) result = sizeof(W) == 4 ? (W)sqrtf((float)var) : (W)sqrt((double)var);
+            break;
+          }
+        }
+      }
+      const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+      out = finite ? cast_out<W, D>(result) : fill;
+    }
+    dst[(int64_t)g * plane + pix] = out;
+  }
+}
+
+template <typename S, typename W, typename D>
+__global__ void __launch_bounds__(256)
+temporal_cumulative_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                           int stat, const int* __restrict__ bin_offsets,
+                           const int* __restrict__ frame_index, const int* __restrict__ out_frame,
+                           int n_bins, int64_t plane) {
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pix >= plane) return;
+  for (int g = 0; g < n_bins; ++g) {
+    W acc = (W)0;
+    int64_t cnt = 0;
+    for (int f = bin_offsets[g]; f < bin_offsets[g + 1]; ++f) {
+      const S v = __ldcs(src + (int64_t)frame_index[f] * plane + pix);
+      const W w = (W)v;
+      const bool valid = !(has_nodata && v == nodata) && (w == w);
+      if (valid) { acc += w; ++cnt; }
+      const int o = out_frame[f];
+      if (o >= 0) {
+        D out;
+        if (stat == GM_STAT_COUNT) out = (D)cnt;
+        else {
+          const bool finite = (acc == acc) && (fabs((double)acc) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+          out = finite ? cast_out<W, D>(acc) : (D)0;
+        }
+        dst[(int64_t)o * plane + pix] = out;
+      }
+    }
+  }
+}
+
+struct TemporalArgs {
+  const void* nodata; int has_nodata; int stat; double q;
+  const int* bins; const int* frames; const int* out_frame; int n_bins; int64_t plane;
+  void* scratch;
+};
+
+template <typename S, typename W, typename D>
+static int launch_aggregate(const Staged& in, Staged& out, const TemporalArgs& a, cudaStream_t s) {
+  S nd = S(0);
+  if (a.has_nodata) memcpy(&nd, a.nodata, sizeof(S));
+  const int64_t blocks = (a.plane + 255) / 256;
+  temporal_aggregate_kernel<S, W, D><<<(unsigned)blocks, 256, 0, s>>>(
+      (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.q, a.bins, a.frames, a.n_bins,
+      a.plane, (W*)a.scratch);
+  GM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename S, typename W, typename D>
+static int launch_cumulative(const Staged& in, Staged& out, const TemporalArgs& a, cudaStream_t s) {
+  S nd = S(0);
+  if (a.has_nodata) memcpy(&nd, a.nodata, sizeof(S));
+  const int64_t blocks = (a.plane + 255) / 256;
+  temporal_cumulative_kernel<S, W, D><<<(unsigned)blocks, 256, 0, s>>>(
+      (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.bins, a.frames, a.out_frame,
+      a.n_bins, a.plane);
+  GM_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool work_is_double(int out_dtype) {
+  // np.result_type(np.float32, out dtype)
+  return out_dtype == GM_F64 || out_dtype == GM_I32 || out_dtype == GM_U32 || out_dtype == GM_I64;
+}
+
+template <typename S, bool CUMULATIVE>
+static int dispatch_out(int out_dtype, const Staged& in, Staged& out, const TemporalArgs& a, cudaStream_t s) {
+#define GM_GO(W, D) (CUMULATIVE ? launch_cumulative<S, W, D>(in, out, a, s) : launch_aggregate<S, W, D>(in, out, a, s))
+  switch (out_dtype) {
+    case GM_U8: case GM_BOOL: return GM_GO(float, uint8_t);
+    case GM_I8: return GM_GO(float, int8_t);
+    case GM_U16: return GM_GO(float, uint16_t);
+    case GM_I16: return GM_GO(float, int16_t);
+    case GM_F32: return GM_GO(float, float);
+    case GM_U32: return GM_GO(double, uint32_t);
+    case GM_I32: return GM_GO(double, int32_t);
+    case GM_I64: return GM_GO(double, int64_t);
+    case GM_F64: return GM_GO(double, double);
+  }
+#undef GM_GO
+  return fail("temporal: unsupported output dtype");
+}
+
+template <bool CUMULATIVE>
+static int dispatch_src(int src_dtype, int out_dtype, const Staged& in, Staged& out,
+                        const TemporalArgs& a, cudaStream_t s) {
+  switch (src_dtype) {
+    case GM_U8: case GM_BOOL: return dispatch_out<uint8_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_I8: return dispatch_out<int8_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_U16: return dispatch_out<uint16_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_I16: return dispatch_out<int16_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_U32: return dispatch_out<uint32_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_I32: return dispatch_out<int32_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_I64: return dispatch_out<int64_t, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_F32: return dispatch_out<float, CUMULATIVE>(out_dtype, in, out, a, s);
+    case GM_F64: return dispatch_out<double, CUMULATIVE>(out_dtype, in, out, a, s);
+  }
+  return fail("temporal: unsupported source dtype");
+}
+
+template <bool CUMULATIVE>
+static int run_temporal(const GmArray* src, GmArray* dst, const void* nodata, int has_nodata,
+                        int stat, double q, const int32_t* bin_offsets, const int32_t* frame_index,
+                        const int32_t* out_frame, int n_bins, void* stream) {
+  if (ensure_init()) return 1;
+  if (!src || !dst || !bin_offsets || (n_bins > 0 && !frame_index)) return fail("temporal: null argument");
+  if (src->shape[1] != dst->shape[1] || src->shape[2] != dst->shape[2])
+    return fail("temporal: spatial shapes differ");
+  cudaStream_t s = resolve_stream(stream);
+  const int n_frames = bin_offsets[n_bins];
+  int longest = 0;
+  for (int g = 0; g < n_bins; ++g) {
+    const int len = bin_offsets[g + 1] - bin_offsets[g];
+    if (len > longest) longest = len;
+  }
+  for (int i = 0; i < n_frames; ++i)
+    if (frame_index[i] < 0 || frame_index[i] >= src->shape[0]) return fail("temporal: frame index out of range");
+  if (!CUMULATIVE && dst->shape[0] != n_bins) return fail("temporal: one output frame per bin expected");
+  const bool needs_sort = !CUMULATIVE && (stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE);
+  if (needs_sort && longest > TMP_MAX_SORT) return fail("temporal: more than 1024 frames per bin for median/percentile");
+
+  TemporalArgs a;
+  a.nodata = nodata; a.has_nodata = has_nodata; a.stat = stat; a.q = q; a.n_bins = n_bins;
+  a.plane = src->shape[1] * src->shape[2];
+  a.scratch = nullptr; a.out_frame = nullptr;
+  Staged in, out;
+  void *dbins = nullptr, *dframes = nullptr, *dout = nullptr;
+  int rc = in.open_input(*src, s);
+  if (!rc) rc = out.open_output(*dst, s);
+  if (!rc) rc = upload(&dbins, bin_offsets, sizeof(int32_t) * (n_bins + 1), s);
+  if (!rc) rc = upload(&dframes, frame_index, sizeof(int32_t) * (n_frames > 0 ? n_frames : 1), s);
+  if (!rc && CUMULATIVE) rc = upload(&dout, out_frame, sizeof(int32_t) * (n_frames > 0 ? n_frames : 1), s);
+  if (!rc && needs_sort) {
+    const size_t w = work_is_double(dst->dtype) ? 8 : 4;
+    cudaError_t e = cudaMallocAsync(&a.scratch, w * (size_t)longest * (size_t)a.plane, s);
+    if (e != cudaSuccess) rc = fail(std::string("temporal scratch: ") + cudaGetErrorString(e));
+  }
+  a.bins = (const int*)dbins; a.frames = (const int*)dframes; a.out_frame = (const int*)dout;
+  if (!rc && a.plane > 0 && array_count(*dst) > 0) {
+    if (CUMULATIVE) {
+      // frames that belong to no bin keep the (extensive) fill 0
+      cudaError_t e = cudaMemsetAsync(out.dev, 0, out.bytes, s);
+      if (e != cudaSuccess) rc = fail("temporal: memset failed");
+    }
+    if (!rc) rc = dispatch_src<CUMULATIVE>(src->dtype, dst->dtype, in, out, a, s);
+  }
+  if (!rc) rc = out.finish_output();
+  const bool sync = out.owned;
+  in.release(); out.release();
+  if (dbins) cudaFreeAsync(dbins, s);
+  if (dframes) cudaFreeAsync(dframes, s);
+  if (dout) cudaFreeAsync(dout, s);
+  if (a.scratch) cudaFreeAsync(a.scratch, s);
+  if (!rc && sync) GM_CUDA(cudaStreamSynchronize(s));
+  return rc;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_temporal_aggregate(const GmArray* src, GmArray* dst, const void* nodata,
+                                     int has_nodata, int stat, double q, const int32_t* bin_offsets,
+                                     const int32_t* frame_index, int n_bins, void* stream) {
+  return run_temporal<false>(src, dst, nodata, has_nodata, stat, q, bin_offsets, frame_index,
+                             nullptr, n_bins, stream);
+}
+
+extern "C" int gm_temporal_cumulative(const GmArray* src, GmArray* dst, const void* nodata,
+                                      int has_nodata, int stat, const int32_t* bin_offsets,
+                                      const int32_t* frame_index, const int32_t* out_frame,
+                                      int n_bins, void* stream) {
+  if (!out_frame) return fail("gm_temporal_cumulative: null out_frame");
+  return run_temporal<true>(src, dst, nodata, has_nodata, stat, 0.0, bin_offsets, frame_index,
+                            out_frame, n_bins, stream);
+}

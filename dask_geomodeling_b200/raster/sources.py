@@ -88,7 +88,6 @@ def resample_window(array, bands, geo_transform, no_data_value, bbox, height, wi
             _native.check(lib.gm_resample_nn(
                 ctypes.byref(src_desc), ctypes.byref(dst_desc), nodata_ptr,
                 col0 - c_lo, col_step, row0 - r_lo, row_step, stream))
-        _native.synchronize()  # the host window may be pageable: finish before returning
     return out if keep_on_device else out.to_host()
 
 

@@ -1,0 +1,268 @@
+"""Spatial stencil blocks: Dilate, MovingMax, Smooth, HillShade.
+
+Drop-in for the stencil part of the reference's raster/spatial.py (``Place`` is
+outside the hot path).  Each block enlarges the request by its halo exactly as
+the reference does -- the halo is obtained by asking the source for a larger
+bbox, not by neighbour communication (raster/spatial.py:27-108) -- and the
+stencil itself runs in CUDA (csrc/gm_stencil.cu).
+"""
+import ctypes
+
+import numpy as np
+
+from .. import _native, _state, utils
+from .base import BaseSingle
+
+__all__ = ["Dilate", "Smooth", "MovingMax", "HillShade"]
+
+
+def expand_request_pixels(request, radius=1):
+    """Request enlarged by ``radius`` pixels on every side; None for non-'vals'
+    and point requests.
+
+    The bbox mixes the x and y amounts exactly as the reference does
+    (raster/spatial.py:44); identical for square pixels."""
+    if request["mode"] != "vals":
+        return None
+    width, height = request["width"], request["height"]
+    x1, y1, x2, y2 = request["bbox"]
+    span_x, span_y = x2 - x1, y2 - y1
+    if span_x == 0 or span_y == 0:
+        return None
+    amount_x = span_x / width * radius
+    amount_y = span_y / height * radius
+    enlarged = request.copy()
+    enlarged["bbox"] = (x1 - amount_x, y1 - amount_x, x2 + amount_y, y2 + amount_y)
+    enlarged["width"] = width + 2 * radius
+    enlarged["height"] = height + 2 * radius
+    return enlarged
+
+
+def expand_request_meters(request, radius_m=1):
+    """Request enlarged by ``radius_m`` metres rounded to whole pixels.
+
+    Returns (new request, radius in pixels as (y, x) floats)
+    (raster/spatial.py:50-108).  Geographic projections would need a detour via
+    EPSG:3857, i.e. a coordinate transformation, and are not supported here."""
+    if utils.is_geographic(request["projection"]):
+        raise NotImplementedError("Smooth on a geographic projection needs pyproj/GDAL")
+    x1, y1, x2, y2 = request["bbox"]
+    span_y, span_x = y2 - y1, x2 - x1
+    if span_y > 0 and span_x > 0:
+        per_m = request["height"] / span_y, request["width"] / span_x
+        radius_px = [radius_m * r for r in per_m]
+        margins_px = [int(round(r)) for r in radius_px]
+        margins_m = [m / r for m, r in zip(margins_px, per_m)]
+    else:
+        radius_px = margins_px = [Smooth.MARGIN_THRESHOLD] * 2
+        margins_m = [radius_m] * 2
+    enlarged = request.copy()
+    enlarged["bbox"] = (x1 - margins_m[1], y1 - margins_m[0], x2 + margins_m[1], y2 + margins_m[0])
+    enlarged["height"] = request["height"] + 2 * margins_px[0]
+    enlarged["width"] = request["width"] + 2 * margins_px[1]
+    return enlarged, radius_px
+
+
+def _call_stencil(values, out_shape, out_dtype, launch):
+    """Allocate the output next to the input (device stays device, host stays
+    host unless a graph is being computed) and run ``launch(src, dst, stream)``."""
+    lib = _native.lib()
+    on_device = _native.is_device(values) or _state.keep_on_device()
+    if on_device and not _native.is_device(values):
+        values = _native.DeviceArray.from_host(values)
+    if not on_device:
+        values = np.ascontiguousarray(values)
+    out = (_native.DeviceArray(out_shape, out_dtype) if on_device
+           else _native.pinned_empty(out_shape, out_dtype))
+    src, dst = _native.as_gm_array(values), _native.as_gm_array(out)
+    _native.check(launch(lib, ctypes.byref(src), ctypes.byref(dst), _native.current_stream()))
+    if on_device and not _state.keep_on_device():
+        out = out.to_host()
+    return out
+
+
+def _nodata_arg(values, no_data_value):
+    """(holder, pointer, has_nodata) for ``values == no_data_value`` in the array dtype."""
+    from ._program import sentinel
+
+    s = sentinel(values.dtype, no_data_value)
+    holder, ptr = _native.scalar_ptr(0 if s is None else s, values.dtype)
+    return holder, ptr, int(s is not None)
+
+
+class Dilate(BaseSingle):
+    """Grow cells holding one of ``values`` by one cell (6-connected in t, y, x),
+    later values on top (reference: raster/spatial.py:111-155)."""
+
+    def __init__(self, store, values):
+        values = np.asarray(values, dtype=store.dtype)
+        super().__init__(store, values.tolist())
+
+    values = property(lambda self: self.args[1])
+
+    def get_sources_and_requests(self, **request):
+        enlarged = expand_request_pixels(request, radius=1)
+        if enlarged is None:
+            return [(self.store, request)]
+        return [(self.store, enlarged), (self.values, None)]
+
+    @staticmethod
+    def process(data, values=None):
+        if data is None or values is None or "values" not in data:
+            return data
+        source = data["values"]
+        wanted = np.ascontiguousarray(np.asarray(values, dtype=source.dtype)).reshape(-1)
+        t, h, w = source.shape
+        out = _call_stencil(
+            source, (t, h - 2, w - 2), source.dtype,
+            lambda lib, src, dst, stream: lib.gm_dilate(src, dst, wanted.ctypes.data, len(wanted), stream),
+        )
+        return {"values": out, "no_data_value": data["no_data_value"]}
+
+
+class MovingMax(BaseSingle):
+    """Maximum over a disc of (odd) diameter ``size``
+    (reference: raster/spatial.py:158-213)."""
+
+    def __init__(self, store, size):
+        size = int(2 * round((size - 1) / 2) + 1)  # nearest odd integer
+        if size < 3:
+            raise ValueError("The size should be odd and larger than 1")
+        super(MovingMax, self).__init__(store, size)
+
+    size = property(lambda self: self.args[1])
+
+    def get_sources_and_requests(self, **request):
+        enlarged = expand_request_pixels(request, radius=int(self.size // 2))
+        if enlarged is None:
+            return [(self.store, request)]
+        return [(self.store, enlarged), (self.size, None)]
+
+    @staticmethod
+    def process(data, size=None):
+        if data is None or size is None or "values" not in data:
+            return data
+        source = data["values"]
+        radius = int(size // 2)
+        t, h, w = source.shape
+        holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
+        out = _call_stencil(
+            source, (t, h - 2 * radius, w - 2 * radius), source.dtype,
+            lambda lib, src, dst, stream: lib.gm_moving_max(src, dst, nodata_ptr, has_nodata,
+                                                            int(size), stream),
+        )
+        return {"values": out, "no_data_value": data["no_data_value"]}
+
+
+def _gaussian_weights(sigma):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius) with
+    radius = int(4 * sigma + 0.5); (weights, radius).  sigma <= 1e-15: axis skipped."""
+    if sigma <= 1e-15:
+        return np.ones(1, dtype=np.float64), 0
+    radius = int(4.0 * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    return np.ascontiguousarray(phi / phi.sum()), radius
+
+
+class Smooth(BaseSingle):
+    """Gaussian smoothing with sigma = size / 3 (in projection units)
+    (reference: raster/spatial.py:216-307)."""
+
+    MARGIN_THRESHOLD = 6
+
+    def __init__(self, store, size, fill=0):
+        for x in (size, fill):
+            if not isinstance(x, (int, float)):
+                raise TypeError("'{}' object is not allowed".format(type(x)))
+        super(Smooth, self).__init__(store, size, fill)
+
+    size = property(lambda self: self.args[1])
+    fill = property(lambda self: self.args[2])
+
+    def get_sources_and_requests(self, **request):
+        if request["mode"] != "vals":
+            return [(self.store, request)]
+        enlarged, size_px = expand_request_meters(request, self.size)
+        if any(s > self.MARGIN_THRESHOLD for s in size_px):
+            # large kernels: smooth a coarser grid over the enlarged extent, zoom back
+            mode = "zoom"
+            zoom = [enlarged[k] / request[k] for k in ("height", "width")]
+            size_px = [s / z for s, z in zip(size_px, zoom)]
+            enlarged["height"], enlarged["width"] = request["height"], request["width"]
+        else:
+            mode = "exact"
+        return [(self.store, enlarged), (dict(smooth_mode=mode, fill=self.fill, size=size_px), None)]
+
+    @staticmethod
+    def process(data, process_kwargs=None):
+        if data is None or process_kwargs is None:
+            return data
+        mode = process_kwargs["smooth_mode"]
+        size_px = process_kwargs["size"]
+        fill = process_kwargs["fill"]
+        source = data["values"]
+        t, ny, nx = source.shape
+        wy, ly = _gaussian_weights(size_px[0] / 3)
+        wx, lx = _gaussian_weights(size_px[1] / 3)
+        holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
+        if mode == "exact":
+            my, mx = [int(round(s)) for s in size_px]
+            out_shape = (t, ny - 2 * my, nx - 2 * mx)
+            zoom, zy, zx, oy, ox = 0, 1.0, 1.0, 0.0, 0.0
+        else:
+            my = mx = 0
+            out_shape = (t, ny, nx)
+            zoom, zy, zx = 1, 1 - 2 * size_px[0] / ny, 1 - 2 * size_px[1] / nx
+            oy, ox = float(size_px[0]), float(size_px[1])
+        out = _call_stencil(
+            source, out_shape, source.dtype,
+            lambda lib, src, dst, stream: lib.gm_smooth(
+                src, dst, nodata_ptr, has_nodata, float(fill), wy.ctypes.data, ly, wx.ctypes.data, lx,
+                my, mx, zoom, zy, zx, oy, ox, stream),
+        )
+        return {"values": out, "no_data_value": data["no_data_value"]}
+
+
+class HillShade(BaseSingle):
+    """Hillshade (Horn) of an elevation raster, uint8 output
+    (reference: raster/spatial.py:310-438)."""
+
+    def __init__(self, store, altitude=45, azimuth=315, fill=0):
+        for x in (altitude, azimuth, fill):
+            if not isinstance(x, (int, float)):
+                raise TypeError("'{}' object is not allowed".format(type(x)))
+        super(HillShade, self).__init__(store, float(altitude), float(azimuth), fill)
+
+    altitude = property(lambda self: self.args[1])
+    azimuth = property(lambda self: self.args[2])
+    fill = property(lambda self: self.args[3])
+    dtype = np.dtype("u1")
+    fillvalue = 256  # on purpose not representable in uint8: the result has no 'no data'
+
+    def get_sources_and_requests(self, **request):
+        enlarged = expand_request_pixels(request, radius=1)
+        if enlarged is None:
+            return [(self.store, request)]
+        x1, y1, x2, y2 = request["bbox"]
+        resolution = ((x2 - x1) / request["width"], (y2 - y1) / request["height"])
+        kwargs = dict(resolution=resolution, altitude=self.altitude, azimuth=self.azimuth,
+                      fill=self.fill)
+        return [(self.store, enlarged), (kwargs, None)]
+
+    @staticmethod
+    def process(data, process_kwargs=None):
+        if process_kwargs is None:
+            return data
+        source = data["values"]
+        t, h, w = source.shape
+        xres, yres = process_kwargs["resolution"]
+        holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
+        out = _call_stencil(
+            source, (t, h - 2, w - 2), np.uint8,
+            lambda lib, src, dst, stream: lib.gm_hillshade(
+                src, dst, nodata_ptr, has_nodata, float(process_kwargs["fill"]), float(xres),
+                float(yres), float(process_kwargs["altitude"]), float(process_kwargs["azimuth"]),
+                stream),
+        )
+        return {"values": out, "no_data_value": 256}

@@ -1,0 +1,96 @@
+"""Stencil kernels (Dilate, MovingMax, Smooth, HillShade) against the oracle, which
+calls the same scipy.ndimage routines the reference calls."""
+import numpy as np
+import pytest
+
+from dask_geomodeling_b200 import raster, workloads
+from oracle import raster as R
+
+pytestmark = pytest.mark.gpu
+
+
+def dem(shape, seed=0, dtype="f4", nodata_fraction=0.02):
+    rng = np.random.default_rng(seed)
+    t, h, w = shape
+    y, x = np.mgrid[0:h, 0:w]
+    base = 50 * np.sin(x / 17.0) + 30 * np.cos(y / 11.0) + 0.05 * x + rng.normal(0, 1, (t, h, w))
+    values = (base + 100).astype(dtype)
+    nodata = R.dtype_max(dtype)
+    values[rng.random(shape) < nodata_fraction] = nodata
+    return values, nodata
+
+
+@pytest.mark.parametrize("dtype", ["u1", "i2", "i4", "f4"])
+@pytest.mark.parametrize("shape", [(1, 21, 34), (3, 40, 67)])
+def test_dilate(dtype, shape):
+    rng = np.random.default_rng(1)
+    values = rng.integers(0, 6, shape).astype(dtype)
+    nodata = R.dtype_max(dtype)
+    wanted = [3, 1, 5]
+    expected, _ = R.dilate(values, nodata, wanted)
+    got = raster.Dilate.process({"values": values, "no_data_value": nodata}, wanted)
+    assert got["values"].dtype == expected.dtype
+    np.testing.assert_array_equal(got["values"], expected)
+    assert got["no_data_value"] == nodata
+
+
+@pytest.mark.parametrize("dtype", ["u1", "i2", "i4", "f4", "f8"])
+@pytest.mark.parametrize("size", [3, 5, 11])
+def test_moving_max(dtype, size):
+    values, nodata = dem((2, 60, 83), 2, dtype=dtype, nodata_fraction=0.3)
+    values[0, 20:40, 30:60] = nodata  # a hole larger than the footprint stays no data
+    expected, _ = R.moving_max(values, nodata, size)
+    got = raster.MovingMax.process({"values": values, "no_data_value": nodata}, size)
+    assert got["values"].dtype == expected.dtype
+    np.testing.assert_array_equal(got["values"], expected)
+
+
+@pytest.mark.parametrize("dtype", ["f4", "f8", "i2"])
+@pytest.mark.parametrize("size_px", [(5.0, 5.0), (2.0, 3.4), (6.0, 1.0)])
+def test_smooth_exact(dtype, size_px):
+    values, nodata = dem((2, 70, 90), 3, dtype=dtype)
+    kwargs = dict(smooth_mode="exact", fill=0, size=list(size_px))
+    expected, _ = R.smooth(values, nodata, size_px, 0, "exact")
+    got = raster.Smooth.process({"values": values, "no_data_value": nodata}, kwargs)
+    assert got["values"].dtype == expected.dtype and got["values"].shape == expected.shape
+    # fp64 accumulation in scipy's tap order: expected to be bit-exact
+    np.testing.assert_array_equal(got["values"], expected)
+
+
+@pytest.mark.parametrize("fill", [0, 7.5])
+def test_smooth_zoom(fill):
+    values, nodata = dem((1, 64, 80), 4)
+    size_px = [3.7, 4.2]
+    kwargs = dict(smooth_mode="zoom", fill=fill, size=size_px)
+    expected, _ = R.smooth(values, nodata, size_px, fill, "zoom")
+    got = raster.Smooth.process({"values": values, "no_data_value": nodata}, kwargs)
+    np.testing.assert_array_equal(got["values"], expected)
+
+
+@pytest.mark.parametrize("dtype", ["f4", "f8", "i2"])
+@pytest.mark.parametrize("angles", [(45.0, 315.0), (30.0, 100.0)])
+def test_hillshade(dtype, angles):
+    values, nodata = dem((2, 80, 101), 5, dtype=dtype)
+    kwargs = dict(resolution=(0.5, 0.5), altitude=angles[0], azimuth=angles[1], fill=0)
+    expected, expected_nodata = R.hillshade(values, nodata, kwargs["resolution"], *angles, 0)
+    got = raster.HillShade.process({"values": values, "no_data_value": nodata}, kwargs)
+    assert got["values"].dtype == np.uint8 and got["values"].shape == expected.shape
+    assert got["no_data_value"] == expected_nodata == 256
+    # stated tolerance: |delta| <= 1 grey level on at most 0.1 % of the cells
+    # (float32 atan2/sin/sqrt differ in the last ulp between libm and CUDA)
+    delta = np.abs(got["values"].astype(int) - expected.astype(int))
+    assert delta.max() <= 1
+    assert (delta > 0).mean() <= 1e-3
+
+
+def test_blocks_through_get_data():
+    a, _ = workloads.cfg1_arrays(96)
+    src = workloads.source(a, workloads.F32_MAX)
+    req = workloads.request(64, 64)
+    req["bbox"] = (16, 16, 80, 80)
+    for view, oracle in [
+        (raster.MovingMax(src, 5), lambda v: R.moving_max(v[:, 14:82, 14:82], workloads.F32_MAX, 5)[0]),
+        (raster.Smooth(src, 2.0), lambda v: R.smooth(v[:, 14:82, 14:82], workloads.F32_MAX, (2.0, 2.0), 0, "exact")[0]),
+    ]:
+        got = view.get_data(**req)
+        np.testing.assert_array_equal(got["values"], oracle(a))
