@@ -76,7 +76,8 @@ def build(force=False, verbose=False):
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as pool:
             list(pool.map(run, jobs))
-    if jobs or not os.path.exists(LIB):
+    stale_lib = not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
+    if jobs or stale_lib or force:
         link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
                 "-Xcompiler", "-fPIC", "-o", LIB] + objs
         run(link)

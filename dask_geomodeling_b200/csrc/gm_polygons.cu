@@ -1,0 +1,888 @@
+// Polygon scanline rasteriser and zonal statistics.
+//
+//   gm_rasterize_polygons  utils.rasterize_geoseries (utils.py:638-756), i.e. GDAL's
+//                          GDALRasterizeLayers without ALL_TOUCHED
+//   gm_zonal_stats         geometry/aggregate.py:113-203 (aggregate_polygons) with
+//                          scipy.ndimage sum/mean/minimum/maximum/median and
+//                          measurements.percentile (measurements.py:18-137)
+//
+// The fill rule restates GDAL's alg/llrasterize.cpp::GDALdllImageFilledPolygon
+// (see oracle/polyfill.c for the CPU restatement it is tested against): vertices in
+// pixel space through the inverse geotransform, scanline at y + 0.5, crossing
+// x = floor(intersect + 0.5), even-odd pairs over all rings of a feature.
+//
+// One thread block owns one polygon; its warps take scanlines round-robin.  A warp
+// finds the crossings of its scanline with a ballot-compacted edge loop, sorts them
+// in shared memory and then walks the spans cooperatively, so that raster reads are
+// coalesced 128-byte segments.  Zonal statistics read the raster directly under the
+// spans -- no label raster is ever materialised -- and order statistics are selected
+// by an MSD radix select over the polygon's values held in shared memory (global
+// scratch for polygons that do not fit).
+#include "gm_common.cuh"
+#include <cfloat>
+#include <limits>
+#include <type_traits>
+
+namespace gm {
+
+constexpr int PG_THREADS = 128;               // 4 warps per polygon
+constexpr int PG_WARPS = PG_THREADS / 32;
+constexpr int PG_MAX_CROSSINGS = 4096;        // per scanline
+constexpr int PG_MAX_HSPANS = 8;
+constexpr int SEL_THREADS = 256;
+
+struct PolyDev {
+  const double* px;             // pixel-space x of every vertex
+  const double* py;
+  const int64_t* ring_offsets;
+  const int64_t* poly_offsets;
+  const int* miny;              // per polygon, clamped to the raster and the stripe
+  const int* maxy;              // inclusive
+  int64_t n_polygons;
+  int height, width;
+  int cap;                      // crossing capacity per warp (power of two)
+  int* error;                   // device flag: 1 = crossing overflow
+};
+
+// ---- preparation -------------------------------------------------------------------
+__global__ void poly_transform_kernel(const double* __restrict__ xy, double* __restrict__ px,
+                                      double* __restrict__ py, int64_t n, double inv0, double inv1,
+                                      double inv3, double inv5) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = xy[2 * i], y = xy[2 * i + 1];
+  // GDALApplyGeoTransform on GDALInvGeoTransform's output (rotation terms are 0)
+  px[i] = (inv0 + x * inv1) + y * 0.0;
+  py[i] = (inv3 + x * 0.0) + y * inv5;
+}
+
+__global__ void poly_rows_kernel(const double* __restrict__ py, const int64_t* __restrict__ ring_offsets,
+                                 const int64_t* __restrict__ poly_offsets, int64_t n_polygons,
+                                 int height, int row_begin, int row_end, int* __restrict__ miny,
+                                 int* __restrict__ maxy) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_polygons) return;
+  const int64_t v0 = ring_offsets[poly_offsets[p]], v1 = ring_offsets[poly_offsets[p + 1]];
+  int lo = 1, hi = 0;
+  if (v1 > v0) {
+    double dmin = py[v0], dmax = py[v0];
+    for (int64_t i = v0 + 1; i < v1; ++i) {
+      dmin = fmin(dmin, py[i]);
+      dmax = fmax(dmax, py[i]);
+    }
+    // static_cast<int>(dminy) / (dmaxy), then clamped to the raster
+    dmin = fmin(fmax(dmin, -1.0e9), 1.0e9);
+    dmax = fmin(fmax(dmax, -1.0e9), 1.0e9);
+    lo = (int)dmin;
+    hi = (int)dmax;
+    if (v1 - v0 == 1) { lo = hi = (int)floor(dmin); }  // point feature: the cell that contains it
+    if (lo < 0) lo = 0;
+    if (hi >= height) hi = height - 1;
+    if (lo < row_begin) lo = row_begin;
+    if (hi >= row_end) hi = row_end - 1;
+  }
+  miny[p] = lo;
+  maxy[p] = hi;
+}
+
+// ---- warp-level scanline walk ---------------------------------------------------------
+__device__ __forceinline__ int clamp_to_int(double v) {
+  return (int)fmin(fmax(v, -2.0e9), 2.0e9);
+}
+
+// sort buf[0..n) ascending, warp cooperative
+__device__ __forceinline__ void warp_sort(int* buf, int n, int lane) {
+  __syncwarp();
+  if (n <= 1) return;
+  if (n <= 32) {
+    const int v = lane < n ? buf[lane] : 0;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const int o = __shfl_sync(0xffffffffu, v, j);
+      rank += (o < v) || (o == v && j < lane);
+    }
+    __syncwarp();
+    if (lane < n) buf[rank] = v;
+    __syncwarp();
+    return;
+  }
+  int m = 1;
+  while (m < n) m <<= 1;
+  for (int i = n + lane; i < m; i += 32) buf[i] = INT_MAX;
+  __syncwarp();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < m; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int a = buf[i], b = buf[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+// is column x inside one of the sorted crossing pairs?
+__device__ __forceinline__ bool in_pairs(int x, const int* buf, int count) {
+  for (int i = 0; i + 1 < count; i += 2)
+    if (x >= buf[i] && x <= buf[i + 1] - 1) return true;
+  return false;
+}
+
+// Visitor interface (all calls are warp-uniform):
+//   span(y, x0, x1)                       regular even-odd span, inclusive, clipped
+//   hspan(y, x0, x1, buf, count)          bottom horizontal edge on the scanline
+template <class Visitor>
+__device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* buf, int* hbuf,
+                                             Visitor& vis) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
+  if (r1 <= r0) return;
+  const int64_t v0 = P.ring_offsets[r0], v1 = P.ring_offsets[r1];
+  const int miny = P.miny[p], maxy = P.maxy[p];
+  const int maxx = P.width - 1;
+  if (v1 - v0 == 1) {  // point feature (GDALdllImagePoint): burn floor(x), floor(y)
+    if (warp == 0 && miny <= maxy) {
+      const int x = clamp_to_int(floor(P.px[v0]));
+      if (x >= 0 && x <= maxx) vis.span(miny, x, x);
+    }
+    return;
+  }
+  for (int y = miny + warp; y <= maxy; y += nwarps) {
+    const double dy = y + 0.5;
+    int count = 0, hcount = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t a = P.ring_offsets[r], b = P.ring_offsets[r + 1];
+      for (int64_t base = a; base < b; base += 32) {
+        const int64_t i = base + lane;
+        bool cross = false, hs = false;
+        int xi = 0, hx1 = 0, hx2 = 0;
+        if (i < b) {
+          const int64_t ind1 = (i == a) ? b - 1 : i - 1;
+          double dy1 = P.py[ind1], dy2 = P.py[i];
+          if (!((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy))) {
+            double dx1, dx2;
+            if (dy1 < dy2) {
+              dx1 = P.px[ind1]; dx2 = P.px[i];
+              cross = true;
+            } else if (dy1 > dy2) {
+              const double t = dy1; dy1 = dy2; dy2 = t;
+              dx2 = P.px[ind1]; dx1 = P.px[i];
+              cross = true;
+            } else {
+              const double xa = P.px[ind1], xb = P.px[i];
+              if (xa > xb) {  // bottom horizontal edge: filled on its own
+                hx1 = clamp_to_int(floor(xb + 0.5));
+                hx2 = clamp_to_int(floor(xa + 0.5));
+                hs = !(hx1 > maxx || hx2 <= 0);
+              }
+            }
+            if (cross) {
+              cross = (dy < dy2 && dy >= dy1);
+              if (cross) {
+                const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+                xi = clamp_to_int(floor(intersect + 0.5));
+              }
+            }
+          }
+        }
+        const unsigned cm = __ballot_sync(0xffffffffu, cross);
+        if (cross) {
+          const int pos = count + __popc(cm & ((1u << lane) - 1u));
+          if (pos < P.cap) buf[pos] = xi;
+        }
+        count += __popc(cm);
+        const unsigned hm = __ballot_sync(0xffffffffu, hs);
+        if (hs) {
+          const int pos = hcount + __popc(hm & ((1u << lane) - 1u));
+          if (pos < PG_MAX_HSPANS) { hbuf[2 * pos] = hx1; hbuf[2 * pos + 1] = hx2; }
+        }
+        hcount += __popc(hm);
+      }
+    }
+    if (count > P.cap || hcount > PG_MAX_HSPANS) {
+      if (lane == 0) atomicExch(P.error, 1);
+      count = count > P.cap ? P.cap : count;
+      hcount = hcount > PG_MAX_HSPANS ? PG_MAX_HSPANS : hcount;
+    }
+    warp_sort(buf, count, lane);
+    for (int i = 0; i + 1 < count; i += 2) {
+      const int xa = buf[i], xb = buf[i + 1];
+      if (xa <= maxx && xb > 0) {
+        const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
+        if (x0 <= x1) vis.span(y, x0, x1);
+      }
+    }
+    __syncwarp();
+    for (int h = 0; h < hcount; ++h) {
+      const int x0 = hbuf[2 * h] < 0 ? 0 : hbuf[2 * h];
+      const int x1 = hbuf[2 * h + 1] - 1 > maxx ? maxx : hbuf[2 * h + 1] - 1;
+      if (x0 <= x1) vis.hspan(y, x0, x1, buf, count);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- rasterise ---------------------------------------------------------------------------
+struct LabelVisitor {
+  int* idx; int width; int label;
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    int* row = idx + (int64_t)y * width;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) atomicMax(row + x, label);
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int*, int) { span(y, x0, x1); }
+};
+
+__global__ void __launch_bounds__(PG_THREADS)
+rasterize_kernel(const PolyDev P, int* __restrict__ idx) {
+  extern __shared__ int pg_smem[];
+  const int warp = threadIdx.x >> 5;
+  int* buf = pg_smem + warp * P.cap;
+  int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    LabelVisitor vis{idx, P.width, (int)p};
+    scan_polygon(P, p, buf, hbuf, vis);
+  }
+}
+
+template <typename T>
+__global__ void resolve_labels_kernel(const int* __restrict__ idx, const T* __restrict__ burn,
+                                      T nodata, T* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = idx[i];
+    dst[i] = l < 0 ? nodata : burn[l];
+  }
+}
+
+// ---- zonal statistics ------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long order_f64(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double unorder_f64(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ unsigned order_f32(float v) {
+  unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_f32(unsigned k) {
+  unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+// sortable key of a raster value: 32 bit for float32, 64 bit otherwise
+template <typename T> struct KeyOf {
+  typedef unsigned long long type;
+  static __device__ __forceinline__ type key(T v) { return order_f64((double)v); }
+  static __device__ __forceinline__ T value(type k) { return (T)unorder_f64(k); }
+};
+template <> struct KeyOf<float> {
+  typedef unsigned type;
+  static __device__ __forceinline__ type key(float v) { return order_f32(v); }
+  static __device__ __forceinline__ float value(type k) { return unorder_f32(k); }
+};
+
+struct AreaVisitor {
+  long long area;
+  __device__ __forceinline__ void span(int, int x0, int x1) {
+    if ((threadIdx.x & 31) == 0) area += x1 - x0 + 1;
+  }
+  __device__ __forceinline__ void hspan(int, int x0, int x1, const int* buf, int count) {
+    int n = 0;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) n += !in_pairs(x, buf, count);
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) area += n;
+  }
+};
+
+__global__ void __launch_bounds__(PG_THREADS)
+zonal_area_kernel(const PolyDev P, long long* __restrict__ area) {
+  extern __shared__ int pg_smem[];
+  __shared__ long long warp_area[PG_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* buf = pg_smem + warp * P.cap;
+  int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    AreaVisitor vis{0};
+    scan_polygon(P, p, buf, hbuf, vis);
+    if (lane == 0) warp_area[warp] = vis.area;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long a = 0;
+      for (int w = 0; w < PG_WARPS; ++w) a += warp_area[w];
+      area[p] = a;
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+struct ActiveTest {
+  T nodata; int has_nodata; int has_threshold; float threshold;
+  __device__ __forceinline__ bool operator()(T v) const {
+    if (has_nodata && v == nodata) return false;
+    if (has_threshold) {
+      if (threshold != threshold) return false;          // NaN threshold: no aggregation
+      if (!((double)v >= (double)threshold)) return false;
+    }
+    return true;
+  }
+};
+
+template <typename T>
+struct ReduceVisitor {
+  const T* raster; int width; ActiveTest<T> active;
+  long long count; double sum, vmin, vmax;
+  __device__ __forceinline__ void take(T v) {
+    if (active(v)) {
+      const double d = (double)v;
+      ++count; sum += d;
+      vmin = d < vmin ? d : vmin;
+      vmax = d > vmax ? d : vmax;
+    }
+  }
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    const T* row = raster + (int64_t)y * width;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) take(__ldg(row + x));
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
+    const T* row = raster + (int64_t)y * width;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32)
+      if (!in_pairs(x, buf, n)) take(__ldg(row + x));
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(PG_THREADS)
+zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                    const float* __restrict__ thresholds, GmZonalPartial* __restrict__ partial) {
+  extern __shared__ int pg_smem[];
+  __shared__ long long s_count[PG_WARPS];
+  __shared__ double s_sum[PG_WARPS], s_min[PG_WARPS], s_max[PG_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* buf = pg_smem + warp * P.cap;
+  int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    ReduceVisitor<T> vis;
+    vis.raster = raster; vis.width = P.width;
+    vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
+    vis.active.has_threshold = thresholds != nullptr;
+    vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
+    vis.count = 0; vis.sum = 0.0; vis.vmin = DBL_MAX; vis.vmax = -DBL_MAX;
+    scan_polygon(P, p, buf, hbuf, vis);
+    for (int o = 16; o > 0; o >>= 1) {
+      vis.count += __shfl_xor_sync(0xffffffffu, vis.count, o);
+      vis.sum += __shfl_xor_sync(0xffffffffu, vis.sum, o);
+      vis.vmin = fmin(vis.vmin, __shfl_xor_sync(0xffffffffu, vis.vmin, o));
+      vis.vmax = fmax(vis.vmax, __shfl_xor_sync(0xffffffffu, vis.vmax, o));
+    }
+    if (lane == 0) { s_count[warp] = vis.count; s_sum[warp] = vis.sum; s_min[warp] = vis.vmin; s_max[warp] = vis.vmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      GmZonalPartial r{0, 0.0, DBL_MAX, -DBL_MAX};
+      for (int w = 0; w < PG_WARPS; ++w) {
+        r.count += s_count[w]; r.sum += s_sum[w];
+        r.vmin = fmin(r.vmin, s_min[w]); r.vmax = fmax(r.vmax, s_max[w]);
+      }
+      partial[p] = r;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void zonal_finalize_kernel(const GmZonalPartial* __restrict__ partial, int stat,
+                                      float* __restrict__ out, int64_t n) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const GmZonalPartial r = partial[p];
+  float v = __int_as_float(0x7fc00000);
+  if (r.count > 0) {
+    switch (stat) {
+      case GM_STAT_COUNT: v = (float)(double)r.count; break;
+      case GM_STAT_SUM: v = (float)r.sum; break;
+      case GM_STAT_MEAN: v = (float)(r.sum / (double)r.count); break;
+      case GM_STAT_MIN: v = (float)r.vmin; break;
+      case GM_STAT_MAX: v = (float)r.vmax; break;
+      default: break;
+    }
+  }
+  out[p] = v;
+}
+
+// gather visitor: append the keys of active cells to the polygon's buffer
+template <typename T>
+struct GatherVisitor {
+  typedef typename KeyOf<T>::type K;
+  const T* raster; int width; ActiveTest<T> active;
+  K* keys; int* cursor; long long capacity;
+  __device__ __forceinline__ void put(bool ok, T v) {
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cursor, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) {
+      const long long pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < capacity) keys[pos] = KeyOf<T>::key(v);
+    }
+  }
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    const T* row = raster + (int64_t)y * width;
+    const int lane = threadIdx.x & 31;
+    for (int xb = x0; xb <= x1; xb += 32) {
+      const int x = xb + lane;
+      T v = T(0);
+      bool ok = false;
+      if (x <= x1) { v = __ldg(row + x); ok = active(v); }
+      put(ok, v);
+    }
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
+    const T* row = raster + (int64_t)y * width;
+    const int lane = threadIdx.x & 31;
+    for (int xb = x0; xb <= x1; xb += 32) {
+      const int x = xb + lane;
+      T v = T(0);
+      bool ok = false;
+      if (x <= x1 && !in_pairs(x, buf, n)) { v = __ldg(row + x); ok = active(v); }
+      put(ok, v);
+    }
+  }
+};
+
+// key of rank r (0-based) among keys[0..n): MSD radix select, 8 bits per pass
+template <typename K>
+__device__ K block_select(const K* keys, int n, long long rank, int* hist, K* shared_prefix) {
+  constexpr int BITS = sizeof(K) * 8;
+  K prefix = 0, mask = 0;
+  for (int shift = BITS - 8; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const K k = keys[i];
+      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long r = rank;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (r < hist[b]) break;
+        r -= hist[b];
+      }
+      shared_prefix[0] = prefix | ((K)b << shift);
+      shared_prefix[1] = (K)r;
+    }
+    __syncthreads();
+    prefix = shared_prefix[0];
+    rank = (long long)shared_prefix[1];
+    mask |= ((K)0xff << shift);
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// smallest key greater than `key` (only called when it exists)
+template <typename K>
+__device__ K block_next_above(const K* keys, int n, K key, K* scratch) {
+  K best = ~(K)0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const K k = keys[i];
+    if (k > key && k < best) best = k;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const K other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other < best ? other : best;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    K b = scratch[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = scratch[w] < b ? scratch[w] : b;
+    scratch[0] = b;
+  }
+  __syncthreads();
+  best = scratch[0];
+  __syncthreads();
+  return best;
+}
+
+template <typename K>
+__device__ int block_count_le(const K* keys, int n, K key, int* counter) {
+  if (threadIdx.x == 0) *counter = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += keys[i] <= key;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(counter, c);
+  __syncthreads();
+  c = *counter;
+  __syncthreads();
+  return c;
+}
+
+// result of the order statistic in the reference's arithmetic
+template <typename T> __device__ __forceinline__ float median_of(T lo, T hi) {
+  // scipy.ndimage._measurements._select: integers are averaged in double
+  return (float)(((double)lo + (double)hi) / 2.0);
+}
+template <> __device__ __forceinline__ float median_of<float>(float lo, float hi) { return (lo + hi) / 2.0f; }
+template <> __device__ __forceinline__ float median_of<double>(double lo, double hi) { return (float)((lo + hi) / 2.0); }
+
+template <typename T> __device__ __forceinline__ float percentile_of(T lo, T hi, double part) {
+  // measurements.py:137: data[lo] + part * (data[hi] - data[lo]); the difference in the data dtype
+  const T diff = (T)(hi - lo);
+  return (float)((double)lo + part * (double)diff);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS)
+zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                    const float* __restrict__ thresholds, int stat, double q,
+                    const long long* __restrict__ area, const long long* __restrict__ big_offset,
+                    typename KeyOf<T>::type* __restrict__ big_keys, int smem_capacity,
+                    float* __restrict__ out) {
+  typedef typename KeyOf<T>::type K;
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  const int nw = SEL_THREADS / 32;
+  int* cross = reinterpret_cast<int*>(sel_smem);
+  const int warp = threadIdx.x >> 5;
+  int* buf = cross + warp * P.cap;
+  int* hbuf = cross + nw * P.cap + warp * 2 * PG_MAX_HSPANS;
+  K* smem_keys = reinterpret_cast<K*>(sel_smem + ((size_t)(nw * P.cap + nw * 2 * PG_MAX_HSPANS) * sizeof(int) + 15) / 16 * 16);
+  __shared__ int hist[256];
+  __shared__ K prefix_scratch[8];
+  __shared__ int cursor;
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    const long long a = area[p];
+    K* keys = a <= smem_capacity ? smem_keys : big_keys + big_offset[p];
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    GatherVisitor<T> vis;
+    vis.raster = raster; vis.width = P.width;
+    vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
+    vis.active.has_threshold = thresholds != nullptr;
+    vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
+    vis.keys = keys; vis.cursor = &cursor; vis.capacity = a;
+    scan_polygon(P, p, buf, hbuf, vis);
+    __threadfence_block();
+    __syncthreads();
+    const int n = cursor;
+    float result = __int_as_float(0x7fc00000);
+    if (n > 0) {
+      long long lo_rank, hi_rank;
+      double part = 0.0;
+      if (stat == GM_STAT_MEDIAN) {
+        lo_rank = (n - 1) / 2; hi_rank = n / 2;
+      } else {
+        const double frac = (double)(n - 1) * (q / 100.0);
+        lo_rank = (long long)floor(frac);
+        hi_rank = (long long)ceil(frac);
+        part = frac - floor(frac);
+      }
+      const K klo = block_select<K>(keys, n, lo_rank, hist, prefix_scratch);
+      K khi = klo;
+      if (hi_rank != lo_rank) {
+        const int le = block_count_le<K>(keys, n, klo, &cursor);
+        if (le < hi_rank + 1) khi = block_next_above<K>(keys, n, klo, prefix_scratch);
+      }
+      const T lo = KeyOf<T>::value(klo), hi = KeyOf<T>::value(khi);
+      result = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
+    }
+    if (threadIdx.x == 0) out[p] = result;
+    __syncthreads();
+  }
+}
+
+__global__ void big_offsets_kernel(const long long* __restrict__ area, int64_t n, int smem_capacity,
+                                   long long* __restrict__ offsets, long long* __restrict__ total) {
+  // single thread: exclusive scan over the few polygons that exceed shared memory
+  long long acc = 0;
+  for (int64_t p = 0; p < n; ++p) {
+    offsets[p] = acc;
+    if (area[p] > smem_capacity) acc += area[p];
+  }
+  *total = acc;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+struct PolyUpload {
+  void *xy = nullptr, *px = nullptr, *py = nullptr, *rings = nullptr, *polys = nullptr;
+  void *miny = nullptr, *maxy = nullptr, *error = nullptr;
+  PolyDev dev;
+  cudaStream_t s;
+  void release() {
+    void* all[] = {xy, px, py, rings, polys, miny, maxy, error};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+  }
+};
+
+static int prepare_polygons(const GmPolygons* polys, const double* geo, int height, int width,
+                            int64_t row_begin, int64_t row_end, PolyUpload& u, cudaStream_t s) {
+  u.s = s;
+  if (!polys || !geo) return fail("polygons: null argument");
+  if (geo[2] != 0.0 || geo[4] != 0.0 || geo[1] == 0.0 || geo[5] == 0.0)
+    return fail("polygons: rotated or degenerate geotransform");
+  const int64_t nv = polys->n_vertices, nr = polys->n_rings, np_ = polys->n_polygons;
+  int64_t max_vertices = 1;
+  for (int64_t p = 0; p < np_; ++p) {
+    const int64_t a = polys->ring_offsets[polys->poly_offsets[p]];
+    const int64_t b = polys->ring_offsets[polys->poly_offsets[p + 1]];
+    if (b - a > max_vertices) max_vertices = b - a;
+  }
+  int cap = 32;
+  while (cap < max_vertices && cap < PG_MAX_CROSSINGS) cap <<= 1;
+  if (upload(&u.xy, polys->xy, sizeof(double) * 2 * nv, s)) return 1;
+  if (upload(&u.rings, polys->ring_offsets, sizeof(int64_t) * (nr + 1), s)) return 1;
+  if (upload(&u.polys, polys->poly_offsets, sizeof(int64_t) * (np_ + 1), s)) return 1;
+  GM_CUDA(cudaMallocAsync(&u.px, sizeof(double) * (nv > 0 ? nv : 1), s));
+  GM_CUDA(cudaMallocAsync(&u.py, sizeof(double) * (nv > 0 ? nv : 1), s));
+  GM_CUDA(cudaMallocAsync(&u.miny, sizeof(int) * (np_ > 0 ? np_ : 1), s));
+  GM_CUDA(cudaMallocAsync(&u.maxy, sizeof(int) * (np_ > 0 ? np_ : 1), s));
+  GM_CUDA(cudaMallocAsync(&u.error, sizeof(int), s));
+  GM_CUDA(cudaMemsetAsync(u.error, 0, sizeof(int), s));
+  const double inv0 = -geo[0] / geo[1], inv1 = 1.0 / geo[1];
+  const double inv3 = -geo[3] / geo[5], inv5 = 1.0 / geo[5];
+  if (nv > 0) {
+    poly_transform_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(
+        (const double*)u.xy, (double*)u.px, (double*)u.py, nv, inv0, inv1, inv3, inv5);
+    GM_LAUNCH_CHECK();
+  }
+  if (np_ > 0) {
+    poly_rows_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
+        (const double*)u.py, (const int64_t*)u.rings, (const int64_t*)u.polys, np_, height,
+        (int)row_begin, (int)row_end, (int*)u.miny, (int*)u.maxy);
+    GM_LAUNCH_CHECK();
+  }
+  u.dev.px = (const double*)u.px; u.dev.py = (const double*)u.py;
+  u.dev.ring_offsets = (const int64_t*)u.rings; u.dev.poly_offsets = (const int64_t*)u.polys;
+  u.dev.miny = (const int*)u.miny; u.dev.maxy = (const int*)u.maxy;
+  u.dev.n_polygons = np_; u.dev.height = height; u.dev.width = width; u.dev.cap = cap;
+  u.dev.error = (int*)u.error;
+  return 0;
+}
+
+static size_t scan_smem(int cap, int warps) {
+  return (size_t)(warps * cap + warps * 2 * PG_MAX_HSPANS) * sizeof(int);
+}
+
+static int check_overflow(PolyUpload& u, cudaStream_t s) {
+  int flag = 0;
+  GM_CUDA(cudaMemcpyAsync(&flag, u.error, sizeof(int), cudaMemcpyDeviceToHost, s));
+  GM_CUDA(cudaStreamSynchronize(s));
+  if (flag) return fail("polygons: more than 4096 edge crossings (or 8 horizontal edges) on one scanline");
+  return 0;
+}
+
+static unsigned poly_grid(int64_t n) {
+  const int64_t cap = (int64_t)sm_count() * 32;
+  return (unsigned)(n < cap ? (n > 0 ? n : 1) : cap);
+}
+
+template <typename T>
+static int run_rasterize(PolyUpload& u, const void* burn, const void* nodata, Staged& out,
+                         int64_t n_pixels, cudaStream_t s) {
+  void *idx = nullptr, *dburn = nullptr;
+  GM_CUDA(cudaMallocAsync(&idx, sizeof(int) * (size_t)n_pixels, s));
+  GM_CUDA(cudaMemsetAsync(idx, 0xff, sizeof(int) * (size_t)n_pixels, s));
+  int rc = 0;
+  const int64_t np_ = u.dev.n_polygons;
+  if (np_ > 0) {
+    const size_t smem = scan_smem(u.dev.cap, PG_WARPS);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024)
+      e = cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      rasterize_kernel<<<poly_grid(np_), PG_THREADS, smem, s>>>(u.dev, (int*)idx);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) rc = fail(std::string("rasterize launch: ") + cudaGetErrorString(e));
+    else count_launch();
+  }
+  if (!rc) rc = upload(&dburn, burn, sizeof(T) * (size_t)(np_ > 0 ? np_ : 1), s);
+  if (!rc) {
+    T nd;
+    memcpy(&nd, nodata, sizeof(T));
+    int64_t blocks = (n_pixels + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    resolve_labels_kernel<T><<<(unsigned)blocks, 256, 0, s>>>((const int*)idx, (const T*)dburn, nd,
+                                                              (T*)out.dev, n_pixels);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(std::string("resolve launch: ") + cudaGetErrorString(e));
+    else count_launch();
+  }
+  cudaFreeAsync(idx, s);
+  if (dburn) cudaFreeAsync(dburn, s);
+  return rc;
+}
+
+template <typename T>
+static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, int has_nodata,
+                     int stat, double q, const float* thresholds, float* out, int64_t* covered,
+                     GmZonalPartial* partial, cudaStream_t s) {
+  const int64_t np_ = u.dev.n_polygons;
+  if (np_ == 0) return 0;
+  T nd = T(0);
+  if (has_nodata) memcpy(&nd, nodata, sizeof(T));
+  void *darea = nullptr, *dthr = nullptr, *dpartial = nullptr, *dout = nullptr;
+  void *doff = nullptr, *dtotal = nullptr, *dbig = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    void* all[] = {darea, dthr, dpartial, dout, doff, dtotal, dbig};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+  };
+#define GM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  GM_TRY(cudaMallocAsync(&darea, sizeof(long long) * np_, s));
+  if (thresholds && upload(&dthr, thresholds, sizeof(float) * np_, s)) { cleanup(); return 1; }
+  const size_t smem_scan = scan_smem(u.dev.cap, PG_WARPS);
+  if (smem_scan > 48 * 1024) {
+    GM_TRY(cudaFuncSetAttribute(zonal_area_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+    GM_TRY(cudaFuncSetAttribute(zonal_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+  }
+  // pixel centres inside every polygon (no raster access): `covered` and buffer sizes
+  zonal_area_kernel<<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea);
+  GM_TRY(cudaGetLastError());
+  count_launch();
+  std::vector<long long> area(np_);
+  GM_TRY(cudaMemcpyAsync(area.data(), darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+  GM_TRY(cudaStreamSynchronize(s));
+  if (covered) for (int64_t p = 0; p < np_; ++p) covered[p] = area[p];
+
+  const bool order_stat = stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE;
+  if (!order_stat || partial) {
+    GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
+    zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
+        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial);
+    GM_TRY(cudaGetLastError());
+    count_launch();
+    if (partial)
+      GM_TRY(cudaMemcpyAsync(partial, dpartial, sizeof(GmZonalPartial) * np_, cudaMemcpyDeviceToHost, s));
+    if (out && !order_stat) {
+      GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
+      zonal_finalize_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
+          (const GmZonalPartial*)dpartial, stat, (float*)dout, np_);
+      GM_TRY(cudaGetLastError());
+      count_launch();
+      GM_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * np_, cudaMemcpyDeviceToHost, s));
+    }
+  }
+  if (order_stat && out) {
+    typedef typename KeyOf<T>::type K;
+    long long max_area = 0;
+    for (int64_t p = 0; p < np_; ++p) max_area = area[p] > max_area ? area[p] : max_area;
+    const size_t head = (scan_smem(u.dev.cap, SEL_THREADS / 32) + 15) / 16 * 16;
+    const size_t budget = 200 * 1024 - head;
+    long long capacity = (long long)(budget / sizeof(K));
+    if (max_area < capacity) capacity = max_area > 0 ? max_area : 1;
+    const size_t smem_sel = head + (size_t)capacity * sizeof(K);
+    GM_TRY(cudaFuncSetAttribute(zonal_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+    GM_TRY(cudaMallocAsync(&doff, sizeof(long long) * np_, s));
+    GM_TRY(cudaMallocAsync(&dtotal, sizeof(long long), s));
+    long long total = 0;
+    if (max_area > capacity) {
+      big_offsets_kernel<<<1, 1, 0, s>>>((const long long*)darea, np_, (int)capacity, (long long*)doff, (long long*)dtotal);
+      GM_TRY(cudaGetLastError());
+      count_launch();
+      GM_TRY(cudaMemcpyAsync(&total, dtotal, sizeof(long long), cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaStreamSynchronize(s));
+    } else {
+      GM_TRY(cudaMemsetAsync(doff, 0, sizeof(long long) * np_, s));
+    }
+    GM_TRY(cudaMallocAsync(&dbig, sizeof(K) * (size_t)(total > 0 ? total : 1), s));
+    GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
+    zonal_select_kernel<T><<<poly_grid(np_), SEL_THREADS, smem_sel, s>>>(
+        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, stat, q,
+        (const long long*)darea, (const long long*)doff, (K*)dbig, (int)capacity, (float*)dout);
+    GM_TRY(cudaGetLastError());
+    count_launch();
+    GM_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * np_, cudaMemcpyDeviceToHost, s));
+  }
+  GM_TRY(cudaStreamSynchronize(s));
+#undef GM_TRY
+  cleanup();
+  return rc;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" int gm_rasterize_polygons(const GmPolygons* polys, const double geo[6],
+                                     const void* burn_values, const void* nodata, GmArray* dst,
+                                     void* stream) {
+  if (ensure_init()) return 1;
+  if (!dst || !burn_values || !nodata) return fail("gm_rasterize_polygons: null argument");
+  if (dst->shape[0] != 1) return fail("gm_rasterize_polygons: one band expected");
+  cudaStream_t s = resolve_stream(stream);
+  const int H = (int)dst->shape[1], W = (int)dst->shape[2];
+  const int64_t n_pixels = (int64_t)H * W;
+  Staged out;
+  PolyUpload u;
+  int rc = out.open_output(*dst, s);
+  if (!rc && n_pixels > 0) {
+    rc = prepare_polygons(polys, geo, H, W, 0, H, u, s);
+    if (!rc) {
+      switch (dst->dtype) {
+        case GM_U8: case GM_BOOL: rc = run_rasterize<uint8_t>(u, burn_values, nodata, out, n_pixels, s); break;
+        case GM_I32: rc = run_rasterize<int32_t>(u, burn_values, nodata, out, n_pixels, s); break;
+        case GM_F64: rc = run_rasterize<double>(u, burn_values, nodata, out, n_pixels, s); break;
+        case GM_F32: rc = run_rasterize<float>(u, burn_values, nodata, out, n_pixels, s); break;
+        default: rc = fail("gm_rasterize_polygons: dtype must be uint8, int32, float32 or float64");
+      }
+    }
+    if (!rc) rc = check_overflow(u, s);
+    u.release();
+  }
+  if (!rc) rc = out.finish_output();
+  const bool sync = out.owned;
+  out.release();
+  if (!rc && sync) GM_CUDA(cudaStreamSynchronize(s));
+  return rc;
+}
+
+extern "C" int gm_zonal_stats(const GmArray* raster, const void* nodata, int has_nodata,
+                              const GmPolygons* polys, const double geo[6], int stat, double q,
+                              const float* thresholds, int64_t row_begin, int64_t row_end,
+                              float* out, int64_t* covered, GmZonalPartial* partial, void* stream) {
+  if (ensure_init()) return 1;
+  if (!raster || !polys) return fail("gm_zonal_stats: null argument");
+  if (raster->shape[0] != 1) return fail("gm_zonal_stats: one frame per call");
+  if (stat < GM_STAT_SUM || stat > GM_STAT_PERCENTILE || stat == GM_STAT_STD || stat == GM_STAT_VAR)
+    return fail("gm_zonal_stats: unsupported statistic");
+  cudaStream_t s = resolve_stream(stream);
+  const int H = (int)raster->shape[1], W = (int)raster->shape[2];
+  if (row_begin < 0) row_begin = 0;
+  if (row_end > H || row_end <= 0) row_end = H;
+  Staged in;
+  PolyUpload u;
+  int rc = in.open_input(*raster, s);
+  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s);
+  if (!rc) {
+#define GM_Z(T) run_zonal<T>(u, in, nodata, has_nodata, stat, q, thresholds, out, covered, partial, s)
+    switch (raster->dtype) {
+      case GM_U8: case GM_BOOL: rc = GM_Z(uint8_t); break;
+      case GM_I8: rc = GM_Z(int8_t); break;
+      case GM_U16: rc = GM_Z(uint16_t); break;
+      case GM_I16: rc = GM_Z(int16_t); break;
+      case GM_U32: rc = GM_Z(uint32_t); break;
+      case GM_I32: rc = GM_Z(int32_t); break;
+      case GM_F32: rc = GM_Z(float); break;
+      case GM_F64: rc = GM_Z(double); break;
+      default: rc = fail("gm_zonal_stats: unsupported raster dtype");
+    }
+#undef GM_Z
+  }
+  if (!rc) rc = check_overflow(u, s);
+  u.release();
+  in.release();
+  return rc;
+}

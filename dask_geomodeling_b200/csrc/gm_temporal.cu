@@ -22,22 +22,6 @@ template <typename D> struct DMax { static __host__ __device__ D value() { retur
 
 template <typename W, typename D> __device__ __forceinline__ D cast_out(W v) { return (D)v; }
 
-// np.nanpercentile(method="linear") on a sorted sample
-template <typename W>
-__device__ __forceinline__ W lerp_percentile(const W* sorted, int n, double q) {
-  const double virt = (q / 100.0) * (double)(n - 1);
-  int lo = (int)floor(virt);
-  if (lo < 0) lo = 0;
-  if (lo > n - 1) lo = n - 1;
-  const int hi = lo + 1 < n ? lo + 1 : n - 1;
-  const W t = (W)(virt - (double)lo);
-  const W a = sorted[lo], b = sorted[hi];
-  const W diff = b - a;
-  W r = a + diff * t;
-  if (t >= (W)0.5) r = b - diff * ((W)1 - t);
-  return r;
-}
-
 template <typename S, typename W, typename D>
 __global__ void __launch_bounds__(256)
 temporal_aggregate_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
@@ -74,17 +58,20 @@ temporal_aggregate_kernel(const S* __restrict__ src, D* __restrict__ dst, S noda
             const W a = col[(int64_t)((n - 1) / 2) * plane], b = col[(int64_t)(n / 2) * plane];
             result = (n & 1) ? a : (a + b) / (W)2;
           } else {
-            // strided column -> tiny local copy of the two neighbours via the same formula
-            const double virt = (q / 100.0) * (double)(n - 1);
-            int lo = (int)floor(virt);
+            // np.nanpercentile(method="linear") in the working dtype W:
+            // q / 100, virtual index (n - 1) * q, gamma and the lerp are all W arithmetic
+            // (numpy/lib/_function_base_impl.py: percentile, _quantile, _lerp)
+            const W qw = (W)q / (W)100;
+            const W virt = (W)(n - 1) * qw;
+            int lo = (int)floor((double)virt);
             if (lo < 0) lo = 0;
             if (lo > n - 1) lo = n - 1;
             const int hi = lo + 1 < n ? lo + 1 : n - 1;
-            W pair[2] = {col[(int64_t)lo * plane], col[(int64_t)hi * plane]};
-            const W t = (W)(virt - (double)lo);
-            const W diff = pair[1] - pair[0];
-            result = pair[0] + diff * t;
-            if (t >= (W)0.5) result = pair[1] - diff * ((W)1 - t);
+            const W a = col[(int64_t)lo * plane], b = col[(int64_t)hi * plane];
+            const W t = virt - (W)lo;
+            const W diff = b - a;
+            result = a + diff * t;
+            if (t >= (W)0.5) result = b - diff * ((W)1 - t);
           }
         }
       } else {

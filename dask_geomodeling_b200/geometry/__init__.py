@@ -1,1 +1,3 @@
 from .base import *  # NOQA
+from .sources import *  # NOQA
+from .aggregate import *  # NOQA

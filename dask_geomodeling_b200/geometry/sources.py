@@ -1,0 +1,91 @@
+"""In-memory geometry source.
+
+The reference ships only file/WKT based geometry sources (geometry/sources.py,
+out of scope: vector file I/O); its tests feed AggregateRaster/Rasterize from
+``MockGeometry`` (tests/factories.py:193-282).  ``MemoryGeometrySource`` is that
+idea as a supported block: polygons (lists of rings or shapely-like objects)
+plus per-feature properties, answered without reprojection.
+"""
+import numpy as np
+import pandas as pd
+
+from .. import utils
+from .base import GeometryBlock
+
+__all__ = ["MemoryGeometrySource"]
+
+
+def _as_geometry(item):
+    if hasattr(item, "geom_type") or hasattr(item, "exterior") or hasattr(item, "geoms"):
+        return item
+    arr = np.asarray(item, dtype=object if isinstance(item, (list, tuple)) and item and
+                     isinstance(item[0], (list, tuple)) and item[0] and
+                     isinstance(item[0][0], (list, tuple, np.ndarray)) else np.float64)
+    if arr.dtype != object and arr.ndim == 2:
+        return utils.Polygon(arr)               # a single ring
+    rings = [np.asarray(r, dtype=np.float64) for r in item]
+    return utils.Polygon(rings[0], rings[1:])   # shell + holes
+
+
+class MemoryGeometrySource(GeometryBlock):
+    """Features held in memory.
+
+    Args:
+      polygons: list of geometries; each a list of (x, y) tuples (one ring), a list
+        of rings (shell followed by holes) or a geometry object
+      properties: optional list of dicts (one per feature); key ``id`` becomes the index
+      projection: projection of the coordinates
+    """
+
+    def __init__(self, polygons, properties=None, projection="EPSG:3857"):
+        super().__init__(polygons, properties, projection)
+
+    polygons = property(lambda self: self.args[0])
+    properties = property(lambda self: self.args[1])
+    projection = property(lambda self: self.args[2])
+
+    @property
+    def columns(self):
+        result = {"geometry"}
+        if self.properties:
+            result |= set(self.properties[0].keys())
+        result.discard("id")
+        return result
+
+    def get_sources_and_requests(self, **request):
+        return [(self.polygons, None), (self.properties, None), (self.projection, None), (request, None)]
+
+    @staticmethod
+    def process(polygons, properties, projection, request):
+        limit = request.get("limit")
+        if limit is not None:
+            polygons = polygons[:limit]
+            properties = properties[:limit] if properties is not None else None
+        mode = request.get("mode", "intersects")
+        geometries = [_as_geometry(p) for p in polygons]
+        if not utils.same_projection(projection, request["projection"]):
+            geometries = [utils.shapely_transform(g, projection, request["projection"]) for g in geometries]
+        bounds = np.array([g.bounds for g in geometries], dtype=np.float64).reshape(-1, 4)
+        if mode == "extent":
+            extent = None
+            if len(geometries):
+                extent = (bounds[:, 0].min(), bounds[:, 1].min(), bounds[:, 2].max(), bounds[:, 3].max())
+            return {"extent": extent, "projection": request["projection"]}
+        if len(geometries) == 0:
+            return {"features": pd.DataFrame([]), "projection": request["projection"]}
+        df = pd.DataFrame.from_records(properties) if properties is not None else pd.DataFrame(index=range(len(geometries)))
+        df["geometry"] = pd.Series(geometries, index=df.index, dtype=object)
+        if "id" in df.columns:
+            df = df.set_index("id", drop=True)
+        else:
+            df.index.name = "id"
+        window = request.get("geometry")
+        if window is not None and mode in ("intersects", "centroid"):
+            x1, y1, x2, y2 = window.bounds
+            if mode == "intersects":  # bounding boxes decide (no GEOS here)
+                keep = (bounds[:, 2] >= x1) & (bounds[:, 0] <= x2) & (bounds[:, 3] >= y1) & (bounds[:, 1] <= y2)
+            else:
+                c = np.array([(g.centroid.x, g.centroid.y) for g in geometries])
+                keep = (c[:, 0] >= x1) & (c[:, 0] <= x2) & (c[:, 1] >= y1) & (c[:, 1] <= y2)
+            df = df[keep]
+        return {"features": df, "projection": request["projection"]}

@@ -11,7 +11,7 @@ FAMILIES = ["elemwise", "misc", "spatial", "temporal", "zonal"]
 
 # ops whose NumPy/libm result cannot be reproduced bit for bit: stated tolerances
 TRANSCENDENTAL = {"power", "exp", "log", "log10"}
-ULP_TOLERANT_TEMPORAL = {"std", "var", "p90"}
+ULP_TOLERANT_TEMPORAL = set()  # every temporal statistic is reproduced bit for bit
 
 
 def load(family):

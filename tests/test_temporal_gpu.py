@@ -40,12 +40,9 @@ def test_aggregate_all_frames(dtype, statistic):
     out = got["values"]
     assert out.dtype == expected.dtype and out.shape == expected.shape
     assert got["no_data_value"] == expected_nodata
-    if name in ("sum", "count", "min", "max", "mean", "median"):
-        np.testing.assert_array_equal(out, expected)      # sequential-in-t accumulation
-    else:
-        # stated tolerance: 2 ulp (np.nanpercentile's lerp / pairwise variance terms)
-        rtol = 3e-7 if expected.dtype == np.float32 else 1e-15
-        np.testing.assert_allclose(out, expected, rtol=rtol)
+    # sequential-in-t accumulation, NumPy's nanvar two-pass form and nanpercentile's
+    # linear interpolation in the working dtype: bit-exact for every statistic
+    np.testing.assert_array_equal(out, expected)
 
 
 @pytest.mark.parametrize("dtype", ["f4", "u1"])
