@@ -50,6 +50,9 @@ typedef struct GmArray {
 /* ---- fused element-wise evaluator ----------------------------------------
  * One accumulator + GM_NREG registers per pixel; every instruction is
  * acc = op(acc, b) where b is a register, an input pixel or an immediate.
+ * Arithmetic and comparison instructions are homogeneous: acc and b already
+ * hold class `cls` (the compiler inserts CVT / MATB conversions); b may come
+ * straight from an input only when the input's storage is a slot of that class.
  * Sentinel ("no data") semantics are evaluated exactly as the reference does
  * between blocks: raster/elemwise.py:235-299 (math/compare/logic),
  * :551-638 (Invert/IsData/IsNoData), :726-757 (FillNoData);
@@ -57,7 +60,7 @@ typedef struct GmArray {
  * :309-328 (Step) :387-399 (Classify) :482-515 (Reclassify).
  */
 enum GmOp {
-  GM_OP_LOAD = 0,   /* acc = b                                              */
+  GM_OP_LOAD = 0,   /* acc = convert(b: cls_b -> cls_out)                   */
   GM_OP_ST,         /* reg[aux] = acc                                       */
   GM_OP_OUT,        /* out[aux][pixel] = acc                                */
   GM_OP_CVT,        /* acc: cls_a -> cls_out (numpy astype)                 */
@@ -74,6 +77,7 @@ enum GmOp {
   GM_OP_STEP,       /* left/at/right around k0                              */
   GM_OP_CLASSIFY,   /* np.digitize against table aux                        */
   GM_OP_RECLASS,    /* sorted/dense table lookup, table aux                 */
+  GM_OP_MATB,       /* reg[aux] = convert(b: cls_b -> cls_out), acc untouched */
   GM_OP_COUNT_
 };
 
@@ -87,8 +91,11 @@ enum GmFlags {
   GM_F_B_BOOL    = 16,  /* Clip: b is a boolean mask                        */
   GM_F_RIGHT     = 32,  /* Classify: right=True                             */
   GM_F_SELECT    = 64,  /* Reclassify: select=True                          */
-  GM_F_ND_T      = 128  /* Mask/Overlay: sentinel given in class `cls` (k1/k2);
+  GM_F_ND_T      = 128, /* Mask/Overlay: sentinel given in class `cls` (k1/k2);
                            Reclassify: produce only the is-data boolean     */
+  GM_F_NAN       = 32   /* LOAD/MATB/CVT to a float class: the sentinel (k2 for
+                           b, k1 for acc) converts to NaN, so that the typed
+                           op that follows needs no sentinel test of its own */
 };
 
 #define GM_NREG       4
