@@ -22,10 +22,12 @@ _OPS = [
     "LOAD", "ST", "OUT", "CVT", "ADD", "SUB", "RSUB", "MUL", "DIV", "RDIV", "POW", "RPOW",
     "EXP", "LOG", "LOG10", "EQ", "NE", "GT", "GE", "LT", "LE", "AND", "OR", "XOR", "NOT",
     "ISDATA", "ISNODATA", "OVERLAY", "CLIP", "MASK", "MASKBELOW", "STEP", "CLASSIFY", "RECLASS",
+    "MATB",
 ]
 OP = {name: i for i, name in enumerate(_OPS)}
 SRC_NONE, SRC_REG, SRC_INPUT, SRC_IMM = 0, 1, 2, 3
 F_ND_A, F_ND_B, F_CLOSE, F_ND_FINITE, F_B_BOOL, F_RIGHT, F_SELECT, F_ND_T = 1, 2, 4, 8, 16, 32, 64, 128
+F_NAN = 32  # LOAD / MATB / CVT: sentinel -> NaN (shares the bit of F_RIGHT)
 
 DENSE_TABLE_LIMIT = 4096
 
@@ -153,8 +155,16 @@ _UNARY_MATH = {"exp": "EXP", "log": "LOG", "log10": "LOG10"}
 
 
 class _Compiler(object):
-    def __init__(self, leaves):
+    """Lowers an expression DAG to the accumulator machine.
+
+    ``word`` is the slot width the program is compiled for (4 or 8 bytes); a
+    staged input can be used directly as the b operand of an instruction only
+    when its storage already is a slot of the class the instruction computes in,
+    otherwise it is first converted into a scratch register (MATB)."""
+
+    def __init__(self, leaves, word=4):
         self.leaves = leaves  # list of _Typed for every input
+        self.word = word
         self.instr = []
         self.tables = []      # dicts with numpy arrays (kept alive until launch)
         self.free_regs = list(range(_native.GM_NREG))
@@ -189,21 +199,9 @@ class _Compiler(object):
             raise FusionLimit("out of registers")
         return self.free_regs.pop(0)
 
-    def type_of(self, x):
-        """_Typed of an operand without emitting code (leaves and cached nodes)."""
-        if isinstance(x, Leaf):
-            return self.leaves[x.index]
-        return None
-
-    def operand(self, x):
-        """Make ``x`` available as the b operand.  Returns (src tuple, _Typed|None, k0)
-        where _Typed is None for scalars."""
-        if isinstance(x, Leaf):
-            return (SRC_INPUT, x.index), self.leaves[x.index], 0
-        if isinstance(x, Node):
-            reg, typed = self.in_reg[id(x)]
-            return (SRC_REG, reg), typed, 0
-        return (SRC_IMM, 0), None, x
+    def free_reg(self, reg):
+        self.free_regs.append(reg)
+        self.free_regs.sort()
 
     def release(self, x):
         """Called once per consumed use of a node that lives in a register."""
@@ -211,29 +209,60 @@ class _Compiler(object):
             self.uses[id(x)] -= 1
             if self.uses[id(x)] <= 0:
                 reg, _ = self.in_reg.pop(id(x))
-                self.free_regs.append(reg)
-                self.free_regs.sort()
+                self.free_reg(reg)
+
+    def is_complex(self, x):
+        return isinstance(x, Node) and id(x) not in self.in_reg
 
     def to_acc(self, x):
-        """Bring ``x`` into the accumulator; returns its _Typed."""
+        """Bring ``x`` into the accumulator in its own class.  Returns (typed, flags,
+        k1): the sentinel test a consuming instruction has to do on acc."""
         if isinstance(x, Leaf):
             t = self.leaves[x.index]
             self.emit("LOAD", cls_b=t.cls, cls_out=t.cls, src=(SRC_INPUT, x.index))
-            return t
-        if isinstance(x, Node):
+        elif isinstance(x, Node):
             if id(x) in self.in_reg:
                 reg, t = self.in_reg[id(x)]
                 self.emit("LOAD", cls_b=t.cls, cls_out=t.cls, src=(SRC_REG, reg))
                 self.release(x)
-                return t
-            t = self.node(x)
-            if self.uses.get(id(x), 1) > 1:
-                reg = self.alloc_reg()
-                self.emit("ST", cls_a=t.cls, cls_out=t.cls, aux=reg)
-                self.in_reg[id(x)] = (reg, t)
-                self.release(x)
-            return t
-        raise TypeError("scalar cannot be the accumulator operand")
+            else:
+                t = self.node(x)
+                if self.uses.get(id(x), 1) > 1:
+                    reg = self.alloc_reg()
+                    self.emit("ST", cls_a=t.cls, cls_out=t.cls, aux=reg)
+                    self.in_reg[id(x)] = (reg, t)
+                    self.release(x)
+        else:
+            raise TypeError("scalar cannot be the accumulator operand")
+        s = sentinel(t.dtype, t.nodata)
+        if s is None:
+            return t, 0, 0
+        return t, F_ND_A, _bits(s, t.cls)
+
+    def acc_to_class(self, t, want):
+        """Convert acc from the class of ``t`` to ``want``; returns the (flags, k1)
+        sentinel test still to be done on the converted acc.  A sentinel entering a
+        float class from another class becomes NaN (no test needed afterwards)."""
+        s = sentinel(t.dtype, t.nodata)
+        if t.cls == want:
+            return (F_ND_A, _bits(s, want)) if s is not None else (0, 0)
+        nanify = s is not None and want in (C_F32, C_F64)
+        last = self.instr[-1] if self.instr else None
+        if last is not None and last["op"] == OP["LOAD"] and last["src_kind"] in (SRC_INPUT, SRC_REG) \
+                and last["cls_out"] == t.cls:
+            # fold the conversion into the load that just produced acc
+            last["cls_out"] = want
+            if nanify:
+                last["flags"] |= F_ND_B | F_NAN
+                last["k"][2] = _bits(s, t.cls)
+            if want in _WIDE:
+                self.wide = True
+        else:
+            self.emit("CVT", cls_a=t.cls, cls_out=want, flags=(F_ND_A | F_NAN) if nanify else 0,
+                      k=(0, _bits(s, t.cls) if nanify else 0))
+        if s is not None and not nanify:
+            return F_ND_A, _bits(s, want)   # injective integer widening
+        return 0, 0
 
     def spill_to_reg(self, x):
         """Evaluate node ``x`` and park it in a register (if not there yet)."""
@@ -246,21 +275,53 @@ class _Compiler(object):
         if self.uses.get(id(x), 1) <= 1:
             self.uses[id(x)] = 1
 
-    def binary_operands(self, a, b):
-        """Decide which operand is accumulated; returns (typed_a, typed_b|None,
-        src, k0, swapped) with the accumulator operand loaded."""
-        a_complex = isinstance(a, Node) and id(a) not in self.in_reg
-        b_complex = isinstance(b, Node) and id(b) not in self.in_reg
+    def _direct(self, src, typed, want):
+        """Can (src, typed) be read as a slot of class ``want`` without conversion?"""
+        if typed.cls != want:
+            return False
+        if src[0] == SRC_REG:
+            return True
+        return typed.dtype.itemsize == self.word and typed.dtype != np.dtype("u4")
+
+    def b_operand(self, x, want, nan_ok=True):
+        """Make ``x`` available as operand b in class ``want``.  Returns
+        (src, typed|None, k0, flags, k2, scratch register to free or None)."""
+        if _is_scalar(x):
+            return (SRC_IMM, 0), None, x, 0, 0, None
+        if isinstance(x, Leaf):
+            typed, src = self.leaves[x.index], (SRC_INPUT, x.index)
+        else:
+            reg, typed = self.in_reg[id(x)]
+            src = (SRC_REG, reg)
+        s = sentinel(typed.dtype, typed.nodata)
+        if self._direct(src, typed, want):
+            return src, typed, 0, (F_ND_B if s is not None else 0), (_bits(s, want) if s is not None else 0), None
+        nanify = nan_ok and s is not None and want != typed.cls and want in (C_F32, C_F64)
+        scratch = self.alloc_reg()
+        self.emit("MATB", cls_b=typed.cls, cls_out=want, src=src, aux=scratch,
+                  flags=(F_ND_B | F_NAN) if nanify else 0, k=(0, 0, _bits(s, typed.cls) if nanify else 0))
+        flags, k2 = 0, 0
+        if s is not None and not nanify:
+            flags, k2 = F_ND_B, _bits(s, want)
+        return (SRC_REG, scratch), typed, 0, flags, k2, scratch
+
+    def order_operands(self, a, b):
+        """Pick the accumulator operand; returns (a, b, swapped) with b no longer complex."""
         if _is_scalar(a) and _is_scalar(b):
             raise TypeError("at least one operand must be a raster")
         swapped = False
-        if b_complex and a_complex:
+        if self.is_complex(a) and self.is_complex(b):
             self.spill_to_reg(b)
-        elif b_complex or _is_scalar(a):
+        elif self.is_complex(b) or _is_scalar(a):
             a, b, swapped = b, a, True
-        ta = self.to_acc(a)
-        src, tb, k0 = self.operand(b)
-        return ta, tb, src, k0, swapped, b
+        return a, b, swapped
+
+    def operand_type(self, x):
+        if isinstance(x, Leaf):
+            return self.leaves[x.index]
+        if isinstance(x, Node) and id(x) in self.in_reg:
+            return self.in_reg[id(x)][1]
+        return None
 
     # -- per-op lowering -----------------------------------------------------------
     def node(self, n):
@@ -277,87 +338,128 @@ class _Compiler(object):
             raise NotImplementedError(n.op)
         return handler(n)
 
-    def _nd_flags(self, ta, tb):
-        flags, k1, k2 = 0, 0, 0
-        if ta is not None:
-            s = sentinel(ta.dtype, ta.nodata)
-            if s is not None:
-                flags |= F_ND_A
-                k1 = _bits(s, ta.cls)
-        if tb is not None:
-            s = sentinel(tb.dtype, tb.nodata)
-            if s is not None:
-                flags |= F_ND_B
-                k2 = _bits(s, tb.cls)
-        return flags, k1, k2
+    def _binary(self, op, a, b, choose_class, out_cls, fill_bits, scalar_bits):
+        """acc = op(a, b).  ``choose_class(ta, tb, scalar)`` picks the compute class
+        once the accumulator operand has been evaluated (tb is None for a scalar b);
+        ``fill_bits(T)`` / ``scalar_bits(v, T)`` encode the fill and an immediate."""
+        a, b, swapped = self.order_operands(a, b)
+        if swapped:
+            op = _REVERSED[op]
+        ta, _, _ = self.to_acc(a)
+        tb = self.operand_type(b)
+        T = choose_class(ta, tb, b if tb is None else None)
+        fa, k1 = self.acc_to_class(ta, T)
+        src, tb, k0, fb, k2, scratch = self.b_operand(b, T)
+        if tb is None:
+            k0 = scalar_bits(k0, T)
+        self.emit(op, cls=T, cls_a=T, cls_b=T, cls_out=T if out_cls is None else out_cls, src=src,
+                  flags=fa | fb, k=(k0, k1, k2, fill_bits(T)))
+        if scratch is not None:
+            self.free_reg(scratch)
+        self.release(b)
+        return T
 
     def math(self, n):
         dtype = np.dtype(n.params["dtype"])
         fill = n.params["fillvalue"]
         T = dtype_class(dtype)
         a, b = n.children
-        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
-        op = _MATH[n.op]
-        if swapped:
-            op = _REVERSED[op]
-        flags, k1, k2 = self._nd_flags(ta, tb)
-        cls_b = T
-        if tb is None:
+        if n.op == "power" and self._power_needs_mask(a, b, T):
+            return self._masked_power(n, dtype, fill, T)
+
+        def scalar_bits(v, cls):
             with np.errstate(all="ignore"):
-                k0 = _bits(np.asarray(k0).astype(dtype)[()], T)
-        else:
-            cls_b = tb.cls
-        self.emit(op, cls=T, cls_a=ta.cls, cls_b=cls_b, cls_out=T, src=src, flags=flags,
-                  k=(k0, k1, k2, _bits(fill, T)))
-        self.release(b_used)
+                return _bits(np.asarray(v).astype(dtype)[()], cls)
+
+        self._binary(_MATH[n.op], a, b, lambda ta, tb, sc: T, None, lambda cls: _bits(fill, cls),
+                     scalar_bits)
+        return _Typed(dtype, fill)
+
+    def _needs_nan(self, x, T):
+        t = self.operand_type(x)
+        if t is None:
+            return isinstance(x, Node)  # unknown until evaluated: be conservative
+        return t.cls != T and sentinel(t.dtype, t.nodata) is not None
+
+    def _power_needs_mask(self, a, b, T):
+        # pow(NaN, 0) == pow(1, NaN) == 1: the sentinel -> NaN substitution used when an
+        # operand changes class would leak through np.power
+        if T not in (C_F32, C_F64):
+            return False
+        return any(not _is_scalar(x) and self._needs_nan(x, T) for x in (a, b))
+
+    def _masked_power(self, n, dtype, fill, T):
+        a, b = n.children
+        if any(isinstance(x, Node) for x in (a, b)):
+            raise FusionLimit("power with mixed operand classes is evaluated on its own")
+        # validity mask of the raster operands, then the power on converted operands
+        rasters = [x for x in (a, b) if isinstance(x, Leaf)]
+        mask_reg = self.alloc_reg()
+        for i, x in enumerate(rasters):
+            t, fa, k1 = self.to_acc(x)
+            self.emit("ISDATA", cls_a=t.cls, flags=fa, k=(0, k1))
+            if i > 0:
+                self.emit("AND", src=(SRC_REG, mask_reg))
+            self.emit("ST", aux=mask_reg)
+
+        def scalar_bits(v, cls):
+            with np.errstate(all="ignore"):
+                return _bits(np.asarray(v).astype(dtype)[()], cls)
+
+        saved = [self.leaves[x.index] for x in rasters]
+        try:
+            for x in rasters:  # operands enter the power without sentinel handling
+                self.leaves[x.index] = _Typed(saved[rasters.index(x)].dtype, None)
+            self._binary(_MATH[n.op], a, b, lambda ta, tb, sc: T, None, lambda cls: _bits(fill, cls),
+                         scalar_bits)
+        finally:
+            for x, t in zip(rasters, saved):
+                self.leaves[x.index] = t
+        self.emit("CLIP", cls_a=T, cls_b=C_I32, cls_out=T, src=(SRC_REG, mask_reg), flags=F_B_BOOL,
+                  k=(0, _bits(fill, T)))
+        self.free_reg(mask_reg)
         return _Typed(dtype, fill)
 
     def unary_math(self, n):
         dtype = np.dtype(n.params["dtype"])
         fill = n.params["fillvalue"]
         T = dtype_class(dtype)
-        ta = self.to_acc(n.children[0])
-        flags, k1, _ = self._nd_flags(ta, None)
-        self.emit(_UNARY_MATH[n.op], cls=T, cls_a=ta.cls, cls_out=T, flags=flags,
-                  k=(0, k1, 0, _bits(fill, T)))
+        ta, _, _ = self.to_acc(n.children[0])
+        fa, k1 = self.acc_to_class(ta, T)
+        self.emit(_UNARY_MATH[n.op], cls=T, cls_a=T, cls_out=T, flags=fa, k=(0, k1, 0, _bits(fill, T)))
         return _Typed(dtype, fill)
 
     def compare(self, n):
         a, b = n.children
-        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
-        op = _COMPARE[n.op]
-        if swapped:
-            op = _REVERSED[op]
-        terms = [ta.dtype, tb.dtype if tb is not None else k0]
-        cmp_dtype = _compare_dtype(terms)
-        T = dtype_class(cmp_dtype)
-        cls_b = tb.cls if tb is not None else T
-        if tb is None:
+
+        def choose(ta, tb, scalar):
+            # NumPy compares in the common type of both operands (python scalars are weak)
+            T = dtype_class(_compare_dtype([ta.dtype, tb.dtype if tb is not None else scalar]))
             if T in (C_I32, C_I64):
-                v = int(k0)
-                if T == C_I32 and not (-2 ** 31 <= v < 2 ** 31):
-                    T = cls_b = C_I64
-                if T == C_I64 and ta.cls == C_I32 and -2 ** 31 <= v < 2 ** 31:
-                    T = cls_b = C_I32   # exact in 32 bits, keeps the program narrow
-                k0 = _bits(v, T)
-            else:
-                k0 = _bits(k0, T)
-        elif T == C_I64 and ta.cls == C_I32 and tb.cls == C_I32:
-            T = C_I32
-        flags, k1, k2 = self._nd_flags(ta, tb)
+                fits = scalar is None or -2 ** 31 <= int(scalar) < 2 ** 31
+                narrow = ta.cls == C_I32 and (tb is None or tb.cls == C_I32)
+                if T == C_I32 and not fits:
+                    T = C_I64
+                elif T == C_I64 and fits and narrow:
+                    T = C_I32   # exact in 32 bits, keeps the program narrow
+            return T
+
         fill = 1 if n.op == "not_equal" else 0
-        self.emit(op, cls=T, cls_a=ta.cls, cls_b=cls_b, cls_out=C_I32, src=src, flags=flags,
-                  k=(k0, k1, k2, fill))
-        self.release(b_used)
+        self._binary(_COMPARE[n.op], a, b, choose, C_I32, lambda cls: fill,
+                     lambda v, cls: _bits(int(v) if cls in (C_I32, C_I64) else v, cls))
         return _Typed(bool, None)
 
     def logic(self, n):
         a, b = n.children
-        ta, tb, src, k0, swapped, b_used = self.binary_operands(a, b)
+        a, b, swapped = self.order_operands(a, b)
+        self.to_acc(a)
+        src, tb, k0, _, _, scratch = self.b_operand(b, C_I32)
         if tb is None:
             k0 = 1 if k0 else 0
-        self.emit(_LOGIC[n.op], cls_a=ta.cls, cls_b=C_I32, src=src, k=(k0,))
-        self.release(b_used)
+        self.emit(_LOGIC[n.op], src=src, k=(k0,))
+        if scratch is not None:
+            self.free_reg(scratch)
+        self.release(b)
         return _Typed(bool, None)
 
     def op_invert(self, n):
@@ -372,9 +474,8 @@ class _Compiler(object):
             if op == "ISNODATA":
                 self.emit("NOT")
             return _Typed(bool, None)
-        ta = self.to_acc(child)
-        flags, k1, _ = self._nd_flags(ta, None)
-        self.emit(op, cls_a=ta.cls, flags=flags, k=(0, k1))
+        t, fa, k1 = self.to_acc(child)
+        self.emit(op, cls_a=t.cls, flags=fa, k=(0, k1))
         return _Typed(bool, None)
 
     def op_isdata(self, n):
@@ -387,12 +488,12 @@ class _Compiler(object):
         dtype = np.dtype(n.params["dtype"])
         fill = get_dtype_max(dtype)
         T = dtype_class(dtype)
-        complex_children = [c for c in n.children if isinstance(c, Node) and id(c) not in self.in_reg]
-        for c in complex_children:
-            self.spill_to_reg(c)
+        for c in n.children:
+            if self.is_complex(c):
+                self.spill_to_reg(c)
         self.emit("LOAD", cls_b=T, cls_out=T, src=(SRC_IMM, 0), k=(_bits(fill, T),))
         for c in n.children:
-            src, tc, _ = self.operand(c)
+            tc = self.operand_type(c)
             flags, cmp_cls, k2, k4 = 0, tc.cls, 0, 0
             if tc.nodata is not None:
                 if tc.dtype.kind == "f":
@@ -404,8 +505,18 @@ class _Compiler(object):
                     s = sentinel(tc.dtype, tc.nodata)
                     if s is not None:
                         flags, k2 = F_ND_T, _bits(s, cmp_cls)
-            self.emit("OVERLAY", cls=cmp_cls, cls_a=T, cls_b=tc.cls, cls_out=T, src=src, flags=flags,
+            saved = None
+            if isinstance(c, Leaf):  # the sentinel test happens inside OVERLAY, in cmp_cls
+                saved, self.leaves[c.index] = self.leaves[c.index], _Typed(tc.dtype, None)
+            try:
+                src, _, _, _, _, scratch = self.b_operand(c, cmp_cls, nan_ok=False)
+            finally:
+                if saved is not None:
+                    self.leaves[c.index] = saved
+            self.emit("OVERLAY", cls=cmp_cls, cls_a=T, cls_b=cmp_cls, cls_out=T, src=src, flags=flags,
                       k=(0, 0, k2, 0, k4))
+            if scratch is not None:
+                self.free_reg(scratch)
             self.release(c)
         return _Typed(dtype, fill)
 
@@ -413,18 +524,24 @@ class _Compiler(object):
         store, mask = n.children
         mask_is_reclass = (isinstance(mask, Node) and mask.op == "reclassify"
                            and self.uses.get(id(mask), 1) <= 1 and id(mask) not in self.in_reg)
-        tm_bool = None
         if mask_is_reclass:
             self.op_reclassify(mask, nd_only=True)
             reg = self.alloc_reg()
             self.emit("ST", aux=reg)
-            tm_bool = _Typed(bool, None)
-            self.in_reg[id(mask)] = (reg, tm_bool)
+            self.in_reg[id(mask)] = (reg, _Typed(bool, None))
             self.uses[id(mask)] = 1
-        elif isinstance(mask, Node) and id(mask) not in self.in_reg:
+        elif self.is_complex(mask):
             self.spill_to_reg(mask)
-        ts = self.to_acc(store)
-        src, tm, _ = self.operand(mask)
+        ts, _, _ = self.to_acc(store)
+        tm = self.operand_type(mask)
+        saved = None
+        if isinstance(mask, Leaf):  # CLIP tests the sentinel itself, in the mask's own class
+            saved, self.leaves[mask.index] = self.leaves[mask.index], _Typed(tm.dtype, None)
+        try:
+            src, _, _, _, _, scratch = self.b_operand(mask, tm.cls, nan_ok=False)
+        finally:
+            if saved is not None:
+                self.leaves[mask.index] = saved
         flags, k2 = 0, 0
         if tm.dtype == bool:
             flags = F_B_BOOL
@@ -435,6 +552,8 @@ class _Compiler(object):
         nd = _cast_into(ts.nodata, ts.dtype) if ts.nodata is not None else 0
         self.emit("CLIP", cls_a=ts.cls, cls_b=tm.cls, cls_out=ts.cls, src=src, flags=flags,
                   k=(0, _bits(nd, ts.cls), k2))
+        if scratch is not None:
+            self.free_reg(scratch)
         self.release(mask)
         return _Typed(ts.dtype, ts.nodata)
 
@@ -448,7 +567,7 @@ class _Compiler(object):
             out_dtype = get_int_dtype(value)
         fill = 1 if value == 0 else 0
         out_cls = dtype_class(out_dtype)
-        ta = self.to_acc(n.children[0])
+        ta, _, _ = self.to_acc(n.children[0])
         flags, cmp_cls, k1, k4 = 0, ta.cls, 0, 0
         if ta.nodata is not None:
             if ta.dtype.kind == "f":
@@ -473,7 +592,7 @@ class _Compiler(object):
 
     def op_maskbelow(self, n):
         value = n.params["value"]
-        ta = self.to_acc(n.children[0])
+        ta, _, _ = self.to_acc(n.children[0])
         T = self._scalar_compare_class(ta, value)
         nd = _cast_into(ta.nodata, ta.dtype)
         self.emit("MASKBELOW", cls=T, cls_a=ta.cls, cls_out=ta.cls,
@@ -482,9 +601,10 @@ class _Compiler(object):
 
     def op_step(self, n):
         p = n.params
-        ta = self.to_acc(n.children[0])
+        ta, _, _ = self.to_acc(n.children[0])
         T = self._scalar_compare_class(ta, p["value"])
-        flags, k1, _ = self._nd_flags(ta, None)
+        s = sentinel(ta.dtype, ta.nodata)
+        flags, k1 = (F_ND_A, _bits(s, ta.cls)) if s is not None else (0, 0)
         cast = lambda v: _bits(_cast_into(v, ta.dtype), ta.cls)  # noqa: E731
         self.emit("STEP", cls=T, cls_a=ta.cls, cls_out=ta.cls, flags=flags,
                   k=(_bits(p["value"], T), k1, cast(p["left"]), cast(p["at"]), cast(p["right"])))
@@ -494,7 +614,7 @@ class _Compiler(object):
         bins = np.asarray(n.params["bins"])
         out_dtype = get_uint_dtype(len(bins) + 2)
         fill = get_dtype_max(out_dtype)
-        ta = self.to_acc(n.children[0])
+        ta, _, _ = self.to_acc(n.children[0])
         small = ta.dtype == bool or (ta.dtype.kind in "iu" and ta.dtype.itemsize <= 2)
         if bins.dtype.kind in "iu" and ta.dtype.kind in "iub":
             fits = len(bins) == 0 or (bins.min() >= -2 ** 31 and bins.max() < 2 ** 31)
@@ -515,7 +635,8 @@ class _Compiler(object):
         self.tables.append(table)
         if len(self.tables) > _native.GM_MAX_TABLES:
             raise FusionLimit("too many tables")
-        flags, k1, _ = self._nd_flags(ta, None)
+        s = sentinel(ta.dtype, ta.nodata)
+        flags, k1 = (F_ND_A, _bits(s, ta.cls)) if s is not None else (0, 0)
         if n.params["right"]:
             flags |= F_RIGHT
         self.emit("CLASSIFY", cls=T, cls_a=ta.cls, cls_out=C_I32, flags=flags, aux=len(self.tables) - 1,
@@ -527,16 +648,18 @@ class _Compiler(object):
         dtype = np.dtype(p["dtype"])
         fill = p["fillvalue"]
         pairs = p["data"]
-        source = np.asarray([s for s, _ in pairs])
-        target = np.asarray([t for _, t in pairs])
-        ta = self.to_acc(n.children[0])
-        nd = ta.nodata
-        if nd is not None and not np.any(source == nd):
-            source = np.append(source, nd)
-            target = np.append(target, fill)
+        source = np.asarray([s for s, _ in pairs]).astype(np.int64)
+        target = np.asarray([t for _, t in pairs]).astype(dtype)
+        ta, _, _ = self.to_acc(n.children[0])
+        # the source's own sentinel maps onto the fill unless the user mapped it
+        # explicitly (raster/misc.py:495-497); it is tested by the instruction itself
+        # so that a far-away sentinel does not blow up the dense table
+        flags, k1 = 0, 0
+        s = sentinel(ta.dtype, ta.nodata)
+        if ta.nodata is not None and not np.any(source == ta.nodata) and s is not None:
+            flags, k1 = F_ND_A, _bits(int(s), C_I64)
         order = np.argsort(source)
-        source = source[order].astype(np.int64)
-        target = target[order].astype(dtype)
+        source, target = source[order], target[order]
         T = dtype_class(dtype)
         with np.errstate(all="ignore"):
             is_fill = target == dtype.type(fill)
@@ -557,12 +680,12 @@ class _Compiler(object):
         self.tables.append(table)
         if len(self.tables) > _native.GM_MAX_TABLES:
             raise FusionLimit("too many tables")
-        flags = (F_SELECT if p["select"] else 0) | (F_ND_T if nd_only else 0)
+        flags |= (F_SELECT if p["select"] else 0) | (F_ND_T if nd_only else 0)
         out_cls = C_I32 if nd_only else T
         if not nd_only:
             self.wide = True
         self.emit("RECLASS", cls=C_I32 if nd_only else C_I64, cls_a=ta.cls, cls_out=out_cls, flags=flags,
-                  aux=len(self.tables) - 1, k=(0, 0, 0, _bits(fill, T) if not nd_only else 0))
+                  aux=len(self.tables) - 1, k=(0, k1, 0, _bits(fill, T) if not nd_only else 0))
         return _Typed(bool, None) if nd_only else _Typed(dtype, fill)
 
 
@@ -589,25 +712,32 @@ def _build_program(compiler, n_inputs, n_outputs):
     return prog
 
 
-def compile_expression(roots, leaf_types):
-    """Lower ``roots`` (list of Node) to a GmProgram with one output per root.
-
-    Returns (program, compiler, [result _Typed per root])."""
-    comp = _Compiler([_Typed(d, nd) for d, nd in leaf_types])
+def _compile(roots, leaf_types, word):
+    comp = _Compiler([_Typed(d, nd) for d, nd in leaf_types], word)
     for r in roots:
         comp.count_uses(r)
     results = []
     for i, r in enumerate(roots):
-        if isinstance(r, Leaf):
-            t = comp.to_acc(r)
-        else:
-            t = comp.to_acc(r)
+        t, _, _ = comp.to_acc(r)
         results.append(t)
         comp.emit("OUT", cls_a=t.cls, cls_out=t.cls, aux=i)
-    if len(leaf_types) > _native.GM_MAX_INPUTS or len(roots) > _native.GM_MAX_OUTPUTS:
-        raise FusionLimit("too many inputs/outputs")
     # inputs whose natural class is wide force the 64-bit machine
     if any(dtype_class(d) in _WIDE for d, _ in leaf_types):
+        comp.wide = True
+    return comp, results
+
+
+def compile_expression(roots, leaf_types):
+    """Lower ``roots`` (list of Node) to a GmProgram with one output per root.
+
+    Returns (program, compiler, [result _Typed per root]).  The program is first
+    compiled for 32-bit slots; if any class turns out to be 64-bit it is compiled
+    again for 64-bit slots (operand directness depends on the slot width)."""
+    if len(leaf_types) > _native.GM_MAX_INPUTS or len(roots) > _native.GM_MAX_OUTPUTS:
+        raise FusionLimit("too many inputs/outputs")
+    comp, results = _compile(roots, leaf_types, 4)
+    if comp.wide:
+        comp, results = _compile(roots, leaf_types, 8)
         comp.wide = True
     return _build_program(comp, len(leaf_types), len(roots)), comp, results
 
