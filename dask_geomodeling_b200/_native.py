@@ -132,6 +132,12 @@ SYMBOLS = {
     "gm_memcpy2d_h2d": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "gm_fill": (_i, [_vp, ctypes.c_int32, _vp, _i64, _vp]),
     "gm_eval_program": (_i, [_P(GmProgram), _P(GmArray), _P(GmArray), _i64, _vp]),
+    "gm_set_eval_mode": (_i, [_i]),
+    "gm_get_eval_mode": (_i, []),
+    "gm_jit_source": (_i, [_P(GmProgram), _P(ctypes.c_int32), _P(ctypes.c_int32), ctypes.c_char_p, _i64,
+                           _P(_i64)]),
+    "gm_jit_check": (_i, [_P(GmProgram), _P(ctypes.c_int32), _P(ctypes.c_int32), _P(_i64)]),
+    "gm_jit_compile_count": (_i64, []),
     "gm_resample_nn": (_i, [_P(GmArray), _P(GmArray), _vp, _d, _d, _d, _d, _vp]),
     "gm_hillshade": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _d, _d, _d, _d, _d, _vp]),
     "gm_moving_max": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _i, _vp]),

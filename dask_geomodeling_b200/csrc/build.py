@@ -46,8 +46,20 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
+def _embed_prelude():
+    """gm_jit_prelude.cuh -> build/gm_jit_prelude.inc (a C++ raw string literal that
+    gm_jit.cu includes; NVRTC compiles it at run time)."""
+    src = os.path.join(HERE, "gm_jit_prelude.cuh")
+    dst = os.path.join(BUILD, "gm_jit_prelude.inc")
+    text = 'R"GMJIT(' + open(src).read() + ')GMJIT"\n'
+    if not os.path.exists(dst) or open(dst).read() != text:
+        with open(dst, "w") as f:
+            f.write(text)
+
+
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
+    _embed_prelude()
     nvcc = _nvcc()
     hdr_time = _deps_mtime()
     jobs = []
@@ -79,7 +91,7 @@ def build(force=False, verbose=False):
     stale_lib = not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
     if jobs or stale_lib or force:
         link = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-                "-Xcompiler", "-fPIC", "-o", LIB] + objs
+                "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-ldl"]
         run(link)
     return LIB
 

@@ -19,6 +19,7 @@
 // :726-757 and raster/misc.py:98-123, :208-222, :245-251, :309-328, :387-399,
 // :482-515.
 #include "gm_common.cuh"
+#include "gm_jit.h"
 #include <type_traits>
 
 namespace gm {
@@ -886,12 +887,38 @@ static int launch_eval(EvalParams& p, const GmProgram* prog, size_t table_bytes,
   return 0;
 }
 
+// Back-end selection: GM_EVAL_AUTO specialises (NVRTC) from kJitMinPixels pixels on and
+// interprets below that, where a launch is latency-bound and a compile would not pay.
+static std::atomic<int> g_eval_mode{-1};
+static const int64_t kJitMinPixels = 1 << 18;
+
+static int eval_mode() {
+  int m = g_eval_mode.load(std::memory_order_relaxed);
+  if (m >= 0) return m;
+  const char* env = getenv("GM_EVAL");
+  m = GM_EVAL_AUTO;
+  if (env && !strcmp(env, "interp")) m = GM_EVAL_INTERPRET;
+  else if (env && !strcmp(env, "jit")) m = GM_EVAL_SPECIALISE;
+  g_eval_mode.store(m);
+  return m;
+}
+
+extern "C" int gm_set_eval_mode(int mode) {
+  if (mode < GM_EVAL_AUTO || mode > GM_EVAL_SPECIALISE) return fail("gm_set_eval_mode: bad mode");
+  g_eval_mode.store(mode);
+  return 0;
+}
+extern "C" int gm_get_eval_mode(void) { return eval_mode(); }
+
 extern "C" int gm_eval_program(const GmProgram* prog, const GmArray* inputs, GmArray* outputs,
                                int64_t n_pixels, void* stream) {
   if (ensure_init()) return 1;
   if (validate(prog, inputs)) return 1;
   if (n_pixels < 0) return fail("gm_eval_program: negative pixel count");
   cudaStream_t s = resolve_stream(stream);
+  const int mode = eval_mode();
+  const bool specialise = mode == GM_EVAL_SPECIALISE || (mode == GM_EVAL_AUTO && n_pixels >= kJitMinPixels);
+  const bool need_tables = !(specialise && jit_tables_baked(prog));
 
   EvalParams p;
   memset(&p, 0, sizeof(p));
@@ -937,7 +964,7 @@ extern "C" int gm_eval_program(const GmProgram* prog, const GmArray* inputs, GmA
     p.out_dtype[i] = outputs[i].dtype;
   }
   size_t table_bytes = 0;
-  for (int t = 0; t < prog->n_tables && !rc; ++t) {
+  for (int t = 0; t < prog->n_tables && !rc && need_tables; ++t) {
     const GmTable& g = prog->tables[t];
     DevTable& d = p.tab[t];
     d.n = g.n; d.kind = g.kind; d.base = g.base;
@@ -957,7 +984,11 @@ extern "C" int gm_eval_program(const GmProgram* prog, const GmArray* inputs, GmA
   }
   if (rc) { cleanup(); return 1; }
 
-  if (n_pixels > 0) {
+  if (n_pixels > 0 && specialise) {
+    const void* tk[GM_MAX_TABLES] = {}; const void* tv[GM_MAX_TABLES] = {}; const void* th[GM_MAX_TABLES] = {};
+    for (int t = 0; t < prog->n_tables; ++t) { tk[t] = p.tab[t].keys; tv[t] = p.tab[t].vals; th[t] = p.tab[t].hit; }
+    if (jit_launch(prog, p.in, p.in_dtype, p.out, p.out_dtype, tk, tv, th, n_pixels, s)) { cleanup(); return 1; }
+  } else if (n_pixels > 0) {
     // widest tile that fits shared memory: more pixels per thread = less decode per pixel
     if (prog->word == 4) {
       rc = launch_eval<4, 16>(p, prog, table_bytes, s);

@@ -174,6 +174,23 @@ int  gm_fill(void* dst, int32_t dtype, const void* value, int64_t count, void* s
 int  gm_eval_program(const GmProgram* prog, const GmArray* inputs,
                      GmArray* outputs, int64_t n_pixels, void* stream);
 
+/* Evaluator back ends.  Both execute the same GmProgram with the same results:
+ *   GM_EVAL_INTERPRET   one resident kernel interprets the bytecode (no compile);
+ *   GM_EVAL_SPECIALISE  the bytecode is translated to a straight-line kernel,
+ *                       compiled once for sm_100a with NVRTC and cached;
+ *   GM_EVAL_AUTO        (default; env GM_EVAL=auto|interp|jit) specialise from
+ *                       2^18 pixels on, interpret below.                      */
+enum GmEvalMode { GM_EVAL_AUTO = 0, GM_EVAL_INTERPRET = 1, GM_EVAL_SPECIALISE = 2 };
+int  gm_set_eval_mode(int mode);
+int  gm_get_eval_mode(void);
+/* inspection: generated CUDA source of a program / NVRTC compile check (neither
+ * needs a GPU); number of kernels compiled so far                            */
+int  gm_jit_source(const GmProgram* prog, const int32_t* in_dtype, const int32_t* out_dtype,
+                   char* buffer, int64_t capacity, int64_t* length);
+int  gm_jit_check(const GmProgram* prog, const int32_t* in_dtype, const int32_t* out_dtype,
+                  int64_t* cubin_bytes);
+int64_t gm_jit_compile_count(void);
+
 /* input adaptor: nearest-neighbour resample of a source window into the
  * request grid; equals the aligned crop/pad for aligned requests
  * (raster/sources.py:119-149, MemorySource).  src_i = floor(i0 + (i+0.5)*si)  */
