@@ -257,6 +257,28 @@ def run_b200(args):
     view, _ = workloads.cfg2_views(ints, floats)
     request = workloads.request(size, size)
 
+    # ---- end to end through the Block API: host arrays in, host array out ----------
+    # exactly what a user of the reference does: view.get_data(**request) on NumPy
+    # inputs; every step uploads both rasters (pinned H2D) and downloads the result
+    h2d = ints.nbytes + floats.nbytes
+    d2h = pixels  # one bool per pixel
+    e2e_s = float("nan")
+    e2e_checksum = None
+    if not args.profile:
+        result = view.get_data(**request)  # warm-up: tokens, page-locking, NVRTC, pools
+        result = view.get_data(**request)
+        _native.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            result = view.get_data(**request)
+        _native.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_checksum = int(result["values"].sum())
+        d2h = result["values"].nbytes
+        del result
+
     # ---- kernel-resident measurement: compile once, launch K times -------------
     graph, name = view.get_compute_graph(**request)
     fused = fusion.optimize(graph, name)
@@ -296,24 +318,7 @@ def run_b200(args):
         clocks = sampler.stop() if sampler else None
         checksum = int(np.asarray(out.to_host()).sum())
         del inputs, leaf_payloads, out
-
-    # ---- end to end through the Block API: host arrays in, host array out ----------
-    h2d = ints.nbytes + floats.nbytes
-    d2h = pixels  # one bool per pixel
-    e2e_s = float("nan")
-    if not args.profile:
-        with _native.use_stream(stream.cuda_stream):
-            view.get_data(**request)  # warm-up: tokens, pinning, pool
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                result = view.get_data(**request)
-            torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
-        assert int(result["values"].sum()) == checksum, "e2e result differs from the resident result"
-        d2h = result["values"].nbytes
+    assert e2e_checksum is None or e2e_checksum == checksum, "e2e result differs from the resident result"
 
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -343,7 +348,7 @@ def run_b200(args):
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                         "bytes_per_pixel": BYTES_PER_PIXEL, "kernel": "eval_kernel<4,2>"},
+                         "bytes_per_pixel": BYTES_PER_PIXEL, "kernel": "gm_fused (NVRTC-specialised evaluator, V=4 px x U=4 groups per thread)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": int(launches),
