@@ -6,8 +6,16 @@
 #include <cfloat>
 #include <cmath>
 #include <limits>
+#include <algorithm>
+#include <type_traits>
 
 namespace gm {
+
+template <typename T> static T read_scalar(const void* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+static dim3 grid3(int W, int H, int bands, int bx, int by) {
+  int gz = bands < 65535 ? bands : 65535;
+  return dim3((W + bx - 1) / bx, (H + by - 1) / by, gz);
+}
 
 template <typename T> struct Lowest { static __host__ __device__ T value() { return std::numeric_limits<T>::lowest(); } };
 
@@ -21,14 +29,17 @@ template <typename T> struct HillArith;
 template <> struct HillArith<float> {
   typedef float acc;
   static __device__ __forceinline__ float div(float v, double res) { return v / (float)res; }
+  static __device__ __forceinline__ float mul(float v, double inv) { return v * (float)inv; }
 };
 template <> struct HillArith<double> {
   typedef double acc;
   static __device__ __forceinline__ float div(double v, double res) { return (float)(v / res); }
+  static __device__ __forceinline__ float mul(double v, double inv) { return (float)(v * inv); }
 };
 template <typename T> struct HillArith {  // integer rasters: arithmetic wraps in T, division in double
   typedef T acc;
   static __device__ __forceinline__ float div(T v, double res) { return (float)((double)v / res); }
+  static __device__ __forceinline__ float mul(T v, double inv) { return (float)((double)v * inv); }
 };
 
 template <typename T>
@@ -64,6 +75,94 @@ hillshade_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata,
     uint8_t out = 0;
     if (!(cang <= 0.0f)) out = (uint8_t)(int)(255.0f * cang);
     dst[(int64_t)b * out_plane + (int64_t)y * W + x] = out;
+  }
+}
+
+
+// Strip version (used for every dtype): a warp walks down a strip of 30 output columns,
+// each lane loading ONE source value per row (one coalesced 128-byte request) and getting
+// its two right-hand neighbours by shuffle, with the three live rows kept in registers:
+// 1.03 loads per pixel instead of 9.  The Horn gradient and the two divisions are the
+// reference's float32 expression; the shading uses the identity
+//   sqrt(x^2+y^2) * sin(atan2(y, x) - az) = y*cos(az) - x*sin(az)
+// and one rsqrt (a few ulp from the reference expression: SURVEY.md Appendix A-13 measured
+// <= 1 grey level on 4e-5 of the pixels for this form; the parity test allows 1e-3).
+constexpr int HS_COLS = 30;    // output columns per warp
+constexpr int HS_ROWS = 64;    // output rows per warp
+constexpr int HS_WARPS = 8;
+constexpr int HS_AHEAD = 8;   // source rows fetched per batch
+
+template <typename A> __device__ __forceinline__ A shfl_down_any(A v, int d) {
+  return __shfl_down_sync(0xffffffffu, v, d);
+}
+template <> __device__ __forceinline__ int8_t shfl_down_any<int8_t>(int8_t v, int d) { return (int8_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
+template <> __device__ __forceinline__ uint8_t shfl_down_any<uint8_t>(uint8_t v, int d) { return (uint8_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
+template <> __device__ __forceinline__ int16_t shfl_down_any<int16_t>(int16_t v, int d) { return (int16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
+template <> __device__ __forceinline__ uint16_t shfl_down_any<uint16_t>(uint16_t v, int d) { return (uint16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
+template <> __device__ __forceinline__ int64_t shfl_down_any<int64_t>(int64_t v, int d) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, d); }
+
+template <typename T>
+__global__ void __launch_bounds__(32 * HS_WARPS)
+hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
+                       T fill, int bands, int H, int W, double xres, double yres,
+                       double inv_xres, double inv_yres, int exact_inverse,
+                       float sin_alt, float cos_alt_zsf, float cos_az, float sin_az, float square_zsf) {
+  typedef typename HillArith<T>::acc A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SW = W + 2;
+  const int64_t in_plane = (int64_t)(H + 2) * SW, out_plane = (int64_t)H * W;
+  const int strips_x = (W + HS_COLS - 1) / HS_COLS;
+  const int64_t strip = (int64_t)blockIdx.x * HS_WARPS + warp;   // (band, y strip, x strip)
+  const int strips_y = (H + HS_ROWS - 1) / HS_ROWS;
+  if (strip >= (int64_t)bands * strips_y * strips_x) return;
+  const int sx = (int)(strip % strips_x);
+  const int sy = (int)((strip / strips_x) % strips_y);
+  const int b = (int)(strip / ((int64_t)strips_x * strips_y));
+  const int x0 = sx * HS_COLS, y0 = sy * HS_ROWS;
+  const int col = x0 + lane;                       // source column of this lane
+  const bool col_ok = col < SW;
+  const bool writes = lane < HS_COLS && x0 + lane < W;
+  uint8_t* o = dst + (int64_t)b * out_plane + (int64_t)y0 * W + x0 + lane;
+  const int rows = min(HS_ROWS, H - y0);
+  // Loads are unconditional (row / column clamped into the array) so that a batch of
+  // HS_AHEAD rows is in flight before the first value is looked at.
+  const int last_row = H + 1;                      // last source row of the band
+  const T* pc = src + (int64_t)b * in_plane + (col_ok ? col : SW - 1);
+  auto raw = [&](int row) -> T { return __ldg(pc + (int64_t)min(row, last_row) * SW); };
+  auto clean = [&](T v) -> A { return (A)((has_nodata && v == nodata) ? fill : v); };
+  A a0 = clean(raw(y0)), b0 = clean(raw(y0 + 1));
+  A a1 = shfl_down_any<A>(a0, 1), a2 = shfl_down_any<A>(a0, 2);
+  A b1 = shfl_down_any<A>(b0, 1), b2 = shfl_down_any<A>(b0, 2);
+  const A two = (A)2;
+  for (int r0 = 0; r0 < rows; r0 += HS_AHEAD) {
+    T next[HS_AHEAD];
+#pragma unroll
+    for (int i = 0; i < HS_AHEAD; ++i) next[i] = raw(y0 + r0 + i + 2);
+#pragma unroll
+    for (int i = 0; i < HS_AHEAD; ++i) {
+      const int r = r0 + i;
+      const A c0 = clean(next[i]);
+      const A c1 = shfl_down_any<A>(c0, 1), c2 = shfl_down_any<A>(c0, 2);
+      // s0 s1 s2 = a0 a1 a2 ; s3 s4 s5 = b0 b1 b2 ; s6 s7 s8 = c0 c1 c2
+      const A gy = ((((a0 + two * a1) + a2) - c0) - two * c1) - c2;
+      const A gx = ((((a0 + two * b0) + c0) - a2) - two * b2) - c2;
+      float fy, fx;
+      if (exact_inverse) {  // resolution is a power of two: v * (1 / res) == v / res bit for bit
+        fy = HillArith<T>::mul((T)gy, inv_yres);
+        fx = HillArith<T>::mul((T)gx, inv_xres);
+      } else {
+        fy = HillArith<T>::div((T)gy, yres);
+        fx = HillArith<T>::div((T)gx, xres);
+      }
+      const float xx_plus_yy = fx * fx + fy * fy;
+      const float num = sin_alt - cos_alt_zsf * (fy * cos_az - fx * sin_az);
+      const float cang = num * rsqrtf(1.0f + square_zsf * xx_plus_yy);
+      const int grey = (int)(255.0f * cang);
+      const uint8_t out = (cang <= 0.0f) ? (uint8_t)0 : (uint8_t)grey;
+      if (writes && r < rows) o[(int64_t)r * W] = out;
+      a0 = b0; a1 = b1; a2 = b2;
+      b0 = c0; b1 = c1; b2 = c2;
+    }
   }
 }
 
@@ -117,6 +216,251 @@ moving_max_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int 
       dst[(int64_t)b * out_plane + (int64_t)y * W + x] = best;
     }
   }
+}
+
+
+// Tiled version for radii up to MM2_MAXR.  The disc is a stack of horizontal chords
+// with only a few distinct half-widths (size 11: 2, 3, 4, 5), so per tile
+//   1. the source tile + halo goes to shared memory (no data -> dtype minimum),
+//   2. every tile row gets its running maximum over each distinct chord width
+//      (one pass outwards from the centre, nested windows reuse the same loads),
+//   3. an output pixel is the maximum of 2r+1 chord maxima, one per footprint row.
+// 11 + K + 11 shared-memory accesses per pixel instead of the 97 taps of the disc.
+constexpr int MM2_TX = 64, MM2_TY = 32, MM2_MAXR = 8, MM2_MAXK = MM2_MAXR + 1;
+struct MMFootprint {
+  int n_widths;
+  int width[MM2_MAXK];            // distinct chord half-widths, ascending
+  int level[2 * MM2_MAXR + 1];    // footprint row dy + r -> index into width[], -1: not in the disc
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+moving_max_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
+                        int bands, int H, int W, int r, const __grid_constant__ MMFootprint fp) {
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  const int tw = MM2_TX + 2 * r, th = MM2_TY + 2 * r;
+  T* tile = reinterpret_cast<T*>(mm_smem);             // th x tw
+  T* chord = tile + (size_t)th * tw;                   // n_widths x th x MM2_TX
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SW = W + 2 * r, SH = H + 2 * r;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int x0 = blockIdx.x * MM2_TX, y0 = blockIdx.y * MM2_TY;
+  const T lowest = Lowest<T>::value();
+  const int wmax = fp.width[fp.n_widths - 1];
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const T* plane = src + (int64_t)b * in_plane;
+    __syncthreads();
+    for (int ty = warp; ty < th; ty += 8) {
+      const int gy = y0 + ty;
+      for (int tx = lane; tx < tw; tx += 32) {
+        const int gx = x0 + tx;
+        T v = lowest;
+        if (gy < SH && gx < SW) {
+          v = __ldg(plane + (int64_t)gy * SW + gx);
+          if (has_nodata && v == nodata) v = lowest;
+        }
+        tile[ty * tw + tx] = v;
+      }
+    }
+    __syncthreads();
+    for (int ty = warp; ty < th; ty += 8) {
+      for (int tx = lane; tx < MM2_TX; tx += 32) {
+        const T* c = tile + ty * tw + tx + r;
+        T m = c[0];
+        int k = 0;
+        if (fp.width[0] == 0) { chord[(size_t)ty * MM2_TX + tx] = m; k = 1; }
+        for (int d = 1; d <= wmax; ++d) {
+          const T lo = c[-d], hi = c[d];
+          m = lo > m ? lo : m;
+          m = hi > m ? hi : m;
+          if (d == fp.width[k]) { chord[((size_t)k * th + ty) * MM2_TX + tx] = m; ++k; }
+        }
+      }
+    }
+    __syncthreads();
+    for (int ty = warp; ty < MM2_TY; ty += 8) {
+      const int y = y0 + ty;
+      if (y >= H) break;
+      for (int tx = lane; tx < MM2_TX; tx += 32) {
+        const int x = x0 + tx;
+        if (x >= W) break;
+        T best = lowest;
+        for (int dy = 0; dy <= 2 * r; ++dy) {
+          const int k = fp.level[dy];
+          if (k < 0) continue;
+          const T v = chord[((size_t)k * th + ty + dy) * MM2_TX + tx];
+          best = v > best ? v : best;
+        }
+        // restore no data only where the centre was no data and nothing was found
+        if (has_nodata && best == lowest &&
+            __ldg(plane + (int64_t)(y + r) * SW + (x + r)) == nodata)
+          best = nodata;
+        dst[(int64_t)b * out_plane + (int64_t)y * W + x] = best;
+      }
+    }
+  }
+}
+
+
+// max as one FMNMX / IMNMX.  For floats this differs from `v > m ? v : m` only when a NaN is
+// present, which cannot happen here: sources turn NaN into no data (raster/sources.py:148)
+// and every element-wise block replaces non-finite results by its fill value.
+template <typename T> __device__ __forceinline__ T vmax(T a, T b) { return a > b ? a : b; }
+template <> __device__ __forceinline__ float vmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double vmax<double>(double a, double b) { return fmax(a, b); }
+
+// Compile-time footprint for the usual odd sizes: the three phases of the tiled kernel
+// fully unrolled (no footprint look-ups, no branches): 11 + 11 shared loads, 4 shared stores
+// and 21 max per pixel at size 11.
+template <int SIZE> struct Disc {
+  static constexpr int R = SIZE / 2;
+  // chord half-width of footprint row dy: largest dx with dx^2 + dy^2 < (SIZE/2)^2, -1 if none
+  static constexpr int half_width(int dy) {
+    int w = -1;
+    for (int dx = 0; dx <= R; ++dx)
+      if (4 * (dx * dx + dy * dy) < SIZE * SIZE) w = dx;
+    return w;
+  }
+  static constexpr bool used(int d) {
+    for (int dy = -R; dy <= R; ++dy)
+      if (half_width(dy) == d) return true;
+    return false;
+  }
+  static constexpr int plane_of(int d) {   // index of width d among the used widths
+    int k = 0;
+    for (int e = 0; e < d; ++e) k += used(e) ? 1 : 0;
+    return k;
+  }
+  static constexpr int n_planes() { return plane_of(R + 1); }
+  static constexpr int wmax() { return half_width(0); }
+};
+
+template <typename T, int SIZE, int D>
+__device__ __forceinline__ void chord_steps(const T* c, T& m, T* chord_px, int plane_stride) {
+  if constexpr (D <= Disc<SIZE>::wmax()) {
+    if constexpr (D > 0) {
+      m = vmax<T>(m, vmax<T>(c[-D], c[D]));
+    }
+    if constexpr (Disc<SIZE>::used(D)) chord_px[Disc<SIZE>::plane_of(D) * plane_stride] = m;
+    chord_steps<T, SIZE, D + 1>(c, m, chord_px, plane_stride);
+  }
+}
+
+template <typename T, int SIZE, int DY>
+__device__ __forceinline__ void disc_rows(const T* chord_px, int plane_stride, T& best) {
+  constexpr int R = Disc<SIZE>::R;
+  if constexpr (DY <= R) {
+    constexpr int w = Disc<SIZE>::half_width(DY);
+    if constexpr (w >= 0) {
+      best = vmax<T>(best, chord_px[Disc<SIZE>::plane_of(w) * plane_stride + (DY + R) * MM2_TX]);
+    }
+    disc_rows<T, SIZE, DY + 1>(chord_px, plane_stride, best);
+  }
+}
+
+template <typename T, int SIZE>
+__global__ void __launch_bounds__(256)
+moving_max_fixed_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
+                        int bands, int H, int W) {
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  constexpr int R = Disc<SIZE>::R;
+  constexpr int TW = MM2_TX + 2 * R, TH = MM2_TY + 2 * R;
+  constexpr int PLANE = TH * MM2_TX;
+  T* tile = reinterpret_cast<T*>(mm_smem);             // TH x TW
+  T* chord = tile + TH * TW;                           // n_planes x TH x MM2_TX
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SW = W + 2 * R, SH = H + 2 * R;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int x0 = blockIdx.x * MM2_TX, y0 = blockIdx.y * MM2_TY;
+  const T lowest = Lowest<T>::value();
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const T* plane = src + (int64_t)b * in_plane;
+    __syncthreads();
+    // unconditional (clamped) loads, two tile rows per round: six requests in flight
+    // per thread before the first value is tested
+    constexpr int NJ = (TW + 31) / 32;
+    for (int ty = warp; ty < TH; ty += 16) {
+      T raw[2][NJ];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gy = min(y0 + ty + 8 * h, SH - 1);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(x0 + lane + 32 * j, SW - 1));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = ty + 8 * h;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int tx = lane + 32 * j;
+          const bool inside = y0 + row < SH && x0 + tx < SW;
+          const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? lowest : raw[h][j];
+          if (tx < TW && row < TH) tile[row * TW + tx] = v;
+        }
+      }
+    }
+    __syncthreads();
+    for (int ty = warp; ty < TH; ty += 8) {
+#pragma unroll
+      for (int j = 0; j < MM2_TX / 32; ++j) {
+        const int tx = lane + 32 * j;
+        const T* c = tile + ty * TW + tx + R;
+        T m = c[0];
+        chord_steps<T, SIZE, 0>(c, m, chord + ty * MM2_TX + tx, PLANE);
+      }
+    }
+    __syncthreads();
+    for (int ty = warp; ty < MM2_TY; ty += 8) {
+      const int y = y0 + ty;
+      if (y >= H) break;
+#pragma unroll
+      for (int j = 0; j < MM2_TX / 32; ++j) {
+        const int tx = lane + 32 * j;
+        const int x = x0 + tx;
+        if (x < W) {
+          T best = lowest;
+          disc_rows<T, SIZE, -R>(chord + ty * MM2_TX + tx, PLANE, best);
+          if (has_nodata && best == lowest &&
+              __ldg(plane + (int64_t)(y + R) * SW + (x + R)) == nodata)
+            best = nodata;
+          dst[(int64_t)b * out_plane + (int64_t)y * W + x] = best;
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int SIZE>
+static int launch_moving_max_fixed(const Staged& in, Staged& out, T nd, int has_nodata, int bands,
+                                   int H, int W, cudaStream_t s) {
+  constexpr int R = Disc<SIZE>::R;
+  const size_t smem = ((size_t)(MM2_TX + 2 * R) * (MM2_TY + 2 * R) +
+                       (size_t)Disc<SIZE>::n_planes() * (MM2_TY + 2 * R) * MM2_TX) * sizeof(T);
+  auto kernel = moving_max_fixed_kernel<T, SIZE>;
+  if (smem > 48 * 1024)
+    GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<grid3(W, H, bands, MM2_TX, MM2_TY), 256, smem, s>>>((const T*)in.dev, (T*)out.dev, nd,
+                                                               has_nodata, bands, H, W);
+  GM_LAUNCH_CHECK();
+  return 0;
+}
+
+// 0: launched, 1: error, -1: no compile-time footprint for this dtype / size
+template <typename T>
+static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, int has_nodata,
+                                int bands, int H, int W, cudaStream_t s) {
+  if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
+                std::is_same<T, int16_t>::value || std::is_same<T, uint8_t>::value ||
+                std::is_same<T, int32_t>::value) {
+    switch (size) {
+#define GM_CASE(N) case N: return launch_moving_max_fixed<T, N>(in, out, nd, has_nodata, bands, H, W, s);
+      GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
+#undef GM_CASE
+      default: break;
+    }
+  }
+  return -1;
 }
 
 // ---------------------------------------------------------------------------------
@@ -224,6 +568,145 @@ smooth_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_
   }
 }
 
+
+// Fast path for ly == lx == L <= SMF_MAXL (every "exact"-mode request: size_px <= 6 gives
+// L = int(4 * size_px / 3 + 0.5) <= 8).  Same arithmetic as smooth_kernel -- double
+// accumulation in SciPy's tap order, array-dtype rounding after each pass -- organised so
+// that the FP64 pipe, not shared memory, is the limit:
+//   * the tile is converted to double ONCE when it is staged (conversions are slow-path
+//     instructions; the generic kernel converts every tap);
+//   * a thread produces 8 consecutive outputs of a column (y pass) or a row (x pass) from a
+//     register window of 8 + 2L values: (8 + 2L) / 8 shared loads per output instead of
+//     2L + 1;
+//   * tile width incl. halo is 128 columns and 32 + 2L rows, so both passes are whole rounds
+//     of the 256 threads; rows are padded to 129 doubles so that the x pass (lane = row) is
+//     bank-conflict free; results leave through a staged, coalesced copy.
+// Bound: 22 FP64 operations per pass per pixel (1 + 3L at L = 7) on a 64-lane FP64 pipe.
+constexpr int SMF_TW = 128, SMF_TY = 32, SMF_RUN = 8, SMF_PITCH = SMF_TW + 1, SMF_MAXL = 8;
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256)
+smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata, T fill,
+                   int bands, int SH, int SW, int H, int W, int my, int mx,
+                   const __grid_constant__ SmoothWeights wts) {
+  extern __shared__ __align__(16) unsigned char sm_smem[];
+  constexpr int TX = SMF_TW - 2 * L;          // output columns per tile
+  constexpr int TH = SMF_TY + 2 * L;          // staged rows
+  constexpr int WIN = SMF_RUN + 2 * L;
+  double* tile = reinterpret_cast<double*>(sm_smem);       // TH x SMF_PITCH (source, no data -> fill)
+  double* mid = tile + (size_t)TH * SMF_PITCH;             // SMF_TY x SMF_PITCH (after the y pass)
+  T* stage = reinterpret_cast<T*>(tile);                   // SMF_TY x TX results (reuses the tile)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int x0 = blockIdx.x * TX, y0 = blockIdx.y * SMF_TY;  // output coordinates of the tile
+  const double dfill = (double)fill;
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const T* plane = src + (int64_t)b * in_plane;
+    __syncthreads();
+    // unconditional (clamped) loads, two tile rows = eight requests per thread per round
+    for (int ty = warp; ty < TH; ty += 16) {
+      T raw[2][SMF_TW / 32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int gy = min(max(y0 + my - L + ty + 8 * h, 0), SH - 1);
+#pragma unroll
+        for (int j = 0; j < SMF_TW / 32; ++j)
+          raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(max(x0 + mx - L + lane + 32 * j, 0), SW - 1));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = ty + 8 * h;
+        const int gy = y0 + my - L + row;
+#pragma unroll
+        for (int j = 0; j < SMF_TW / 32; ++j) {
+          const int tx = lane + 32 * j;
+          const int gx = x0 + mx - L + tx;
+          const bool inside = gy >= 0 && gy < SH && gx >= 0 && gx < SW;
+          const double v = (!inside || (has_nodata && raw[h][j] == nodata)) ? dfill : (double)raw[h][j];
+          if (row < TH) tile[row * SMF_PITCH + tx] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // y pass: task = (run of 8 rows, column); 4 x 128 tasks = two rounds of 256 threads
+#pragma unroll 1
+    for (int task = tid; task < (SMF_TY / SMF_RUN) * SMF_TW; task += 256) {
+      const int tx = task & (SMF_TW - 1), run = task >> 7;
+      const double* c = tile + (run * SMF_RUN) * SMF_PITCH + tx;
+      double win[WIN];
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) win[i] = c[i * SMF_PITCH];
+      const int gx = x0 + mx - L + tx;
+      const bool pad = gx < 0 || gx >= SW;   // columns outside the source: constant padding
+#pragma unroll
+      for (int o = 0; o < SMF_RUN; ++o) {
+        double tmp = win[o + L] * wts.wy[0];
+#pragma unroll
+        for (int k = L; k >= 1; --k) tmp += (win[o + L - k] + win[o + L + k]) * wts.wy[k];
+        const T r = from_double<T>(tmp);
+        mid[(run * SMF_RUN + o) * SMF_PITCH + tx] = pad ? dfill : (double)r;
+      }
+    }
+    __syncthreads();
+    // x pass: lane = row, each warp takes runs of 8 output columns
+#pragma unroll 1
+    for (int run = warp; run * SMF_RUN < TX; run += 8) {
+      const double* c = mid + lane * SMF_PITCH + run * SMF_RUN;
+      double win[WIN];
+#pragma unroll
+      for (int i = 0; i < WIN; ++i) win[i] = (run * SMF_RUN + i < SMF_TW) ? c[i] : 0.0;
+#pragma unroll
+      for (int o = 0; o < SMF_RUN; ++o) {
+        double tmp = win[o + L] * wts.wx[0];
+#pragma unroll
+        for (int k = L; k >= 1; --k) tmp += (win[o + L - k] + win[o + L + k]) * wts.wx[k];
+        if (run * SMF_RUN + o < TX) stage[lane * TX + run * SMF_RUN + o] = from_double<T>(tmp);
+      }
+    }
+    __syncthreads();
+    for (int ty = warp; ty < SMF_TY; ty += 8) {
+      const int y = y0 + ty;
+      if (y >= H) break;
+      for (int tx = lane; tx < TX; tx += 32) {
+        const int x = x0 + tx;
+        if (x < W) dst[(int64_t)b * out_plane + (int64_t)y * W + x] = stage[ty * TX + tx];
+      }
+    }
+  }
+}
+
+template <typename T, int L>
+static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
+                              int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
+                              cudaStream_t s) {
+  constexpr int TX = SMF_TW - 2 * L;
+  const size_t smem = ((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH * sizeof(double);
+  auto kernel = smooth_fast_kernel<T, L>;
+  GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<grid3(W, H, bands, TX, SMF_TY), 256, smem, s>>>((const T*)in.dev, target, nd, has_nodata, fill,
+                                                           bands, SH, SW, H, W, my, mx, wts);
+  GM_LAUNCH_CHECK();
+  return 0;
+}
+
+// 0: launched, 1: error, -1: no fast path for this dtype / radius
+template <typename T>
+static int try_smooth_fast(int L, const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
+                           int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
+                           cudaStream_t s) {
+  if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
+                std::is_same<T, int16_t>::value || std::is_same<T, uint8_t>::value ||
+                std::is_same<T, int32_t>::value) {
+    switch (L) {
+#define GM_CASE(N) case N: return launch_smooth_fast<T, N>(in, target, nd, has_nodata, fill, bands, SH, SW, H, W, my, mx, wts, s);
+      GM_CASE(1) GM_CASE(2) GM_CASE(3) GM_CASE(4) GM_CASE(5) GM_CASE(6) GM_CASE(7) GM_CASE(8)
+#undef GM_CASE
+      default: break;
+    }
+  }
+  return -1;
+}
+
 // zoom-back of Smooth's "zoom" mode: ndimage.affine_transform(order=0,
 // matrix=diag(1, zy, zx), offset=(0, oy, ox)) -> out[i, j] = in[floor(oy + i*zy + .5), ...]
 template <typename T>
@@ -246,13 +729,8 @@ __global__ void zoom_nn_kernel(const T* __restrict__ src, T* __restrict__ dst, i
 }
 
 // ---- host side ---------------------------------------------------------------------
-template <typename T> static T read_scalar(const void* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 template <typename T> static T cast_fill(double fill) { return (T)fill; }
 
-static dim3 grid3(int W, int H, int bands, int bx, int by) {
-  int gz = bands < 65535 ? bands : 65535;
-  return dim3((W + bx - 1) / bx, (H + by - 1) / by, gz);
-}
 
 template <typename T>
 static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int has_nodata,
@@ -261,11 +739,17 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
   const double alt = alt_deg * (M_PI / 180.0), az = az_deg * (M_PI / 180.0);
   // math.radians(x) = x * (pi / 180) in CPython
   const double zsf = 1.0 / 8.0;
-  dim3 block(32, 8);
-  hillshade_kernel<T><<<grid3(W, H, bands, 32, 8), block, 0, s>>>(
+  // a power-of-two resolution (in float32 for float rasters) has an exact reciprocal
+  auto pow2 = [](double v) { int e; return v > 0 && std::frexp(v, &e) == 0.5 && e > -100 && e < 100; };
+  const bool is_f32 = std::is_same<T, float>::value;
+  const int exact = pow2(is_f32 ? (double)(float)xres : xres) && pow2(is_f32 ? (double)(float)yres : yres);
+  const int strips_x = (W + HS_COLS - 1) / HS_COLS, strips_y = (H + HS_ROWS - 1) / HS_ROWS;
+  const int64_t strips = (int64_t)bands * strips_x * strips_y;
+  const unsigned blocks = (unsigned)((strips + HS_WARPS - 1) / HS_WARPS);
+  hillshade_strip_kernel<T><<<blocks, 32 * HS_WARPS, 0, s>>>(
       (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
-      cast_fill<T>(fill), bands, H, W, xres, yres, (float)sin(alt), (float)(cos(alt) * zsf),
-      (float)az, (float)(zsf * zsf));
+      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, exact,
+      (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf));
   GM_LAUNCH_CHECK();
   return 0;
 }
@@ -283,6 +767,37 @@ static int run_moving_max(const Staged& in, Staged& out, const void* nodata, int
     for (int dx = 0; dx <= r; ++dx)
       if ((double)(dx * dx + dy * dy) < rad2) w = dx;
     hw[dy + r] = w;  // -1: the row is not part of the footprint
+  }
+  {
+    const int fixed = try_moving_max_fixed<T>(size, in, out, has_nodata ? read_scalar<T>(nodata) : T(0),
+                                              has_nodata, bands, H, W, s);
+    if (fixed >= 0) return fixed;
+  }
+  if (r >= 1 && r <= MM2_MAXR) {
+    MMFootprint fp;
+    memset(&fp, 0, sizeof(fp));
+    for (int i = 0; i < 2 * MM2_MAXR + 1; ++i) fp.level[i] = -1;
+    std::vector<int> distinct;
+    for (int w : hw) if (w >= 0) distinct.push_back(w);
+    std::sort(distinct.begin(), distinct.end());
+    distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+    fp.n_widths = (int)distinct.size();
+    for (int k = 0; k < fp.n_widths; ++k) fp.width[k] = distinct[k];
+    for (int dy = 0; dy <= 2 * r; ++dy)
+      if (hw[dy] >= 0)
+        fp.level[dy] = (int)(std::find(distinct.begin(), distinct.end(), hw[dy]) - distinct.begin());
+    const size_t tile_smem = ((size_t)(MM2_TX + 2 * r) * (MM2_TY + 2 * r) +
+                              (size_t)fp.n_widths * (MM2_TY + 2 * r) * MM2_TX) * sizeof(T);
+    if (tile_smem <= 200 * 1024) {
+      auto tiled = moving_max_tiled_kernel<T>;
+      if (tile_smem > 48 * 1024)
+        GM_CUDA(cudaFuncSetAttribute(tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      tiled<<<grid3(W, H, bands, MM2_TX, MM2_TY), 256, tile_smem, s>>>(
+          (const T*)in.dev, (T*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
+          bands, H, W, r, fp);
+      GM_LAUNCH_CHECK();
+      return 0;
+    }
   }
   void* dev_hw = nullptr;
   if (upload(&dev_hw, hw.data(), (int64_t)hw.size() * sizeof(int), s)) return 1;
@@ -336,15 +851,24 @@ static int run_smooth(const Staged& in, Staged& out, const void* nodata, int has
     GM_CUDA(cudaMallocAsync(&tmp, (size_t)bands * H * W * sizeof(T), s));
     target = (T*)tmp;
   }
-  kernel<<<grid3(W, H, bands, SM_TX, SM_TY), dim3(SM_TX, SM_TY), smem, s>>>(
-      (const T*)in.dev, target, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
-      cast_fill<T>(fill), bands, SH, SW, H, W, my, mx, ly, lx, wts);
+  int fast = -1;
+  if (ly == lx && ly >= 1 && ly <= SMF_MAXL)
+    fast = try_smooth_fast<T>(ly, in, target, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
+                              cast_fill<T>(fill), bands, SH, SW, H, W, my, mx, wts, s);
+  if (fast == 1) {
+    if (tmp) cudaFreeAsync(tmp, s);
+    return 1;
+  }
+  if (fast == -1)
+    kernel<<<grid3(W, H, bands, SM_TX, SM_TY), dim3(SM_TX, SM_TY), smem, s>>>(
+        (const T*)in.dev, target, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
+        cast_fill<T>(fill), bands, SH, SW, H, W, my, mx, ly, lx, wts);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     if (tmp) cudaFreeAsync(tmp, s);
     return fail(std::string("smooth launch: ") + cudaGetErrorString(e));
   }
-  count_launch();
+  if (fast == -1) count_launch();
   if (zoom) {
     const int64_t total = (int64_t)bands * H * W;
     int64_t blocks = (total + 255) / 256;

@@ -119,6 +119,74 @@ temporal_aggregate_kernel(const S* __restrict__ src, D* __restrict__ dst, S noda
   }
 }
 
+// Streaming fast path for sum / count / min / max / mean: the statistic is a template
+// argument (only the accumulators it needs exist), a thread owns VEC = 16 / sizeof(S)
+// consecutive pixels so every frame is read with 128-bit loads, and UNROLL frames are in
+// flight per thread (64 B).  Same sequential-in-t arithmetic as the generic kernel.
+template <typename S, int VEC> struct alignas(16) PixelVec { S v[VEC]; };
+template <typename S, int VEC>
+__device__ __forceinline__ PixelVec<S, VEC> load_pixels(const PixelVec<S, VEC>* p) {
+  static_assert(sizeof(PixelVec<S, VEC>) == 16, "16-byte pixel groups");
+  union { uint4 raw; PixelVec<S, VEC> vec; } u;
+  u.raw = ::__ldcs(reinterpret_cast<const uint4*>(p));
+  return u.vec;
+}
+
+template <typename S, typename W, typename D, int STAT>
+__global__ void __launch_bounds__(256)
+temporal_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                       const int* __restrict__ bin_offsets, const int* __restrict__ frame_index,
+                       int n_bins, int64_t plane) {
+  constexpr int VEC = 16 / (int)sizeof(S);
+  constexpr int UNROLL = 4;
+  typedef PixelVec<S, VEC> V;
+  const int64_t groups = plane / VEC;
+  const int64_t grp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (grp >= groups) return;
+  const int64_t pix = grp * VEC;
+  const D fill = (STAT == GM_STAT_SUM || STAT == GM_STAT_COUNT) ? (D)0 : DMax<D>::value();
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
+    W acc[VEC];
+    int cnt[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i] = (STAT == GM_STAT_MIN || STAT == GM_STAT_MAX) ? nan_<W>() : (W)0; cnt[i] = 0; }
+    auto take = [&](const V& x) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const S v = x.v[i];
+        const W w = (W)v;
+        const bool valid = !(has_nodata && v == nodata) && (w == w);
+        if (STAT == GM_STAT_SUM || STAT == GM_STAT_MEAN) acc[i] = valid ? acc[i] + w : acc[i];
+        if (STAT == GM_STAT_MIN) acc[i] = (valid && (acc[i] != acc[i] || w < acc[i])) ? w : acc[i];
+        if (STAT == GM_STAT_MAX) acc[i] = (valid && (acc[i] != acc[i] || w > acc[i])) ? w : acc[i];
+        if (STAT == GM_STAT_COUNT || STAT == GM_STAT_MEAN) cnt[i] += valid ? 1 : 0;
+      }
+    };
+    int f = f0;
+    for (; f + UNROLL <= f1; f += UNROLL) {
+      V x[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        x[u] = load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f + u] * plane + pix));
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) take(x[u]);
+    }
+    for (; f < f1; ++f)
+      take(load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f] * plane + pix)));
+    D* o = dst + (int64_t)g * plane + pix;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      W result;
+      if (STAT == GM_STAT_COUNT) result = (W)(int64_t)cnt[i];
+      else if (STAT == GM_STAT_MEAN) result = (W)((double)acc[i] / (double)(int64_t)cnt[i]);
+      else result = acc[i];
+      const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+      o[i] = (f1 > f0 && finite) ? cast_out<W, D>(result) : fill;
+    }
+  }
+}
+
 template <typename S, typename W, typename D>
 __global__ void __launch_bounds__(256)
 temporal_cumulative_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
@@ -159,6 +227,28 @@ template <typename S, typename W, typename D>
 static int launch_aggregate(const Staged& in, Staged& out, const TemporalArgs& a, cudaStream_t s) {
   S nd = S(0);
   if (a.has_nodata) memcpy(&nd, a.nodata, sizeof(S));
+  constexpr int VEC = 16 / (int)sizeof(S);
+  const bool streamable =
+      (a.stat == GM_STAT_SUM || a.stat == GM_STAT_COUNT || a.stat == GM_STAT_MIN ||
+       a.stat == GM_STAT_MAX || a.stat == GM_STAT_MEAN) &&
+      a.plane % VEC == 0 && ((uintptr_t)in.dev % 16) == 0;
+  if (streamable) {
+    const int64_t groups = a.plane / VEC;
+    const unsigned nb = (unsigned)((groups + 255) / 256);
+#define GM_STREAM(ST)                                                                        \
+    temporal_stream_kernel<S, W, D, ST><<<nb, 256, 0, s>>>(                                  \
+        (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.bins, a.frames, a.n_bins, a.plane)
+    switch (a.stat) {
+      case GM_STAT_SUM: GM_STREAM(GM_STAT_SUM); break;
+      case GM_STAT_COUNT: GM_STREAM(GM_STAT_COUNT); break;
+      case GM_STAT_MIN: GM_STREAM(GM_STAT_MIN); break;
+      case GM_STAT_MAX: GM_STREAM(GM_STAT_MAX); break;
+      default: GM_STREAM(GM_STAT_MEAN); break;
+    }
+#undef GM_STREAM
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t blocks = (a.plane + 255) / 256;
   temporal_aggregate_kernel<S, W, D><<<(unsigned)blocks, 256, 0, s>>>(
       (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.q, a.bins, a.frames, a.n_bins,

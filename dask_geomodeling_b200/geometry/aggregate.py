@@ -93,12 +93,12 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     like the reference (geometry/aggregate.py:113-203)."""
     from ..raster._program import sentinel
 
-    geometries = list(geometries)
     depth, height, width = values.shape
-    soup = utils.PolygonSoup(geometries)
+    # a ready-made PolygonSoup is accepted so that callers can reuse it between requests
+    soup = geometries if isinstance(geometries, utils.PolygonSoup) else utils.PolygonSoup(list(geometries))
     polys = soup.as_struct()
     geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(agg_bbox, height, width))
-    n = len(geometries)
+    n = soup.n_polygons
     agg = np.full((depth, n), np.nan, dtype="f4")
     covered = np.zeros(n, dtype=np.int64)
     s = sentinel(values.dtype, no_data_value)
