@@ -149,6 +149,8 @@ SYMBOLS = {
     "gm_rasterize_polygons": (_i, [_P(GmPolygons), _P(_d), _vp, _vp, _P(GmArray), _vp]),
     "gm_zonal_stats": (_i, [_P(GmArray), _vp, _i, _P(GmPolygons), _P(_d), _i, _d, _vp,
                             _i64, _i64, _vp, _vp, _vp, _vp]),
+    "gm_zonal_values": (_i, [_P(GmArray), _vp, _i, _P(GmPolygons), _P(_d), _vp, _vp, _vp, _vp]),
+    "gm_segment_order_stat": (_i, [_vp, ctypes.c_int32, _vp, _i64, _i, _d, _vp, _vp]),
 }
 
 _lib = None
@@ -390,3 +392,32 @@ def scalar_ptr(value, dtype):
     """Pointer to one element of `dtype` holding `value` (kept alive by the caller)."""
     holder = np.array([value], dtype=dtype)
     return holder, holder.ctypes.data
+
+
+def zonal_values(raster_desc, nodata_ptr, has_nodata, polys, geo, thresholds, counts):
+    """Active cell values under every polygon (gm_zonal_values): (counts, packed values)."""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    values = np.empty(int(counts.sum()), dtype=_CODE_DTYPES[raster_desc.dtype])
+    check(lib().gm_zonal_values(
+        ctypes.byref(raster_desc), nodata_ptr, has_nodata, ctypes.byref(polys), geo,
+        None if thresholds is None else thresholds.ctypes.data, counts.ctypes.data,
+        values.ctypes.data if values.size else None or np.empty(1, values.dtype).ctypes.data,
+        current_stream()))
+    return counts, values
+
+
+_ORDER_STATS = {"median": 5, "percentile": 8}
+
+
+def segment_order_statistic(values, offsets, statistic, percentile=None):
+    """float32 median / percentile of every segment values[offsets[k]:offsets[k+1]]."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    out = np.empty(n, dtype=np.float32)
+    if n == 0:
+        return out
+    values = np.ascontiguousarray(values)
+    check(lib().gm_segment_order_stat(
+        values.ctypes.data if values.size else None, dtype_code(values.dtype), offsets.ctypes.data, n,
+        _ORDER_STATS[statistic], float(percentile or 0.0), out.ctypes.data, current_stream()))
+    return out

@@ -543,6 +543,35 @@ template <typename T> __device__ __forceinline__ float percentile_of(T lo, T hi,
   return (float)((double)lo + part * (double)diff);
 }
 
+// median / percentile of the n keys in `keys` in the reference's arithmetic (block-wide call)
+template <typename T>
+__device__ float order_statistic(const typename KeyOf<T>::type* keys, int n, int stat, double q,
+                                 int* hist, typename KeyOf<T>::type* prefix_scratch, int* counter) {
+  typedef typename KeyOf<T>::type K;
+  float result = __int_as_float(0x7fc00000);
+  if (n > 0) {
+    long long lo_rank, hi_rank;
+    double part = 0.0;
+    if (stat == GM_STAT_MEDIAN) {
+      lo_rank = (n - 1) / 2; hi_rank = n / 2;
+    } else {
+      const double frac = (double)(n - 1) * (q / 100.0);
+      lo_rank = (long long)floor(frac);
+      hi_rank = (long long)ceil(frac);
+      part = frac - floor(frac);
+    }
+    const K klo = block_select<K>(keys, n, lo_rank, hist, prefix_scratch);
+    K khi = klo;
+    if (hi_rank != lo_rank) {
+      const int le = block_count_le<K>(keys, n, klo, counter);
+      if (le < hi_rank + 1) khi = block_next_above<K>(keys, n, klo, prefix_scratch);
+    }
+    const T lo = KeyOf<T>::value(klo), hi = KeyOf<T>::value(khi);
+    result = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
+  }
+  return result;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(SEL_THREADS)
 zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
@@ -576,28 +605,95 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
     __threadfence_block();
     __syncthreads();
     const int n = cursor;
-    float result = __int_as_float(0x7fc00000);
-    if (n > 0) {
-      long long lo_rank, hi_rank;
-      double part = 0.0;
-      if (stat == GM_STAT_MEDIAN) {
-        lo_rank = (n - 1) / 2; hi_rank = n / 2;
-      } else {
-        const double frac = (double)(n - 1) * (q / 100.0);
-        lo_rank = (long long)floor(frac);
-        hi_rank = (long long)ceil(frac);
-        part = frac - floor(frac);
-      }
-      const K klo = block_select<K>(keys, n, lo_rank, hist, prefix_scratch);
-      K khi = klo;
-      if (hi_rank != lo_rank) {
-        const int le = block_count_le<K>(keys, n, klo, &cursor);
-        if (le < hi_rank + 1) khi = block_next_above<K>(keys, n, klo, prefix_scratch);
-      }
-      const T lo = KeyOf<T>::value(klo), hi = KeyOf<T>::value(khi);
-      result = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
-    }
+    const float result = order_statistic<T>(keys, n, stat, q, hist, prefix_scratch, &cursor);
     if (threadIdx.x == 0) out[p] = result;
+    __syncthreads();
+  }
+}
+
+// ---- multi-GPU order statistics: raw values out, segments in ---------------------------------
+// Append the ACTIVE cell values under polygon p at values[offsets[p] ...] (any order).
+template <typename T>
+struct ValueVisitor {
+  const T* raster; int width; ActiveTest<T> active;
+  T* out; int* cursor; long long capacity;
+  __device__ __forceinline__ void put(bool ok, T v) {
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cursor, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (ok) {
+      const long long pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < capacity) out[pos] = v;
+    }
+  }
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    const T* row = raster + (int64_t)y * width;
+    const int lane = threadIdx.x & 31;
+    for (int xb = x0; xb <= x1; xb += 32) {
+      const int x = xb + lane;
+      T v = T(0);
+      bool ok = false;
+      if (x <= x1) { v = __ldg(row + x); ok = active(v); }
+      put(ok, v);
+    }
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
+    const T* row = raster + (int64_t)y * width;
+    const int lane = threadIdx.x & 31;
+    for (int xb = x0; xb <= x1; xb += 32) {
+      const int x = xb + lane;
+      T v = T(0);
+      bool ok = false;
+      if (x <= x1 && !in_pairs(x, buf, n)) { v = __ldg(row + x); ok = active(v); }
+      put(ok, v);
+    }
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(PG_THREADS)
+zonal_values_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                    const float* __restrict__ thresholds, const long long* __restrict__ offsets,
+                    T* __restrict__ values) {
+  extern __shared__ int pg_smem[];
+  __shared__ int cursor;
+  const int warp = threadIdx.x >> 5;
+  int* buf = pg_smem + warp * P.cap;
+  int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    ValueVisitor<T> vis;
+    vis.raster = raster; vis.width = P.width;
+    vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
+    vis.active.has_threshold = thresholds != nullptr;
+    vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
+    vis.out = values + offsets[p]; vis.cursor = &cursor; vis.capacity = offsets[p + 1] - offsets[p];
+    scan_polygon(P, p, buf, hbuf, vis);
+    __syncthreads();
+  }
+}
+
+// One block per segment: values -> sortable keys (in place in `keys`), then select.
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS)
+segment_select_kernel(const T* __restrict__ values, const long long* __restrict__ offsets, int64_t n_seg,
+                      typename KeyOf<T>::type* __restrict__ keys, int stat, double q,
+                      float* __restrict__ out) {
+  typedef typename KeyOf<T>::type K;
+  __shared__ int hist[256];
+  __shared__ K prefix_scratch[8];
+  __shared__ int counter;
+  for (int64_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
+    const long long a = offsets[seg], b = offsets[seg + 1];
+    K* k = keys + a;
+    for (long long i = threadIdx.x; i < b - a; i += blockDim.x) k[i] = KeyOf<T>::key(values[a + i]);
+    __syncthreads();
+    const float result = order_statistic<T>(k, (int)(b - a), stat, q, hist, prefix_scratch, &counter);
+    if (threadIdx.x == 0) out[seg] = result;
     __syncthreads();
   }
 }
@@ -812,9 +908,122 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   return rc;
 }
 
+template <typename T>
+static int run_zonal_values(PolyUpload& u, const Staged& raster, const void* nodata, int has_nodata,
+                            const float* thresholds, const int64_t* counts, void* values_host,
+                            cudaStream_t s) {
+  const int64_t np_ = u.dev.n_polygons;
+  std::vector<long long> offsets(np_ + 1, 0);
+  for (int64_t p = 0; p < np_; ++p) offsets[p + 1] = offsets[p] + counts[p];
+  const long long total = offsets[np_];
+  if (np_ == 0 || total == 0) return 0;
+  T nd = T(0);
+  if (has_nodata) memcpy(&nd, nodata, sizeof(T));
+  void *doff = nullptr, *dthr = nullptr, *dval = nullptr;
+  int rc = upload(&doff, offsets.data(), sizeof(long long) * (np_ + 1), s);
+  if (!rc && thresholds) rc = upload(&dthr, thresholds, sizeof(float) * np_, s);
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaMallocAsync(&dval, sizeof(T) * (size_t)total, s);
+  if (!rc && e == cudaSuccess) {
+    const size_t smem = scan_smem(u.dev.cap, PG_WARPS);
+    if (smem > 48 * 1024)
+      e = cudaFuncSetAttribute(zonal_values_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      zonal_values_kernel<T><<<poly_grid(np_), PG_THREADS, smem, s>>>(
+          u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (const long long*)doff, (T*)dval);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) count_launch();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values_host, dval, sizeof(T) * (size_t)total, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  if (doff) cudaFreeAsync(doff, s);
+  if (dthr) cudaFreeAsync(dthr, s);
+  if (dval) cudaFreeAsync(dval, s);
+  if (!rc && e != cudaSuccess) rc = fail(std::string("gm_zonal_values: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+template <typename T>
+static int run_segment_select(const void* values, const int64_t* offsets, int64_t n_seg, int stat,
+                              double q, float* out, cudaStream_t s) {
+  typedef typename KeyOf<T>::type K;
+  const int64_t total = offsets[n_seg];
+  if (n_seg == 0) return 0;
+  void *dval = nullptr, *doff = nullptr, *dkeys = nullptr, *dout = nullptr;
+  int rc = upload(&dval, values, sizeof(T) * (size_t)total, s);
+  if (!rc) rc = upload(&doff, offsets, sizeof(int64_t) * (n_seg + 1), s);
+  cudaError_t e = cudaSuccess;
+  if (!rc) e = cudaMallocAsync(&dkeys, sizeof(K) * (size_t)(total > 0 ? total : 1), s);
+  if (!rc && e == cudaSuccess) e = cudaMallocAsync(&dout, sizeof(float) * n_seg, s);
+  if (!rc && e == cudaSuccess) {
+    segment_select_kernel<T><<<poly_grid(n_seg), SEL_THREADS, 0, s>>>(
+        (const T*)dval, (const long long*)doff, n_seg, (K*)dkeys, stat, q, (float*)dout);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) count_launch();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(float) * n_seg, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  }
+  void* all[] = {dval, doff, dkeys, dout};
+  for (void* p : all) if (p) cudaFreeAsync(p, s);
+  if (!rc && e != cudaSuccess) rc = fail(std::string("gm_segment_order_stat: ") + cudaGetErrorString(e));
+  return rc;
+}
+
 }  // namespace gm
 
 using namespace gm;
+
+#define GM_RASTER_DISPATCH(dtype, CALL, WHAT)                                     \
+  switch (dtype) {                                                                \
+    case GM_U8: case GM_BOOL: { typedef uint8_t T; rc = CALL; break; }            \
+    case GM_I8: { typedef int8_t T; rc = CALL; break; }                           \
+    case GM_U16: { typedef uint16_t T; rc = CALL; break; }                        \
+    case GM_I16: { typedef int16_t T; rc = CALL; break; }                         \
+    case GM_U32: { typedef uint32_t T; rc = CALL; break; }                        \
+    case GM_I32: { typedef int32_t T; rc = CALL; break; }                         \
+    case GM_F32: { typedef float T; rc = CALL; break; }                           \
+    case GM_F64: { typedef double T; rc = CALL; break; }                          \
+    default: rc = fail(WHAT ": unsupported raster dtype");                        \
+  }
+
+extern "C" int gm_zonal_values(const GmArray* raster, const void* nodata, int has_nodata,
+                               const GmPolygons* polys, const double geo[6], const float* thresholds,
+                               const int64_t* counts, void* values, void* stream) {
+  if (ensure_init()) return 1;
+  if (!raster || !polys || !counts || !values) return fail("gm_zonal_values: null argument");
+  if (raster->shape[0] != 1) return fail("gm_zonal_values: one frame per call");
+  cudaStream_t s = resolve_stream(stream);
+  const int H = (int)raster->shape[1], W = (int)raster->shape[2];
+  Staged in;
+  PolyUpload u;
+  int rc = in.open_input(*raster, s);
+  if (!rc) rc = prepare_polygons(polys, geo, H, W, 0, H, u, s);
+  if (!rc) {
+    GM_RASTER_DISPATCH(raster->dtype, run_zonal_values<T>(u, in, nodata, has_nodata, thresholds, counts, values, s),
+                       "gm_zonal_values")
+  }
+  if (!rc) rc = check_overflow(u, s);
+  u.release();
+  in.release();
+  return rc;
+}
+
+extern "C" int gm_segment_order_stat(const void* values, int32_t dtype, const int64_t* offsets,
+                                     int64_t n_segments, int stat, double q, float* out, void* stream) {
+  if (ensure_init()) return 1;
+  if (!offsets || !out || (n_segments > 0 && offsets[n_segments] > 0 && !values))
+    return fail("gm_segment_order_stat: null argument");
+  if (stat != GM_STAT_MEDIAN && stat != GM_STAT_PERCENTILE)
+    return fail("gm_segment_order_stat: median or percentile expected");
+  for (int64_t i = 0; i < n_segments; ++i)
+    if (offsets[i + 1] - offsets[i] > 0x7fffffffLL) return fail("gm_segment_order_stat: segment too long");
+  cudaStream_t s = resolve_stream(stream);
+  int rc = 0;
+  GM_RASTER_DISPATCH(dtype, run_segment_select<T>(values, offsets, n_segments, stat, q, out, s),
+                     "gm_segment_order_stat")
+  return rc;
+}
 
 extern "C" int gm_rasterize_polygons(const GmPolygons* polys, const double geo[6],
                                      const void* burn_values, const void* nodata, GmArray* dst,

@@ -1,0 +1,402 @@
+"""Row-stripe sharding of the raster path over the GPUs of one box.
+
+The reference's only spatial parallelism is ``RasterTiler``
+(raster/parallelize.py:43-125): split a ``vals`` request into tiles, compute them
+independently, stitch.  This module is that idea across processes -- one process
+per GPU, ``torch.distributed`` for the plumbing (NCCL on GPUs, gloo in the CPU
+tests) -- with the three exchanges the path needs:
+
+* element-wise / misc / temporal / rasterise: pixels are independent; every rank
+  evaluates the request of its own row stripe, no collective (`stripe_request`,
+  `get_data_striped`);
+* stencils: one neighbour exchange of `halo` rows before the kernel
+  (`exchange_halo`, `stencil_striped`); the outer boundary is padded with no
+  data exactly like a source does outside its extent;
+* zonal statistics: every rank reduces the polygons over its stripe into
+  (count, sum, min, max) partials, one all-reduce of N-vectors finishes them
+  (`allreduce_partials`, `finalize_partials`, `zonal_striped`); order statistics
+  route each polygon's values to its owner rank ``p % world``
+  (`exchange_segments`) where `segment_order_statistic` selects them.
+
+Everything that talks to ``torch.distributed`` works on CPU tensors as well, so the
+N > 1 logic is covered by world-size-2 gloo tests without a GPU; the compute
+calls themselves always go through libgeokernels.so.
+"""
+import numpy as np
+
+__all__ = [
+    "stripe_rows", "stripe_request", "get_data_striped", "exchange_halo", "pad_columns",
+    "stencil_striped", "allreduce_partials", "finalize_partials", "zonal_striped",
+    "exchange_segments", "segment_order_statistic",
+]
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def _world(group=None):
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+# ---------------------------------------------------------------------------
+# stripes
+# ---------------------------------------------------------------------------
+
+
+def stripe_rows(height, world):
+    """[(r0, r1)] per rank: contiguous row ranges that differ by at most one row."""
+    base, extra = divmod(int(height), int(world))
+    bounds, r0 = [], 0
+    for rank in range(world):
+        r1 = r0 + base + (1 if rank < extra else 0)
+        bounds.append((r0, r1))
+        r0 = r1
+    return bounds
+
+
+def stripe_request(request, rank, world):
+    """The request of `rank`'s row stripe and its (r0, r1) in the full request grid.
+
+    Row 0 is the northern edge (utils.GeoTransform.from_bbox), so stripe rows
+    [r0, r1) span y in [y2 - r1*dy, y2 - r0*dy]."""
+    x1, y1, x2, y2 = request["bbox"]
+    height = request["height"]
+    r0, r1 = stripe_rows(height, world)[rank]
+    dy = (y2 - y1) / height
+    sub = dict(request)
+    sub["bbox"] = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
+    sub["height"] = r1 - r0
+    return sub, (r0, r1)
+
+
+def get_data_striped(view, group=None, gather=False, **request):
+    """Evaluate ``view.get_data(**request)`` as row stripes, one per rank.
+
+    Returns this rank's stripe (a response dict, or None for empty data) and its
+    row range; with ``gather=True`` every rank receives the stitched full result
+    instead (RasterTiler's stitch, raster/parallelize.py:93-125)."""
+    rank, world = _world(group)
+    sub, rows = stripe_request(request, rank, world)
+    local = None if sub["height"] == 0 else view.get_data(**sub)
+    if not gather or world == 1:
+        return local, rows
+    dist = _dist()
+    parts = [None] * world
+    dist.all_gather_object(parts, local, group=group)
+    parts = [p for p in parts if p is not None]
+    if not parts:
+        return None, (0, request["height"])
+    if "values" not in parts[0]:
+        return parts[0], (0, request["height"])
+    values = np.concatenate([p["values"] for p in parts], axis=1)
+    return {"values": values, "no_data_value": parts[0]["no_data_value"]}, (0, request["height"])
+
+
+# ---------------------------------------------------------------------------
+# stencils: halo exchange
+# ---------------------------------------------------------------------------
+
+
+def exchange_halo(local, halo, fill, group=None):
+    """(bands, rows, width) stripe -> (bands, rows + 2*halo, width): `halo` rows of the
+    northern neighbour on top, of the southern neighbour below, `fill` at the outer
+    boundary.  One grouped send/recv per neighbour (ncclSend/ncclRecv under NCCL)."""
+    import torch
+
+    rank, world = _world(group)
+    bands, rows, width = local.shape
+    out = torch.full((bands, rows + 2 * halo, width), fill, dtype=local.dtype, device=local.device)
+    out[:, halo:halo + rows] = local
+    if halo == 0 or world == 1:
+        return out
+    if rows < halo:
+        raise ValueError("stripe of {} rows is thinner than the halo of {} rows".format(rows, halo))
+    dist = _dist()
+    # gloo moves host memory: CUDA stripes are staged through the CPU (one-GPU tests);
+    # under NCCL the halos go GPU to GPU over NVLink
+    staged = local.is_cuda and dist.get_backend(group) != "nccl"
+    edge = (lambda t: t.cpu()) if staged else (lambda t: t.contiguous())
+    ops, landing = [], []
+    if rank > 0:  # northern neighbour
+        send = edge(local[:, :halo])
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+        landing.append((slice(0, halo), recv))
+    if rank < world - 1:  # southern neighbour
+        send = edge(local[:, rows - halo:])
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+        landing.append((slice(halo + rows, 2 * halo + rows), recv))
+    for work in dist.batch_isend_irecv(ops):
+        work.wait()
+    for where, recv in landing:
+        out[:, where] = recv.to(out.device)
+    return out
+
+
+def pad_columns(values, halo, fill):
+    """Add `halo` columns of `fill` on both sides (the x halo a stencil block requests;
+    stripes span the full width, so this is always the outer boundary)."""
+    import torch
+
+    if halo == 0:
+        return values
+    bands, rows, width = values.shape
+    out = torch.full((bands, rows, width + 2 * halo), fill, dtype=values.dtype, device=values.device)
+    out[:, :, halo:halo + width] = values
+    return out
+
+
+def _as_payload(tensor):
+    """torch tensor -> what a block's ``process`` accepts (DeviceArray on CUDA, numpy on CPU)."""
+    if tensor.device.type == "cuda":
+        from . import _native
+
+        tensor = tensor.contiguous()
+        return _native.DeviceArray(tuple(tensor.shape), str(tensor.dtype).replace("torch.", ""),
+                                   ptr=tensor.data_ptr(), owner=tensor)
+    return tensor.numpy()
+
+
+def stencil_striped(process, local, no_data_value, halo_rows, halo_cols, *process_args, group=None):
+    """Run a stencil block's ``process`` (Smooth, MovingMax, Dilate, HillShade) on a row
+    stripe of a raster that is sharded over the ranks.
+
+    `local` is this rank's (bands, rows, width) torch tensor.  The halo the block
+    would have requested from its store (raster/spatial.py:27-108) is assembled from the
+    neighbours (`exchange_halo`) and from no data at the outer boundary, so the stitched
+    result equals the single-GPU result of the whole raster."""
+    haloed = exchange_halo(local, halo_rows, no_data_value, group)
+    haloed = pad_columns(haloed, halo_cols, no_data_value)
+    from .core import fusion
+
+    with fusion.device_resident():
+        return process({"values": _as_payload(haloed), "no_data_value": no_data_value}, *process_args)
+
+
+# ---------------------------------------------------------------------------
+# zonal statistics: partials + all-reduce
+# ---------------------------------------------------------------------------
+
+PARTIAL_DTYPE = np.dtype([("count", "<i8"), ("sum", "<f8"), ("vmin", "<f8"), ("vmax", "<f8")])
+
+
+def allreduce_partials(partial, covered, group=None, device=None):
+    """Combine per-stripe (count, sum, min, max)[N] partials and covered-cell counts
+    over all ranks: three all-reduces (sum / min / max) of N-vectors."""
+    import torch
+
+    rank, world = _world(group)
+    partial = np.asarray(partial, dtype=PARTIAL_DTYPE)
+    covered = np.asarray(covered, dtype=np.int64)
+    if world == 1:
+        return partial.copy(), covered.copy()
+    dist = _dist()
+    dev = device or ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    counts = torch.from_numpy(np.stack([partial["count"], covered])).to(dev)
+    sums = torch.from_numpy(np.ascontiguousarray(partial["sum"])).to(dev)
+    mins = torch.from_numpy(np.ascontiguousarray(partial["vmin"])).to(dev)
+    maxs = torch.from_numpy(np.ascontiguousarray(partial["vmax"])).to(dev)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    out = np.empty(len(partial), dtype=PARTIAL_DTYPE)
+    counts = counts.cpu().numpy()
+    out["count"], covered = counts[0], counts[1]
+    out["sum"], out["vmin"], out["vmax"] = sums.cpu().numpy(), mins.cpu().numpy(), maxs.cpu().numpy()
+    return out, covered
+
+
+def finalize_partials(partial, statistic):
+    """float32 statistic per polygon from reduced partials (the arithmetic of
+    zonal_finalize_kernel: f64 sum / f64 count -> f32; NaN where nothing was active)."""
+    partial = np.asarray(partial, dtype=PARTIAL_DTYPE)
+    out = np.full(len(partial), np.nan, dtype=np.float32)
+    has = partial["count"] > 0
+    if statistic == "count":
+        out[has] = partial["count"][has].astype(np.float64).astype(np.float32)
+    elif statistic == "sum":
+        out[has] = partial["sum"][has].astype(np.float32)
+    elif statistic == "mean":
+        out[has] = (partial["sum"][has] / partial["count"][has].astype(np.float64)).astype(np.float32)
+    elif statistic == "min":
+        out[has] = partial["vmin"][has].astype(np.float32)
+    elif statistic == "max":
+        out[has] = partial["vmax"][has].astype(np.float32)
+    else:
+        raise ValueError("not a reducible statistic: {}".format(statistic))
+    return out
+
+
+def zonal_striped(geometries, local, no_data_value, bbox, height, rows, statistic, percentile=None,
+                  threshold_values=None, group=None):
+    """Zonal statistic of a raster that is sharded in row stripes.
+
+    `local` is this rank's (1, r1 - r0, width) stripe (numpy, DeviceArray or CUDA tensor),
+    `bbox`/`height` describe the FULL raster grid, `rows` = (r0, r1).  Returns the float32
+    statistic per geometry (identical on every rank) and the indices of geometries that
+    cover no cell centre anywhere."""
+    import ctypes
+
+    from . import _native, utils
+    from .geometry.aggregate import _STAT_CODES, _frame_descriptor
+    from .raster._program import sentinel
+
+    if hasattr(local, "data_ptr"):
+        local = _as_payload(local)
+    r0, r1 = rows
+    x1, y1, x2, y2 = bbox
+    dy = (y2 - y1) / height
+    stripe_bbox = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
+    soup = geometries if isinstance(geometries, utils.PolygonSoup) else utils.PolygonSoup(list(geometries))
+    n = soup.n_polygons
+    partial = np.zeros(n, dtype=PARTIAL_DTYPE)
+    partial["vmin"], partial["vmax"] = np.finfo(np.float64).max, -np.finfo(np.float64).max
+    covered = np.zeros(n, dtype=np.int64)
+    order_stat = statistic in ("median", "percentile")
+    counts = values = None
+    if r1 > r0 and n > 0:
+        _, h, w = local.shape
+        geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, h, w))
+        s = sentinel(local.dtype, no_data_value)
+        holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, local.dtype)
+        thresholds = None
+        if threshold_values is not None:
+            thresholds = np.ascontiguousarray(threshold_values, dtype=np.float32)
+        polys = soup.as_struct()
+        desc = _frame_descriptor(local, 0)
+        lib = _native.lib()
+        _native.check(lib.gm_zonal_stats(
+            ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
+            _STAT_CODES["sum"], 0.0, None if thresholds is None else thresholds.ctypes.data, 0, h,
+            None, covered.ctypes.data, partial.ctypes.data, _native.current_stream()))
+        if order_stat:
+            counts, values = _native.zonal_values(desc, nodata_ptr, int(s is not None), polys, geo,
+                                                  thresholds, partial["count"])
+    partial, covered = allreduce_partials(partial, covered, group)
+    no_cells = np.nonzero(covered == 0)[0].tolist()
+    if not order_stat:
+        return finalize_partials(partial, statistic), no_cells
+    if counts is None:
+        counts, values = np.zeros(n, dtype=np.int64), np.zeros(0, dtype=np.asarray(local[:0]).dtype if not _native.is_device(local) else local.dtype)
+    owned, offsets, merged = exchange_segments(counts, values, group)
+    mine = segment_order_statistic(merged, offsets, statistic, percentile)
+    return _gather_owned(mine, owned, n, group), no_cells
+
+
+# ---------------------------------------------------------------------------
+# order statistics: route every polygon's values to its owner
+# ---------------------------------------------------------------------------
+
+
+def exchange_segments(counts, values, group=None):
+    """All-to-all-v of per-polygon value segments.
+
+    `values` holds this rank's active cell values packed polygon by polygon
+    (`counts[p]` values for polygon p).  Polygon p is owned by rank ``p % world``.
+    Returns (owned polygon ids, segment offsets, values) for this rank, where the
+    values of an owned polygon are the concatenation over all ranks."""
+    import torch
+
+    rank, world = _world(group)
+    counts = np.asarray(counts, dtype=np.int64)
+    values = np.ascontiguousarray(values)
+    n = len(counts)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    owned = np.arange(rank, n, world)
+    if world == 1:
+        return owned, starts.copy(), values
+    dist = _dist()
+    # every rank learns every rank's counts (N int64 each)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    all_counts = [torch.empty(n, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_counts, torch.from_numpy(counts).to(dev), group=group)
+    all_counts = np.stack([c.cpu().numpy() for c in all_counts])  # (world, N)
+    # pack what goes to each destination: its polygons in ascending order
+    send_chunks, send_sizes = [], []
+    for dest in range(world):
+        ids = np.arange(dest, n, world)
+        chunk = [values[starts[p]:starts[p + 1]] for p in ids]
+        chunk = np.concatenate(chunk) if chunk else values[:0]
+        send_chunks.append(chunk)
+        send_sizes.append(len(chunk))
+    recv_sizes = [int(all_counts[src, owned].sum()) for src in range(world)]
+    send = torch.from_numpy(np.concatenate(send_chunks) if send_chunks else values[:0]).to(dev)
+    recv = torch.empty(sum(recv_sizes), dtype=send.dtype, device=dev)
+    if dev == "cuda":
+        dist.all_to_all_single(recv, send, recv_sizes, send_sizes, group=group)
+    else:  # gloo has no all_to_all_single for uneven splits on every build: grouped send/recv
+        ops, pieces, at = [], [], 0
+        for src in range(world):
+            pieces.append(recv[at:at + recv_sizes[src]])
+            at += recv_sizes[src]
+        at = 0
+        for dest in range(world):
+            piece = send[at:at + send_sizes[dest]]
+            at += send_sizes[dest]
+            if dest == rank:
+                pieces[rank].copy_(piece)
+                continue
+            if send_sizes[dest]:
+                ops.append(dist.P2POp(dist.isend, piece.contiguous(), dest, group))
+        for src in range(world):
+            if src != rank and recv_sizes[src]:
+                ops.append(dist.P2POp(dist.irecv, pieces[src], src, group))
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+    recv = recv.cpu().numpy()
+    # received layout: for each source rank, its segments of my polygons in ascending id order;
+    # regroup per polygon
+    per_src_starts, at = [], 0
+    for src in range(world):
+        c = all_counts[src, owned]
+        per_src_starts.append(at + np.concatenate([[0], np.cumsum(c)]))
+        at += int(c.sum())
+    totals = all_counts[:, owned].sum(axis=0)
+    offsets = np.concatenate([[0], np.cumsum(totals)]).astype(np.int64)
+    merged = np.empty(int(offsets[-1]), dtype=values.dtype)
+    for k in range(len(owned)):
+        at = offsets[k]
+        for src in range(world):
+            a, b = per_src_starts[src][k], per_src_starts[src][k + 1]
+            merged[at:at + (b - a)] = recv[a:b]
+            at += b - a
+    return owned, offsets, merged
+
+
+def segment_order_statistic(values, offsets, statistic, percentile=None):
+    """Median / percentile of every segment ``values[offsets[k]:offsets[k+1]]`` on the GPU
+    (radix select of libgeokernels.so; the interpolation arithmetic of
+    measurements.py:132-137 and scipy.ndimage's median)."""
+    from . import _native
+
+    return _native.segment_order_statistic(np.ascontiguousarray(values), np.asarray(offsets, dtype=np.int64),
+                                           statistic, percentile)
+
+
+def _gather_owned(mine, owned, n, group=None):
+    """Every rank contributes the results of its own polygons; all ranks get all N."""
+    import torch
+
+    rank, world = _world(group)
+    out = np.full(n, np.nan, dtype=np.float32)
+    out[owned] = mine
+    if world == 1:
+        return out
+    dist = _dist()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    # NaN marks "not mine": a max-reduce over ranks would lose NaN results, so gather instead
+    gathered = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(out).to(dev), group=group)
+    for src in range(world):
+        ids = np.arange(src, n, world)
+        out[ids] = gathered[src].cpu().numpy()[ids]
+    return out

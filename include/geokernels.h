@@ -256,6 +256,18 @@ int  gm_zonal_stats(const GmArray* raster, const void* nodata, int has_nodata,
                     float* out, int64_t* covered, GmZonalPartial* partial,
                     void* stream);
 
+/* Multi-GPU order statistics (measurements.py:18-137): a rank
+ * extracts the ACTIVE cell values under every polygon of its row stripe
+ * (counts[p] = partial[p].count of a previous gm_zonal_stats call; values are
+ * packed polygon by polygon, `values` has sum(counts) elements of the raster
+ * dtype), the segments are routed to the polygons' owner ranks, and the owner
+ * selects median / percentile per segment with the reference's interpolation. */
+int  gm_zonal_values(const GmArray* raster, const void* nodata, int has_nodata,
+                     const GmPolygons* polys, const double geo[6], const float* thresholds,
+                     const int64_t* counts, void* values, void* stream);
+int  gm_segment_order_stat(const void* values, int32_t dtype, const int64_t* offsets,
+                           int64_t n_segments, int stat, double q, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
