@@ -26,7 +26,7 @@ import numpy as np
 
 __all__ = [
     "stripe_rows", "stripe_request", "get_data_striped", "exchange_halo", "pad_columns",
-    "stencil_striped", "allreduce_partials", "finalize_partials", "zonal_striped",
+    "stencil_striped", "smooth_halo", "allreduce_partials", "finalize_partials", "zonal_striped",
     "exchange_segments", "segment_order_statistic",
 ]
 
@@ -151,6 +151,13 @@ def pad_columns(values, halo, fill):
     out = torch.full((bands, rows, width + 2 * halo), fill, dtype=values.dtype, device=values.device)
     out[:, :, halo:halo + width] = values
     return out
+
+
+def smooth_halo(size_px):
+    """Rows a stripe needs from each neighbour for Smooth to equal the whole-raster result:
+    the Gaussian radius int(4 * sigma + 0.5) with sigma = size_px / 3 (scipy.ndimage), which
+    exceeds the round(size_px) margin the block itself crops (raster/spatial.py:293-295)."""
+    return int(4.0 * (float(size_px) / 3.0) + 0.5)
 
 
 def _as_payload(tensor):

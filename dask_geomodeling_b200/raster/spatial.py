@@ -207,7 +207,9 @@ class Smooth(BaseSingle):
         wx, lx = _gaussian_weights(size_px[1] / 3)
         holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
         if mode == "exact":
-            my, mx = [int(round(s)) for s in size_px]
+            # "margin" (rows, cols) overrides the cropped halo: row stripes carry the full
+            # filter radius from their neighbours (parallel.stencil_striped)
+            my, mx = process_kwargs.get("margin") or [int(round(s)) for s in size_px]
             out_shape = (t, ny - 2 * my, nx - 2 * mx)
             zoom, zy, zx, oy, ox = 0, 1.0, 1.0, 0.0, 0.0
         else:

@@ -86,8 +86,11 @@ def _stencil_worker(rank, world):
     expected, _ = R.moving_max(whole(5), nodata, 11)
     np.testing.assert_array_equal(np.asarray(got["values"]), expected[:, r0:r1])
 
-    kwargs = dict(smooth_mode="exact", fill=0, size=[5.0, 5.0])
-    got = parallel.stencil_striped(raster.Smooth.process, local, nodata, 5, 5, kwargs)
+    # Smooth: the stripe needs the full Gaussian radius (7 rows), not only the cropped margin (5)
+    lw = parallel.smooth_halo(5.0)
+    assert lw == 7
+    kwargs = dict(smooth_mode="exact", fill=0, size=[5.0, 5.0], margin=(lw, 5))
+    got = parallel.stencil_striped(raster.Smooth.process, local, nodata, lw, 5, kwargs)
     expected, _ = R.smooth(whole(5), nodata, (5.0, 5.0), 0, "exact")
     np.testing.assert_array_equal(np.asarray(got["values"]), expected[:, r0:r1])
 
