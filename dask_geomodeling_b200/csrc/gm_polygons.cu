@@ -30,6 +30,10 @@ constexpr int PG_WARPS = PG_THREADS / 32;
 constexpr int PG_MAX_CROSSINGS = 4096;        // per scanline
 constexpr int PG_MAX_HSPANS = 8;
 constexpr int SEL_THREADS = 256;
+constexpr int PG_FAST_MAXV = 64;             // vertices of a polygon handled lane-per-scanline
+constexpr int PG_FAST_MAXC = 8;              // crossings per scanline on that path
+constexpr int PG_FAST_WARPS = SEL_THREADS / 32;
+constexpr int PG_BATCH = 4;                 // single-span rows handed to a visitor at once
 
 struct PolyDev {
   const double* px;             // pixel-space x of every vertex
@@ -131,6 +135,19 @@ __device__ __forceinline__ bool in_pairs(int x, const int* buf, int count) {
   return false;
 }
 
+// default: one span at a time (visitors that gain from batching overload this)
+template <class Visitor>
+__device__ __forceinline__ void span_batch(Visitor& vis, int n, const int* ys, const int* x0, const int* x1) {
+  for (int i = 0; i < n; ++i)
+    if (x0[i] <= x1[i]) vis.span(ys[i], x0[i], x1[i]);
+}
+template <typename T> struct ReduceVisitor;
+template <typename T> struct GatherVisitor;
+template <typename T>
+__device__ __forceinline__ void span_batch(GatherVisitor<T>& vis, int n, const int* ys, const int* x0, const int* x1);
+template <typename T>
+__device__ __forceinline__ void span_batch(ReduceVisitor<T>& vis, int n, const int* ys, const int* x0, const int* x1);
+
 // Visitor interface (all calls are warp-uniform):
 //   span(y, x0, x1)                       regular even-odd span, inclusive, clipped
 //   hspan(y, x0, x1, buf, count)          bottom horizontal edge on the scanline
@@ -151,7 +168,8 @@ __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* b
     }
     return;
   }
-  for (int y = miny + warp; y <= maxy; y += nwarps) {
+  // generic scanline: the whole warp works on ONE row (any number of vertices / crossings)
+  auto generic_row = [&](int y) {
     const double dy = y + 0.5;
     int count = 0, hcount = 0;
     for (int64_t r = r0; r < r1; ++r) {
@@ -221,6 +239,103 @@ __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* b
       const int x0 = hbuf[2 * h] < 0 ? 0 : hbuf[2 * h];
       const int x1 = hbuf[2 * h + 1] - 1 > maxx ? maxx : hbuf[2 * h + 1] - 1;
       if (x0 <= x1) vis.hspan(y, x0, x1, buf, count);
+    }
+    __syncwarp();
+    };
+
+  const int nv = (int)(v1 - v0);
+  if (nv > PG_FAST_MAXV) {
+    for (int y = miny + warp; y <= maxy; y += nwarps) generic_row(y);
+    return;
+  }
+
+  // Small polygons (<= PG_FAST_MAXV vertices, the usual case): the vertices are staged in
+  // shared memory once, then each warp takes 32 scanlines at a time -- lane = scanline --
+  // so the edge tests of 32 rows run in parallel instead of one row per warp; the
+  // crossings (same arithmetic as generic_row) are sorted per lane in shared memory and
+  // the spans are then walked by the whole warp row by row (coalesced raster reads).
+  // Rows with more than PG_FAST_MAXC crossings or a horizontal bottom edge fall back to
+  // generic_row.
+  __shared__ double s_px[PG_FAST_MAXV], s_py[PG_FAST_MAXV];
+  __shared__ int s_prev[PG_FAST_MAXV];
+  __shared__ int s_cross[PG_FAST_WARPS][PG_FAST_MAXC][32];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    s_px[i] = P.px[v0 + i];
+    s_py[i] = P.py[v0 + i];
+    int prev = i - 1;
+    for (int64_t r = r0; r < r1; ++r)
+      if ((int64_t)i + v0 == P.ring_offsets[r]) prev = (int)(P.ring_offsets[r + 1] - v0) - 1;
+    s_prev[i] = prev;
+  }
+  __syncthreads();
+  for (int base = miny + 32 * warp; base <= maxy; base += 32 * nwarps) {
+    const int y = base + lane;
+    const double dy = y + 0.5;
+    int cnt = 0;
+    bool complex_row = false;
+    if (y <= maxy) {
+      for (int i = 0; i < nv; ++i) {
+        const int ind1 = s_prev[i];
+        double dy1 = s_py[ind1], dy2 = s_py[i];
+        if ((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy)) continue;
+        double dx1, dx2;
+        if (dy1 < dy2) {
+          dx1 = s_px[ind1]; dx2 = s_px[i];
+        } else if (dy1 > dy2) {
+          const double t = dy1; dy1 = dy2; dy2 = t;
+          dx2 = s_px[ind1]; dx1 = s_px[i];
+        } else {
+          if (s_px[ind1] > s_px[i]) complex_row = true;  // bottom horizontal edge on the scanline
+          continue;
+        }
+        if (dy < dy2 && dy >= dy1) {
+          const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+          if (cnt < PG_FAST_MAXC) s_cross[warp][cnt][lane] = clamp_to_int(floor(intersect + 0.5));
+          ++cnt;
+        }
+      }
+      if (cnt > PG_FAST_MAXC) complex_row = true;
+      if (!complex_row)
+        for (int a = 1; a < cnt; ++a) {  // insertion sort of this lane's column
+          const int v = s_cross[warp][a][lane];
+          int j = a - 1;
+          while (j >= 0 && s_cross[warp][j][lane] > v) { s_cross[warp][j + 1][lane] = s_cross[warp][j][lane]; --j; }
+          s_cross[warp][j + 1][lane] = v;
+        }
+    }
+    __syncwarp();
+    const unsigned complex_mask = __ballot_sync(0xffffffffu, complex_row);
+    const int n_rows = min(32, maxy - base + 1);
+    for (int r = 0; r < n_rows; ++r) {
+      const int yy = base + r;
+      if ((complex_mask >> r) & 1u) { generic_row(yy); continue; }
+      const int c = __shfl_sync(0xffffffffu, cnt, r);
+      if (c == 2) {
+        // the usual case, one span per row: hand up to PG_BATCH consecutive such rows to the
+        // visitor together so that it can keep the raster reads of all of them in flight
+        int ys[PG_BATCH], xs0[PG_BATCH], xs1[PG_BATCH];
+        int nb = 0;
+        while (nb < PG_BATCH && r + nb < n_rows) {
+          const int rr = r + nb;
+          if (((complex_mask >> rr) & 1u) || __shfl_sync(0xffffffffu, cnt, rr) != 2) break;
+          const int xa = s_cross[warp][0][rr], xb = s_cross[warp][1][rr];
+          int x0 = 1, x1 = 0;  // empty unless the span touches the raster
+          if (xa <= maxx && xb > 0) { x0 = xa < 0 ? 0 : xa; x1 = xb - 1 > maxx ? maxx : xb - 1; }
+          ys[nb] = base + rr; xs0[nb] = x0; xs1[nb] = x1;
+          ++nb;
+        }
+        span_batch(vis, nb, ys, xs0, xs1);
+        r += nb - 1;
+        continue;
+      }
+      for (int i = 0; i + 1 < c; i += 2) {
+        const int xa = s_cross[warp][i][r], xb = s_cross[warp][i + 1][r];
+        if (xa <= maxx && xb > 0) {
+          const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
+          if (x0 <= x1) vis.span(yy, x0, x1);
+        }
+      }
     }
     __syncwarp();
   }
@@ -338,7 +453,7 @@ struct ActiveTest {
 template <typename T>
 struct ReduceVisitor {
   const T* raster; int width; ActiveTest<T> active;
-  long long count; double sum, vmin, vmax;
+  long long count, cells; double sum, vmin, vmax;
   __device__ __forceinline__ void take(T v) {
     if (active(v)) {
       const double d = (double)v;
@@ -349,21 +464,60 @@ struct ReduceVisitor {
   }
   __device__ __forceinline__ void span(int y, int x0, int x1) {
     const T* row = raster + (int64_t)y * width;
-    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) take(__ldg(row + x));
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) cells += x1 - x0 + 1;
+    int x = x0 + lane;
+    for (; x + 96 <= x1; x += 128) {  // four independent 128-byte requests in flight
+      const T a = __ldg(row + x), b = __ldg(row + x + 32), c = __ldg(row + x + 64), d = __ldg(row + x + 96);
+      take(a); take(b); take(c); take(d);
+    }
+    for (; x <= x1; x += 32) take(__ldg(row + x));
   }
   __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
     const T* row = raster + (int64_t)y * width;
+    int extra = 0;
     for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32)
-      if (!in_pairs(x, buf, n)) take(__ldg(row + x));
+      if (!in_pairs(x, buf, n)) { take(__ldg(row + x)); ++extra; }
+    cells += extra;   // per lane; summed over the warp with the other accumulators
   }
 };
+
+// PG_BATCH rows x 4 requests of 128 bytes are issued before the first value is consumed
+template <typename T>
+__device__ __forceinline__ void span_batch(ReduceVisitor<T>& vis, int n, const int* ys, const int* x0, const int* x1) {
+  const int lane = threadIdx.x & 31;
+  T v[PG_BATCH][4];
+  bool ok[PG_BATCH][4];
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b) {
+    const T* row = vis.raster + (int64_t)(b < n ? ys[b] : 0) * vis.width;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = (b < n ? x0[b] : 1) + lane + 32 * k;
+      ok[b][k] = b < n && x <= x1[b];
+      v[b][k] = ok[b][k] ? __ldg(row + x) : T(0);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b) {
+    if (b < n && lane == 0 && x0[b] <= x1[b]) vis.cells += x1[b] - x0[b] + 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[b][k]) vis.take(v[b][k]);
+  }
+  for (int b = 0; b < n; ++b) {  // rows longer than 128 cells: the rest
+    const T* row = vis.raster + (int64_t)ys[b] * vis.width;
+    for (int x = x0[b] + 128 + lane; x <= x1[b]; x += 32) vis.take(__ldg(row + x));
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(PG_THREADS)
 zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
-                    const float* __restrict__ thresholds, GmZonalPartial* __restrict__ partial) {
+                    const float* __restrict__ thresholds, GmZonalPartial* __restrict__ partial,
+                    long long* __restrict__ cells) {
   extern __shared__ int pg_smem[];
-  __shared__ long long s_count[PG_WARPS];
+  __shared__ long long s_count[PG_WARPS], s_cells[PG_WARPS];
   __shared__ double s_sum[PG_WARPS], s_min[PG_WARPS], s_max[PG_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* buf = pg_smem + warp * P.cap;
@@ -374,23 +528,26 @@ zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
     vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
     vis.active.has_threshold = thresholds != nullptr;
     vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
-    vis.count = 0; vis.sum = 0.0; vis.vmin = DBL_MAX; vis.vmax = -DBL_MAX;
+    vis.count = 0; vis.cells = 0; vis.sum = 0.0; vis.vmin = DBL_MAX; vis.vmax = -DBL_MAX;
     scan_polygon(P, p, buf, hbuf, vis);
     for (int o = 16; o > 0; o >>= 1) {
       vis.count += __shfl_xor_sync(0xffffffffu, vis.count, o);
+      vis.cells += __shfl_xor_sync(0xffffffffu, vis.cells, o);
       vis.sum += __shfl_xor_sync(0xffffffffu, vis.sum, o);
       vis.vmin = fmin(vis.vmin, __shfl_xor_sync(0xffffffffu, vis.vmin, o));
       vis.vmax = fmax(vis.vmax, __shfl_xor_sync(0xffffffffu, vis.vmax, o));
     }
-    if (lane == 0) { s_count[warp] = vis.count; s_sum[warp] = vis.sum; s_min[warp] = vis.vmin; s_max[warp] = vis.vmax; }
+    if (lane == 0) { s_count[warp] = vis.count; s_cells[warp] = vis.cells; s_sum[warp] = vis.sum; s_min[warp] = vis.vmin; s_max[warp] = vis.vmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
       GmZonalPartial r{0, 0.0, DBL_MAX, -DBL_MAX};
+      long long c = 0;
       for (int w = 0; w < PG_WARPS; ++w) {
-        r.count += s_count[w]; r.sum += s_sum[w];
+        r.count += s_count[w]; r.sum += s_sum[w]; c += s_cells[w];
         r.vmin = fmin(r.vmin, s_min[w]); r.vmax = fmax(r.vmax, s_max[w]);
       }
       partial[p] = r;
+      cells[p] = c;
     }
     __syncthreads();
   }
@@ -457,76 +614,152 @@ struct GatherVisitor {
   }
 };
 
-// key of rank r (0-based) among keys[0..n): MSD radix select, 8 bits per pass
+// PG_BATCH rows x 4 requests in flight, ONE cursor update for the whole batch
+template <typename T>
+__device__ __forceinline__ void span_batch(GatherVisitor<T>& vis, int n, const int* ys, const int* x0, const int* x1) {
+  const int lane = threadIdx.x & 31;
+  T v[PG_BATCH][4];
+  bool ok[PG_BATCH][4];
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b) {
+    const T* row = vis.raster + (int64_t)(b < n ? ys[b] : 0) * vis.width;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = (b < n ? x0[b] : 1) + lane + 32 * k;
+      ok[b][k] = b < n && x <= x1[b];
+      v[b][k] = ok[b][k] ? __ldg(row + x) : T(0);
+    }
+  }
+  int total = 0, mine[PG_BATCH][4];
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ok[b][k] = ok[b][k] && vis.active(v[b][k]);
+      const unsigned m = __ballot_sync(0xffffffffu, ok[b][k]);
+      mine[b][k] = total + __popc(m & ((1u << lane) - 1u));
+      total += __popc(m);
+    }
+  int base = 0;
+  if (lane == 0 && total > 0) base = atomicAdd(vis.cursor, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[b][k]) {
+        const long long pos = base + mine[b][k];
+        if (pos < vis.capacity) vis.keys[pos] = KeyOf<T>::key(v[b][k]);
+      }
+  for (int b = 0; b < n; ++b)  // rows longer than 128 cells: the rest
+    if (x0[b] + 128 <= x1[b]) vis.span(ys[b], x0[b] + 128, x1[b]);
+}
+
+// Keys of ranks rank_lo <= rank_hi <= rank_lo + 1 (0-based) among keys[0..n): MSD radix
+// select, 8 bits per level, block-wide.  `keys` is consumed: after every level each warp
+// compacts, in place and warp-synchronously, the candidates of its own slice that fall
+// into the selected digit, so level L+1 only sweeps what survived level L (a polygon's
+// values collapse from n to a few dozen after two levels).  When the two ranks part ways
+// at some level, the upper one is the smallest key of the next occupied digit.
+template <typename K> struct SelectScratch { int b_lo, b_hi; long long r_lo, r_hi; K min_key; };
+
+__device__ __forceinline__ unsigned atomic_min_key(unsigned* a, unsigned v) { return atomicMin(a, v); }
+__device__ __forceinline__ unsigned long long atomic_min_key(unsigned long long* a, unsigned long long v) {
+  return atomicMin(a, v);
+}
+
 template <typename K>
-__device__ K block_select(const K* keys, int n, long long rank, int* hist, K* shared_prefix) {
+__device__ void block_select2(K* keys, int n, long long rank_lo, long long rank_hi, K* out_lo, K* out_hi,
+                              int* hist, SelectScratch<K>* sc) {
   constexpr int BITS = sizeof(K) * 8;
-  K prefix = 0, mask = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int slice = (n + nwarps - 1) / nwarps;
+  const int begin = min(warp * slice, n);
+  int cnt = min(begin + slice, n) - begin;   // candidates left in this warp's slice
+  K* mine = keys + begin;
+  K prefix = 0, khi = 0;
+  bool diverged = false;                     // block-uniform: rank_hi already resolved
   for (int shift = BITS - 8; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) sc->min_key = ~(K)0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const K k = keys[i];
-      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      long long r = rank;
-      int b = 0;
-      for (; b < 255; ++b) {
-        if (r < hist[b]) break;
-        r -= hist[b];
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      const bool live = i < cnt;
+      const int digit = live ? (int)((mine[i] >> shift) & 0xff) : 256 + lane;
+      if (shift == BITS - 8) {
+        // first level: a handful of digits (exponents) hold everything -> one add per digit
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (live && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+      } else if (live) {
+        atomicAdd(&hist[digit], 1);
       }
-      shared_prefix[0] = prefix | ((K)b << shift);
-      shared_prefix[1] = (K)r;
     }
     __syncthreads();
-    prefix = shared_prefix[0];
-    rank = (long long)shared_prefix[1];
-    mask |= ((K)0xff << shift);
+    if (warp == 0) {  // which digit holds each rank: 8 bins per lane + warp scan
+      int local[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { local[j] = hist[lane * 8 + j]; sum += local[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int excl = incl - sum;
+      if (rank_lo >= excl && rank_lo < incl) {
+        long long r = rank_lo - excl;
+        int j = 0;
+        while (r >= local[j]) { r -= local[j]; ++j; }
+        sc->b_lo = lane * 8 + j; sc->r_lo = r;
+      }
+      if (!diverged && rank_hi >= excl && rank_hi < incl) {
+        long long r = rank_hi - excl;
+        int j = 0;
+        while (r >= local[j]) { r -= local[j]; ++j; }
+        sc->b_hi = lane * 8 + j; sc->r_hi = r;
+      }
+    }
+    __syncthreads();
+    const int b_lo = sc->b_lo;
+    rank_lo = sc->r_lo;
+    if (!diverged) {
+      const int b_hi = sc->b_hi;
+      if (b_hi != b_lo) {  // the upper rank leaves the path: smallest key of digit b_hi
+        K m = ~(K)0;
+        for (int i = lane; i < cnt; i += 32) {
+          const K k = mine[i];
+          if ((int)((k >> shift) & 0xff) == b_hi && k < m) m = k;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const K other = __shfl_xor_sync(0xffffffffu, m, o);
+          m = other < m ? other : m;
+        }
+        if (lane == 0) atomic_min_key(&sc->min_key, m);
+        __syncthreads();
+        khi = sc->min_key;
+        diverged = true;
+      } else {
+        rank_hi = sc->r_hi;
+      }
+    }
+    int out = 0;
+    for (int i0 = 0; i0 < cnt; i0 += 32) {
+      const int i = i0 + lane;
+      const bool live = i < cnt;
+      const K k = live ? mine[i] : (K)0;
+      const bool keep = live && (int)((k >> shift) & 0xff) == b_lo;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) mine[out + __popc(m & ((1u << lane) - 1u))] = k;
+      out += __popc(m);
+      __syncwarp();
+    }
+    cnt = out;
+    prefix |= (K)b_lo << shift;
     __syncthreads();
   }
-  return prefix;
-}
-
-// smallest key greater than `key` (only called when it exists)
-template <typename K>
-__device__ K block_next_above(const K* keys, int n, K key, K* scratch) {
-  K best = ~(K)0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const K k = keys[i];
-    if (k > key && k < best) best = k;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    const K other = __shfl_xor_sync(0xffffffffu, best, o);
-    best = other < best ? other : best;
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    K b = scratch[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) b = scratch[w] < b ? scratch[w] : b;
-    scratch[0] = b;
-  }
-  __syncthreads();
-  best = scratch[0];
-  __syncthreads();
-  return best;
-}
-
-template <typename K>
-__device__ int block_count_le(const K* keys, int n, K key, int* counter) {
-  if (threadIdx.x == 0) *counter = 0;
-  __syncthreads();
-  int c = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) c += keys[i] <= key;
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(counter, c);
-  __syncthreads();
-  c = *counter;
-  __syncthreads();
-  return c;
+  *out_lo = prefix;
+  *out_hi = diverged ? khi : prefix;
 }
 
 // result of the order statistic in the reference's arithmetic
@@ -543,10 +776,11 @@ template <typename T> __device__ __forceinline__ float percentile_of(T lo, T hi,
   return (float)((double)lo + part * (double)diff);
 }
 
-// median / percentile of the n keys in `keys` in the reference's arithmetic (block-wide call)
+// median / percentile of the n keys in `keys` in the reference's arithmetic (block-wide
+// call; `keys` is consumed)
 template <typename T>
-__device__ float order_statistic(const typename KeyOf<T>::type* keys, int n, int stat, double q,
-                                 int* hist, typename KeyOf<T>::type* prefix_scratch, int* counter) {
+__device__ float order_statistic(typename KeyOf<T>::type* keys, int n, int stat, double q, int* hist,
+                                 SelectScratch<typename KeyOf<T>::type>* scratch) {
   typedef typename KeyOf<T>::type K;
   float result = __int_as_float(0x7fc00000);
   if (n > 0) {
@@ -560,12 +794,8 @@ __device__ float order_statistic(const typename KeyOf<T>::type* keys, int n, int
       hi_rank = (long long)ceil(frac);
       part = frac - floor(frac);
     }
-    const K klo = block_select<K>(keys, n, lo_rank, hist, prefix_scratch);
-    K khi = klo;
-    if (hi_rank != lo_rank) {
-      const int le = block_count_le<K>(keys, n, klo, counter);
-      if (le < hi_rank + 1) khi = block_next_above<K>(keys, n, klo, prefix_scratch);
-    }
+    K klo, khi;
+    block_select2<K>(keys, n, lo_rank, hi_rank, &klo, &khi, hist, scratch);
     const T lo = KeyOf<T>::value(klo), hi = KeyOf<T>::value(khi);
     result = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
   }
@@ -573,7 +803,7 @@ __device__ float order_statistic(const typename KeyOf<T>::type* keys, int n, int
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 3)
 zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
                     const float* __restrict__ thresholds, int stat, double q,
                     const long long* __restrict__ area, const long long* __restrict__ big_offset,
@@ -588,7 +818,7 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
   int* hbuf = cross + nw * P.cap + warp * 2 * PG_MAX_HSPANS;
   K* smem_keys = reinterpret_cast<K*>(sel_smem + ((size_t)(nw * P.cap + nw * 2 * PG_MAX_HSPANS) * sizeof(int) + 15) / 16 * 16);
   __shared__ int hist[256];
-  __shared__ K prefix_scratch[8];
+  __shared__ SelectScratch<K> select_scratch;
   __shared__ int cursor;
   for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
     const long long a = area[p];
@@ -605,7 +835,7 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
     __threadfence_block();
     __syncthreads();
     const int n = cursor;
-    const float result = order_statistic<T>(keys, n, stat, q, hist, prefix_scratch, &cursor);
+    const float result = order_statistic<T>(keys, n, stat, q, hist, &select_scratch);
     if (threadIdx.x == 0) out[p] = result;
     __syncthreads();
   }
@@ -685,14 +915,13 @@ segment_select_kernel(const T* __restrict__ values, const long long* __restrict_
                       float* __restrict__ out) {
   typedef typename KeyOf<T>::type K;
   __shared__ int hist[256];
-  __shared__ K prefix_scratch[8];
-  __shared__ int counter;
+  __shared__ SelectScratch<K> select_scratch;
   for (int64_t seg = blockIdx.x; seg < n_seg; seg += gridDim.x) {
     const long long a = offsets[seg], b = offsets[seg + 1];
     K* k = keys + a;
     for (long long i = threadIdx.x; i < b - a; i += blockDim.x) k[i] = KeyOf<T>::key(values[a + i]);
     __syncthreads();
-    const float result = order_statistic<T>(k, (int)(b - a), stat, q, hist, prefix_scratch, &counter);
+    const float result = order_statistic<T>(k, (int)(b - a), stat, q, hist, &select_scratch);
     if (threadIdx.x == 0) out[seg] = result;
     __syncthreads();
   }
@@ -844,22 +1073,30 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
     GM_TRY(cudaFuncSetAttribute(zonal_area_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
     GM_TRY(cudaFuncSetAttribute(zonal_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
   }
-  // pixel centres inside every polygon (no raster access): `covered` and buffer sizes
-  zonal_area_kernel<<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea);
-  GM_TRY(cudaGetLastError());
-  count_launch();
-  std::vector<long long> area(np_);
-  GM_TRY(cudaMemcpyAsync(area.data(), darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
-  GM_TRY(cudaStreamSynchronize(s));
-  if (covered) for (int64_t p = 0; p < np_; ++p) covered[p] = area[p];
-
   const bool order_stat = stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE;
-  if (!order_stat || partial) {
-    GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
-    zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
-        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial);
+  std::vector<long long> area(np_);
+  if (order_stat) {
+    // pixel centres inside every polygon (no raster access): `covered` and buffer sizes
+    zonal_area_kernel<<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea);
     GM_TRY(cudaGetLastError());
     count_launch();
+    GM_TRY(cudaMemcpyAsync(area.data(), darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+    GM_TRY(cudaStreamSynchronize(s));
+    if (covered) for (int64_t p = 0; p < np_; ++p) covered[p] = area[p];
+  }
+
+  if (!order_stat || partial) {
+    // one pass: partials and the covered-cell counts together
+    GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
+    zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
+        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial,
+        (long long*)darea);
+    GM_TRY(cudaGetLastError());
+    count_launch();
+    if (!order_stat && covered) {
+      static_assert(sizeof(long long) == sizeof(int64_t), "covered is int64");
+      GM_TRY(cudaMemcpyAsync(covered, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+    }
     if (partial)
       GM_TRY(cudaMemcpyAsync(partial, dpartial, sizeof(GmZonalPartial) * np_, cudaMemcpyDeviceToHost, s));
     if (out && !order_stat) {

@@ -654,7 +654,7 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
       const double* c = mid + lane * SMF_PITCH + run * SMF_RUN;
       double win[WIN];
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) win[i] = (run * SMF_RUN + i < SMF_TW) ? c[i] : 0.0;
+      for (int i = 0; i < WIN; ++i) win[i] = c[i];  // may run into the next row / the slack: only feeds outputs >= TX
 #pragma unroll
       for (int o = 0; o < SMF_RUN; ++o) {
         double tmp = win[o + L] * wts.wx[0];
@@ -680,7 +680,7 @@ static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata,
                               int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
                               cudaStream_t s) {
   constexpr int TX = SMF_TW - 2 * L;
-  const size_t smem = ((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH * sizeof(double);
+  const size_t smem = (((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH + 2 * SMF_MAXL) * sizeof(double);
   auto kernel = smooth_fast_kernel<T, L>;
   GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid3(W, H, bands, TX, SMF_TY), 256, smem, s>>>((const T*)in.dev, target, nd, has_nodata, fill,
