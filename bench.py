@@ -280,8 +280,11 @@ def run_b200(args):
         del result
 
     # ---- kernel-resident measurement: compile once, launch K times -------------
+    from dask_geomodeling_b200._compat import config as gm_config
+
     graph, name = view.get_compute_graph(**request)
-    fused = fusion.optimize(graph, name)
+    with gm_config.set({"geomodeling.stream": False}):  # resident launch, not the chunk pipeline
+        fused = fusion.optimize(graph, name)
     task = fused[name]
     assert task[0] is fusion.fused_process, "the chain did not fuse into one task"
     plan, leaf_keys = task[1], task[2:]

@@ -147,9 +147,15 @@ except ImportError:
             cache[key] = result
             return result
 
-        if isinstance(keys, list):
-            return tuple(evaluate(k) for k in keys)
-        return evaluate(keys)
+        # `resolve` and `evaluate` reference each other, so `cache` sits on a reference cycle:
+        # empty it explicitly, otherwise every intermediate raster (HBM) and every pinned
+        # result would stay alive until the cyclic garbage collector happens to run
+        try:
+            if isinstance(keys, list):
+                return tuple(evaluate(k) for k in keys)
+            return evaluate(keys)
+        finally:
+            cache.clear()
 
     def _hashable_key(x, dsk):
         try:

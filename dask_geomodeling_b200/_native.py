@@ -129,6 +129,9 @@ SYMBOLS = {
     "gm_memcpy_h2d": (_i, [_vp, _vp, _i64, _vp]),
     "gm_memcpy_d2h": (_i, [_vp, _vp, _i64, _vp]),
     "gm_memcpy_d2d": (_i, [_vp, _vp, _i64, _vp]),
+    "gm_memcpy_d2h_async": (_i, [_vp, _vp, _i64, _vp]),
+    "gm_stream_create": (_i, [_P(_vp)]),
+    "gm_stream_destroy": (_i, [_vp]),
     "gm_memcpy2d_h2d": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "gm_fill": (_i, [_vp, ctypes.c_int32, _vp, _i64, _vp]),
     "gm_eval_program": (_i, [_P(GmProgram), _P(GmArray), _P(GmArray), _i64, _vp]),
@@ -300,6 +303,7 @@ class DeviceArray:
         return "DeviceArray(shape={}, dtype={})".format(self.shape, self.dtype)
 
 
+STATS = {"pinned_allocations": 0}
 _pinned_free = {}          # nbytes -> [ptr, ...] page-locked blocks ready for reuse
 _pinned_cached_bytes = 0
 PINNED_CACHE_LIMIT = int(os.environ.get("GM_PINNED_CACHE_BYTES", 8 << 30))
@@ -337,6 +341,7 @@ def pinned_empty(shape, dtype):
         p = ctypes.c_void_p()
         check(lib().gm_host_alloc(ctypes.byref(p), nbytes))
         ptr = p.value
+        STATS["pinned_allocations"] += 1
     buf = (ctypes.c_uint8 * nbytes).from_address(ptr)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
     weakref.finalize(buf, _recycle_pinned, ptr, nbytes)
@@ -421,3 +426,19 @@ def segment_order_statistic(values, offsets, statistic, percentile=None):
         values.ctypes.data if values.size else None, dtype_code(values.dtype), offsets.ctypes.data, n,
         _ORDER_STATS[statistic], float(percentile or 0.0), out.ctypes.data, current_stream()))
     return out
+
+
+_pipeline_streams = []
+
+
+def pipeline_streams(n=3):
+    """`n` extra CUDA streams (created once) for chunk pipelines."""
+    while len(_pipeline_streams) < n:
+        p = ctypes.c_void_p()
+        check(lib().gm_stream_create(ctypes.byref(p)))
+        _pipeline_streams.append(p.value)
+    return _pipeline_streams[:n]
+
+
+def stream_sync(stream):
+    check(lib().gm_stream_sync(stream))

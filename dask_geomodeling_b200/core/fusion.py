@@ -14,7 +14,7 @@ import contextlib
 from .. import _native, _state
 from .._compat import config
 
-__all__ = ["optimize", "device_resident", "to_host", "fused_process"]
+__all__ = ["optimize", "device_resident", "to_host", "fused_process", "streamed_fused_process"]
 
 
 def _is_key(arg, graph):
@@ -89,6 +89,12 @@ def optimize(graph, name):
             plan = {"root": root, "nodes": {key: describe(key) for key in group}}
             # `describe` filled `leaves` in first-seen order
             out[root] = (fused_process, plan) + tuple(leaves)
+            if root == name:
+                sources = [_streamable_source(graph.get(leaf)) for leaf in leaves]
+                if sources and all(kw is not None for kw in sources) and _worth_streaming(sources):
+                    # the requested key itself, fed by in-memory sources only: upload, evaluate
+                    # and download in row chunks on rotating streams (dict literals, not keys)
+                    out[root] = (streamed_fused_process, plan) + tuple(sources)
             for key in group:
                 if key != root:
                     out.pop(key, None)
@@ -129,6 +135,103 @@ def build_expression(plan):
     return build(plan["root"])
 
 
+STREAM_MIN_PIXELS = 1 << 24      # below this one upload + one launch is as fast
+STREAM_CHUNK_PIXELS = 1 << 24    # pixels (all bands) per pipeline chunk
+
+
+def _streamable_source(task):
+    """The process_kwargs of a MemorySource ``vals`` task whose request is pixel-aligned
+    with the source (row_step == col_step == 1), else None."""
+    from ..raster.sources import RasterSourceBase, window_geometry
+    from .. import utils
+
+    if type(task) is not tuple or len(task) != 2 or task[0] is not RasterSourceBase.process:
+        return None
+    kw = task[1]
+    if not isinstance(kw, dict) or kw.get("mode") != "vals":
+        return None
+    bbox = kw["bbox"]
+    if bbox[0] == bbox[2] or bbox[1] == bbox[3] or kw["width"] == 0 or kw["height"] == 0:
+        return None
+    if not utils.same_projection(kw["projection"], kw["source_projection"]):
+        return None
+    _, col_step, _, row_step = window_geometry(kw["geo_transform"], bbox, kw["height"], kw["width"])
+    if col_step != 1.0 or row_step != 1.0:
+        return None
+    return kw
+
+
+def _worth_streaming(sources):
+    if not config.get("geomodeling.stream", True):
+        return False
+    first = sources[0]
+    bands = first["bands"][1] - first["bands"][0]
+    if any(kw["bands"][1] - kw["bands"][0] != bands or kw["height"] != first["height"]
+           or kw["width"] != first["width"] for kw in sources):
+        return False
+    return bands * first["height"] * first["width"] >= STREAM_MIN_PIXELS and bands >= 1
+
+
+def streamed_fused_process(plan, *sources):
+    """A fused group that is the requested key and reads only in-memory sources.
+
+    The request is cut in row chunks; chunk c is uploaded (pinned H2D), evaluated (one launch
+    of the compiled program) and downloaded (into the pinned result) on stream c % 3, so the
+    upload of a chunk overlaps the download of the previous one (PCIe is full duplex) and the
+    kernels hide behind both.  Results are identical to the unchunked evaluation: pixels are
+    independent and aligned requests crop rows without resampling arithmetic."""
+    import numpy as np
+
+    from .. import utils
+    from ..raster import _program
+    from ..raster.sources import RasterSourceBase, resample_window
+
+    def fallback():
+        with _state.device_resident(True):
+            payloads = [RasterSourceBase.process(kw) for kw in sources]
+            result = fused_process(plan, *payloads)
+        return to_host(result)
+
+    first = sources[0]
+    b0, b1 = first["bands"]
+    bands, height, width = b1 - b0, first["height"], first["width"]
+    rows = max(64, STREAM_CHUNK_PIXELS // max(bands * width, 1))
+    if height < 2 * rows:
+        return fallback()
+    leaf_types = [(np.dtype(kw["dtype"]), kw["fillvalue"].item()) for kw in sources]
+    try:
+        prog, compiler, results = _program.compile_expression([build_expression(plan)], leaf_types)
+    except _program.FusionLimit:
+        return fallback()
+    out_dtype = results[0].dtype
+    out = _native.pinned_empty((bands, height, width), out_dtype)
+    if config.get("geomodeling.pin-sources", True):
+        for kw in sources:
+            _native.pin(kw["array"])
+    lib = _native.lib()
+    streams = _native.pipeline_streams(3)
+    item = np.dtype(out_dtype).itemsize
+    for c, r0 in enumerate(range(0, height, rows)):
+        r1 = min(r0 + rows, height)
+        stream = streams[c % len(streams)]
+        with _native.use_stream(stream):
+            inputs = [
+                resample_window(kw["array"], kw["bands"], utils.GeoTransform(kw["geo_transform"]),
+                                kw["fillvalue"].item(), kw["bbox"], height, width, True, row_range=(r0, r1))
+                for kw in sources
+            ]
+            chunk, = _program.run_program(prog, inputs, [out_dtype], (bands, r1 - r0, width), True)
+            plane = (r1 - r0) * width * item
+            for band in range(bands):
+                _native.check(lib.gm_memcpy_d2h_async(
+                    out[band, r0:r1].ctypes.data, chunk.ptr + band * plane, plane, stream))
+            del inputs, chunk   # freed stream-ordered (cudaFreeAsync on this chunk's stream)
+    for stream in streams:
+        _native.stream_sync(stream)
+    del compiler
+    return {"values": out, "no_data_value": results[0].nodata}
+
+
 def _payload_is_raster(data):
     return isinstance(data, dict) and "values" in data
 
@@ -167,7 +270,10 @@ def fused_process(plan, *leaf_data):
         cache[key] = func(*args)
         return cache[key]
 
-    return run(plan["root"])
+    try:
+        return run(plan["root"])
+    finally:
+        cache.clear()  # `run` is recursive: break the cycle that would keep the rasters alive
 
 
 @contextlib.contextmanager

@@ -191,6 +191,28 @@ int gm_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream) {
   return 0;
 }
 
+int gm_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (ensure_init()) return 1;
+  if (bytes > 0)
+    GM_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, resolve_stream(stream)));
+  return 0;
+}
+
+int gm_stream_create(void** stream) {
+  if (ensure_init()) return 1;
+  if (!stream) return fail("gm_stream_create: null argument");
+  cudaStream_t s;
+  GM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  *stream = (void*)s;
+  return 0;
+}
+
+int gm_stream_destroy(void* stream) {
+  if (!stream) return 0;
+  GM_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+  return 0;
+}
+
 int gm_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
   if (ensure_init()) return 1;
   if (bytes > 0)

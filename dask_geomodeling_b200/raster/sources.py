@@ -34,13 +34,9 @@ def _window(n_target, first, step, n_source):
     return max(lo, 0), min(hi, n_source)
 
 
-def resample_window(array, bands, geo_transform, no_data_value, bbox, height, width, keep_on_device):
-    """Nearest-neighbour resample of ``array[bands[0]:bands[1]]`` into the request grid."""
-    lib = _native.lib()
-    stream = _native.current_stream()
-    b0, b1 = bands
-    n_bands = b1 - b0
-    _, src_h, src_w = array.shape
+def window_geometry(geo_transform, bbox, height, width):
+    """(col0, col_step, row0, row_step): target cell (i, j) reads source cell
+    (floor(row0 + i*row_step), floor(col0 + j*col_step))."""
     p, a, _, q, _, d = geo_transform
     x1, y1, x2, y2 = bbox
     tdx, tdy = (x2 - x1) / width, (y2 - y1) / height
@@ -50,6 +46,24 @@ def resample_window(array, bands, geo_transform, no_data_value, bbox, height, wi
     col_step = tdx / a
     row0 = (y2 - 0.5 * tdy - q) / d + 1e-10
     row_step = -tdy / d
+    return col0, col_step, row0, row_step
+
+
+def resample_window(array, bands, geo_transform, no_data_value, bbox, height, width, keep_on_device,
+                    row_range=None):
+    """Nearest-neighbour resample of ``array[bands[0]:bands[1]]`` into the request grid.
+
+    ``row_range=(r0, r1)`` produces only rows [r0, r1) of the request (used by the chunk
+    pipeline for pixel-aligned requests, where row_step == 1 keeps the arithmetic exact)."""
+    lib = _native.lib()
+    stream = _native.current_stream()
+    b0, b1 = bands
+    n_bands = b1 - b0
+    _, src_h, src_w = array.shape
+    col0, col_step, row0, row_step = window_geometry(geo_transform, bbox, height, width)
+    if row_range is not None:
+        row0 = row0 + row_range[0] * row_step
+        height = row_range[1] - row_range[0]
     c_lo, c_hi = _window(width, col0, col_step, src_w)
     r_lo, r_hi = _window(height, row0, row_step, src_h)
 

@@ -163,7 +163,11 @@ int  gm_host_register(void* ptr, int64_t bytes);           /* pin user memory  *
 int  gm_host_unregister(void* ptr);
 int  gm_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream);
 int  gm_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream);  /* syncs */
+int  gm_memcpy_d2h_async(void* dst, const void* src, int64_t bytes, void* stream);  /* no sync */
 int  gm_memcpy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+/* extra streams for chunk pipelines (upload / evaluate / download of row chunks overlap) */
+int  gm_stream_create(void** stream);
+int  gm_stream_destroy(void* stream);
 /* rectangle copy host->device: rows x row_bytes, pitches in bytes           */
 int  gm_memcpy2d_h2d(void* dst, int64_t dpitch, const void* src, int64_t spitch,
                      int64_t row_bytes, int64_t rows, void* stream);

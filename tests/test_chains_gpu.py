@@ -66,3 +66,55 @@ def test_window_requests_crop_and_pad():
     expected = np.zeros((1, 32, 32), dtype=np.uint8)
     expected[:, 8:, 8:] = full[:, 0:24, 0:24]
     np.testing.assert_array_equal(got["values"], expected)
+
+
+@pytest.fixture
+def small_stream_chunks(monkeypatch):
+    # make the chunk pipeline kick in at test sizes: 3 streams x chunks of >= 64 rows
+    monkeypatch.setattr(fusion, "STREAM_MIN_PIXELS", 1 << 12)
+    monkeypatch.setattr(fusion, "STREAM_CHUNK_PIXELS", 1 << 15)
+
+
+def test_streamed_chain_equals_oracle(small_stream_chunks):
+    size = 517  # ragged last chunk
+    ints, floats = workloads.cfg2_arrays(size, chunk=128)
+    isdata, step = workloads.cfg2_views(ints, floats)
+    request = workloads.request(size, size)
+    graph, name = step.get_compute_graph(**request)
+    assert fusion.optimize(graph, name)[name][0] is fusion.streamed_fused_process
+    (e_isdata, _), (e_step, e_nodata) = oracle_workloads.cfg2(ints, floats, workloads.CFG2_PAIRS)
+    got = step.get_data(**request)
+    np.testing.assert_array_equal(got["values"], e_step)
+    assert got["no_data_value"] == e_nodata
+    np.testing.assert_array_equal(isdata.get_data(**request)["values"], e_isdata)
+    with config.set({"geomodeling.stream": False}):
+        np.testing.assert_array_equal(step.get_data(**request)["values"], e_step)
+
+
+def test_streamed_chain_window_and_bands(small_stream_chunks):
+    # three frames, request window partly outside the source (pads with no data)
+    from dask_geomodeling_b200 import raster
+    from oracle import raster as R
+
+    rng = np.random.default_rng(9)
+    data = rng.uniform(0, 100, (3, 300, 260)).astype("f4")
+    nodata = workloads.F32_MAX
+    data[rng.random(data.shape) < 0.05] = nodata
+    src = raster.MemorySource(data, nodata, workloads.PROJECTION, pixel_size=1.0, pixel_origin=(0, 300),
+                              time_first=0, time_delta=3600000)
+    view = raster.Multiply(raster.Add(src, 1.5), src)
+    request = dict(mode="vals", bbox=(-10, -20, 250, 280), width=260, height=300,
+                   projection=workloads.PROJECTION, start=None, stop=None)
+    from datetime import datetime
+
+    request["start"], request["stop"] = datetime(1970, 1, 1), datetime(1970, 1, 1, 2)
+    graph, name = view.get_compute_graph(**request)
+    assert fusion.optimize(graph, name)[name][0] is fusion.streamed_fused_process
+    window = np.full((3, 300, 260), nodata, dtype="f4")
+    # row 0 of the request is y = 280 -> source row 20; column 0 is x = -10 -> 10 cells left of the source
+    window[:, 0:280, 10:260] = data[:, 20:300, 0:250]
+    s = R.elementwise("add", "float32", nodata, (window, nodata), 1.5)
+    expected = R.elementwise("multiply", "float32", nodata, s, (window, nodata))
+    got = view.get_data(**request)
+    assert got["values"].shape == (3, 300, 260)
+    np.testing.assert_array_equal(got["values"], expected[0])
