@@ -26,7 +26,7 @@ import numpy as np
 
 __all__ = [
     "stripe_rows", "stripe_request", "get_data_striped", "exchange_halo", "pad_columns",
-    "stencil_striped", "smooth_halo", "allreduce_partials", "finalize_partials", "zonal_striped",
+    "stencil_striped", "refresh_halo", "stencil_haloed", "smooth_halo", "allreduce_partials", "finalize_partials", "zonal_striped",
     "exchange_segments", "segment_order_statistic",
 ]
 
@@ -140,6 +140,43 @@ def exchange_halo(local, halo, fill, group=None):
     return out
 
 
+def refresh_halo(haloed, halo_rows, halo_cols=0, group=None):
+    """In-place halo exchange for a stripe that is STORED with its halo.
+
+    `haloed` is (bands, rows + 2*halo_rows, width + 2*halo_cols); its interior is this rank's
+    stripe.  The top/bottom `halo_rows` interior rows are sent to the neighbours and their
+    edge rows land in the halo rows -- only 2*halo_rows rows move, the stripe itself is not
+    copied (what a resident multi-GPU pipeline calls before every stencil step).  Halo rows
+    at the outer boundary and the halo columns keep whatever they hold (no data)."""
+    import torch
+
+    rank, world = _world(group)
+    if halo_rows == 0 or world == 1:
+        return haloed
+    dist = _dist()
+    rows = haloed.shape[1] - 2 * halo_rows
+    if rows < halo_rows:
+        raise ValueError("stripe of {} rows is thinner than the halo of {} rows".format(rows, halo_rows))
+    staged = haloed.is_cuda and dist.get_backend(group) != "nccl"
+    edge = (lambda t: t.cpu()) if staged else (lambda t: t.contiguous())
+    ops, landing = [], []
+    if rank > 0:
+        send = edge(haloed[:, halo_rows:2 * halo_rows])
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+        landing.append((slice(0, halo_rows), recv))
+    if rank < world - 1:
+        send = edge(haloed[:, rows:rows + halo_rows])
+        recv = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+        landing.append((slice(halo_rows + rows, 2 * halo_rows + rows), recv))
+    for work in dist.batch_isend_irecv(ops):
+        work.wait()
+    for where, recv in landing:
+        haloed[:, where] = recv.to(haloed.device)
+    return haloed
+
+
 def pad_columns(values, halo, fill):
     """Add `halo` columns of `fill` on both sides (the x halo a stencil block requests;
     stripes span the full width, so this is always the outer boundary)."""
@@ -181,6 +218,16 @@ def stencil_striped(process, local, no_data_value, halo_rows, halo_cols, *proces
     result equals the single-GPU result of the whole raster."""
     haloed = exchange_halo(local, halo_rows, no_data_value, group)
     haloed = pad_columns(haloed, halo_cols, no_data_value)
+    from .core import fusion
+
+    with fusion.device_resident():
+        return process({"values": _as_payload(haloed), "no_data_value": no_data_value}, *process_args)
+
+
+def stencil_haloed(process, haloed, no_data_value, halo_rows, halo_cols, *process_args, group=None):
+    """`stencil_striped` for a stripe stored with its halo (see `refresh_halo`): exchange the
+    halo rows in place, then run the block's ``process`` on the resident array."""
+    refresh_halo(haloed, halo_rows, halo_cols, group)
     from .core import fusion
 
     with fusion.device_resident():

@@ -75,6 +75,14 @@ def _halo_worker(rank, world, halo):
     assert (cols[:, :, :2] == fill).all() and (cols[:, :, -2:] == fill).all()
 
 
+    # the in-place variant on a stripe stored with its halo gives the same array
+    stored = parallel.pad_columns(parallel.exchange_halo(torch.from_numpy(full[:, r0:r1].copy()), halo, fill), 2, fill)
+    stored[:, :halo] = fill
+    stored[:, -halo:] = fill
+    parallel.refresh_halo(stored, halo, 2)
+    np.testing.assert_array_equal(stored.numpy(), cols)
+
+
 @pytest.mark.parametrize("halo", [1, 5, 7])
 def test_exchange_halo_two_ranks(halo):
     spawn(_halo_worker, halo)
