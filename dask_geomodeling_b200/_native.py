@@ -96,6 +96,7 @@ class GmPolygons(ctypes.Structure):
         ("n_polygons", ctypes.c_int64),
         ("n_rings", ctypes.c_int64),
         ("n_vertices", ctypes.c_int64),
+        ("resident", ctypes.c_void_p),
     ]
 
 
@@ -152,6 +153,8 @@ SYMBOLS = {
     "gm_rasterize_polygons": (_i, [_P(GmPolygons), _P(_d), _vp, _vp, _P(GmArray), _vp]),
     "gm_zonal_stats": (_i, [_P(GmArray), _vp, _i, _P(GmPolygons), _P(_d), _i, _d, _vp,
                             _i64, _i64, _vp, _vp, _vp, _vp]),
+    "gm_polygons_upload": (_i, [_P(GmPolygons), _P(_vp)]),
+    "gm_polygons_free": (_i, [_vp]),
     "gm_zonal_values": (_i, [_P(GmArray), _vp, _i, _P(GmPolygons), _P(_d), _vp, _vp, _vp, _vp]),
     "gm_segment_order_stat": (_i, [_vp, ctypes.c_int32, _vp, _i64, _i, _d, _vp, _vp]),
 }
@@ -442,3 +445,8 @@ def pipeline_streams(n=3):
 
 def stream_sync(stream):
     check(lib().gm_stream_sync(stream))
+
+
+def free_polygons(handle):
+    if _lib is not None and handle:
+        _lib.gm_polygons_free(handle)

@@ -939,16 +939,38 @@ __global__ void big_offsets_kernel(const long long* __restrict__ area, int64_t n
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+// Polygon soup kept in HBM between calls (gm_polygons_upload): the CSR arrays and the
+// largest vertex count, so that a request only runs the two small preparation kernels.
+struct ResidentPolygons {
+  void *xy = nullptr, *rings = nullptr, *polys = nullptr;
+  int64_t n_polygons = 0, n_rings = 0, n_vertices = 0, max_vertices = 1;
+};
+
 struct PolyUpload {
   void *xy = nullptr, *px = nullptr, *py = nullptr, *rings = nullptr, *polys = nullptr;
   void *miny = nullptr, *maxy = nullptr, *error = nullptr;
+  bool borrowed = false;   // xy / rings / polys belong to a ResidentPolygons
   PolyDev dev;
   cudaStream_t s;
   void release() {
-    void* all[] = {xy, px, py, rings, polys, miny, maxy, error};
-    for (void* p : all) if (p) cudaFreeAsync(p, s);
+    void* own[] = {px, py, miny, maxy, error};
+    for (void* p : own) if (p) cudaFreeAsync(p, s);
+    if (!borrowed) {
+      void* csr[] = {xy, rings, polys};
+      for (void* p : csr) if (p) cudaFreeAsync(p, s);
+    }
   }
 };
+
+static int64_t largest_polygon(const GmPolygons* polys) {
+  int64_t max_vertices = 1;
+  for (int64_t p = 0; p < polys->n_polygons; ++p) {
+    const int64_t a = polys->ring_offsets[polys->poly_offsets[p]];
+    const int64_t b = polys->ring_offsets[polys->poly_offsets[p + 1]];
+    if (b - a > max_vertices) max_vertices = b - a;
+  }
+  return max_vertices;
+}
 
 static int prepare_polygons(const GmPolygons* polys, const double* geo, int height, int width,
                             int64_t row_begin, int64_t row_end, PolyUpload& u, cudaStream_t s) {
@@ -957,17 +979,20 @@ static int prepare_polygons(const GmPolygons* polys, const double* geo, int heig
   if (geo[2] != 0.0 || geo[4] != 0.0 || geo[1] == 0.0 || geo[5] == 0.0)
     return fail("polygons: rotated or degenerate geotransform");
   const int64_t nv = polys->n_vertices, nr = polys->n_rings, np_ = polys->n_polygons;
-  int64_t max_vertices = 1;
-  for (int64_t p = 0; p < np_; ++p) {
-    const int64_t a = polys->ring_offsets[polys->poly_offsets[p]];
-    const int64_t b = polys->ring_offsets[polys->poly_offsets[p + 1]];
-    if (b - a > max_vertices) max_vertices = b - a;
-  }
+  const ResidentPolygons* resident = static_cast<const ResidentPolygons*>(polys->resident);
+  if (resident && (resident->n_polygons != np_ || resident->n_rings != nr || resident->n_vertices != nv))
+    return fail("polygons: resident handle does not match the descriptor");
+  const int64_t max_vertices = resident ? resident->max_vertices : largest_polygon(polys);
   int cap = 32;
   while (cap < max_vertices && cap < PG_MAX_CROSSINGS) cap <<= 1;
-  if (upload(&u.xy, polys->xy, sizeof(double) * 2 * nv, s)) return 1;
-  if (upload(&u.rings, polys->ring_offsets, sizeof(int64_t) * (nr + 1), s)) return 1;
-  if (upload(&u.polys, polys->poly_offsets, sizeof(int64_t) * (np_ + 1), s)) return 1;
+  if (resident) {
+    u.borrowed = true;
+    u.xy = resident->xy; u.rings = resident->rings; u.polys = resident->polys;
+  } else {
+    if (upload(&u.xy, polys->xy, sizeof(double) * 2 * nv, s)) return 1;
+    if (upload(&u.rings, polys->ring_offsets, sizeof(int64_t) * (nr + 1), s)) return 1;
+    if (upload(&u.polys, polys->poly_offsets, sizeof(int64_t) * (np_ + 1), s)) return 1;
+  }
   GM_CUDA(cudaMallocAsync(&u.px, sizeof(double) * (nv > 0 ? nv : 1), s));
   GM_CUDA(cudaMallocAsync(&u.py, sizeof(double) * (nv > 0 ? nv : 1), s));
   GM_CUDA(cudaMallocAsync(&u.miny, sizeof(int) * (np_ > 0 ? np_ : 1), s));
@@ -1223,6 +1248,37 @@ using namespace gm;
     case GM_F64: { typedef double T; rc = CALL; break; }                          \
     default: rc = fail(WHAT ": unsupported raster dtype");                        \
   }
+
+extern "C" int gm_polygons_upload(const GmPolygons* polys, void** handle) {
+  if (ensure_init()) return 1;
+  if (!polys || !handle) return fail("gm_polygons_upload: null argument");
+  cudaStream_t s = resolve_stream(nullptr);
+  ResidentPolygons* r = new ResidentPolygons();
+  r->n_polygons = polys->n_polygons; r->n_rings = polys->n_rings; r->n_vertices = polys->n_vertices;
+  r->max_vertices = largest_polygon(polys);
+  int rc = upload(&r->xy, polys->xy, sizeof(double) * 2 * r->n_vertices, s);
+  if (!rc) rc = upload(&r->rings, polys->ring_offsets, sizeof(int64_t) * (r->n_rings + 1), s);
+  if (!rc) rc = upload(&r->polys, polys->poly_offsets, sizeof(int64_t) * (r->n_polygons + 1), s);
+  if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail("gm_polygons_upload: copy failed");
+  if (rc) {
+    void* all[] = {r->xy, r->rings, r->polys};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+    delete r;
+    return 1;
+  }
+  *handle = r;
+  return 0;
+}
+
+extern "C" int gm_polygons_free(void* handle) {
+  if (!handle) return 0;
+  ResidentPolygons* r = static_cast<ResidentPolygons*>(handle);
+  cudaStream_t s = resolve_stream(nullptr);
+  void* all[] = {r->xy, r->rings, r->polys};
+  for (void* p : all) if (p) cudaFreeAsync(p, s);
+  delete r;
+  return 0;
+}
 
 extern "C" int gm_zonal_values(const GmArray* raster, const void* nodata, int has_nodata,
                                const GmPolygons* polys, const double geo[6], const float* thresholds,

@@ -96,6 +96,8 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     depth, height, width = values.shape
     # a ready-made PolygonSoup is accepted so that callers can reuse it between requests
     soup = geometries if isinstance(geometries, utils.PolygonSoup) else utils.PolygonSoup(list(geometries))
+    if depth > 1:
+        soup.to_device()  # several frames: upload the polygons once
     polys = soup.as_struct()
     geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(agg_bbox, height, width))
     n = soup.n_polygons

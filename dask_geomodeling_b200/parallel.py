@@ -311,6 +311,12 @@ def zonal_striped(geometries, local, no_data_value, bbox, height, rows, statisti
     stripe_bbox = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
     soup = geometries if isinstance(geometries, utils.PolygonSoup) else utils.PolygonSoup(list(geometries))
     n = soup.n_polygons
+    if _world(group)[1] == 1:  # one stripe = the whole raster: the single-GPU path, select included
+        from .geometry.aggregate import aggregate_polygons
+
+        agg, no_cells = aggregate_polygons(soup, local, no_data_value, stripe_bbox, None, threshold_values,
+                                           statistic, percentile)
+        return agg[0], no_cells
     partial = np.zeros(n, dtype=PARTIAL_DTYPE)
     partial["vmin"], partial["vmax"] = np.finfo(np.float64).max, -np.finfo(np.float64).max
     covered = np.zeros(n, dtype=np.int64)

@@ -508,7 +508,24 @@ class PolygonSoup(object):
         s.n_polygons = self.n_polygons
         s.n_rings = len(self.ring_offsets) - 1
         s.n_vertices = len(self.xy)
+        s.resident = getattr(self, "_resident", None)
         return s
+
+    def to_device(self):
+        """Keep the CSR arrays in HBM (gm_polygons_upload) for as long as this soup lives:
+        later rasterise / zonal calls skip the per-call upload."""
+        import ctypes
+        import weakref
+
+        from . import _native
+
+        if getattr(self, "_resident", None) is None:
+            handle = ctypes.c_void_p()
+            polys = self.as_struct()
+            _native.check(_native.lib().gm_polygons_upload(ctypes.byref(polys), ctypes.byref(handle)))
+            self._resident = handle.value
+            weakref.finalize(self, _native.free_polygons, handle.value)
+        return self
 
 
 # ---------------------------------------------------------------------------

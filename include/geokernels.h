@@ -239,7 +239,15 @@ typedef struct GmPolygons {
   int64_t n_polygons;
   int64_t n_rings;
   int64_t n_vertices;
+  const void* resident;         /* NULL, or a handle from gm_polygons_upload: the
+                                   CSR arrays already live in HBM (no per-call copy) */
 } GmPolygons;
+
+/* keep a polygon soup in HBM between calls (AggregateRaster over many frames /
+ * requests, multi-GPU stripes); the host arrays must still be valid in the
+ * descriptor, the handle only replaces their upload                          */
+int  gm_polygons_upload(const GmPolygons* polys, void** handle);
+int  gm_polygons_free(void* handle);
 
 /* utils.rasterize_geoseries (utils.py:638-756): burn value[p] (dst dtype) for
  * every pixel whose centre is inside polygon p, later polygons on top.      */
