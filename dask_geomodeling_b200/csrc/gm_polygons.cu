@@ -512,7 +512,7 @@ __device__ __forceinline__ void span_batch(ReduceVisitor<T>& vis, int n, const i
 }
 
 template <typename T>
-__global__ void __launch_bounds__(PG_THREADS)
+__global__ void __launch_bounds__(PG_THREADS, 8)
 zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
                     const float* __restrict__ thresholds, GmZonalPartial* __restrict__ partial,
                     long long* __restrict__ cells) {

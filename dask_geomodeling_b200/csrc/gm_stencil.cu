@@ -593,13 +593,15 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
   constexpr int TX = SMF_TW - 2 * L;          // output columns per tile
   constexpr int TH = SMF_TY + 2 * L;          // staged rows
   constexpr int WIN = SMF_RUN + 2 * L;
-  double* tile = reinterpret_cast<double*>(sm_smem);       // TH x SMF_PITCH (source, no data -> fill)
-  double* mid = tile + (size_t)TH * SMF_PITCH;             // SMF_TY x SMF_PITCH (after the y pass)
-  T* stage = reinterpret_cast<T*>(tile);                   // SMF_TY x TX results (reuses the tile)
+  // Both tiles hold the ARRAY dtype (what SciPy stores between the passes); values are
+  // widened to double when a thread fills its register window.  For float32 this halves the
+  // shared memory of a double tile: 40 KB per CTA, four CTAs per SM.
+  T* tile = reinterpret_cast<T*>(sm_smem);                 // TH x SMF_PITCH (source, no data -> fill)
+  T* mid = tile + (size_t)TH * SMF_PITCH;                  // SMF_TY x SMF_PITCH (+ slack) after the y pass
+  T* stage = tile;                                         // SMF_TY x TX results (reuses the tile)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
   const int x0 = blockIdx.x * TX, y0 = blockIdx.y * SMF_TY;  // output coordinates of the tile
-  const double dfill = (double)fill;
   for (int b = blockIdx.z; b < bands; b += gridDim.z) {
     const T* plane = src + (int64_t)b * in_plane;
     __syncthreads();
@@ -622,7 +624,7 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
           const int tx = lane + 32 * j;
           const int gx = x0 + mx - L + tx;
           const bool inside = gy >= 0 && gy < SH && gx >= 0 && gx < SW;
-          const double v = (!inside || (has_nodata && raw[h][j] == nodata)) ? dfill : (double)raw[h][j];
+          const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? fill : raw[h][j];
           if (row < TH) tile[row * SMF_PITCH + tx] = v;
         }
       }
@@ -632,10 +634,10 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
 #pragma unroll 1
     for (int task = tid; task < (SMF_TY / SMF_RUN) * SMF_TW; task += 256) {
       const int tx = task & (SMF_TW - 1), run = task >> 7;
-      const double* c = tile + (run * SMF_RUN) * SMF_PITCH + tx;
+      const T* c = tile + (run * SMF_RUN) * SMF_PITCH + tx;
       double win[WIN];
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) win[i] = c[i * SMF_PITCH];
+      for (int i = 0; i < WIN; ++i) win[i] = (double)c[i * SMF_PITCH];
       const int gx = x0 + mx - L + tx;
       const bool pad = gx < 0 || gx >= SW;   // columns outside the source: constant padding
 #pragma unroll
@@ -644,17 +646,17 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
 #pragma unroll
         for (int k = L; k >= 1; --k) tmp += (win[o + L - k] + win[o + L + k]) * wts.wy[k];
         const T r = from_double<T>(tmp);
-        mid[(run * SMF_RUN + o) * SMF_PITCH + tx] = pad ? dfill : (double)r;
+        mid[(run * SMF_RUN + o) * SMF_PITCH + tx] = pad ? fill : r;
       }
     }
     __syncthreads();
     // x pass: lane = row, each warp takes runs of 8 output columns
 #pragma unroll 1
     for (int run = warp; run * SMF_RUN < TX; run += 8) {
-      const double* c = mid + lane * SMF_PITCH + run * SMF_RUN;
+      const T* c = mid + lane * SMF_PITCH + run * SMF_RUN;
       double win[WIN];
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) win[i] = c[i];  // may run into the next row / the slack: only feeds outputs >= TX
+      for (int i = 0; i < WIN; ++i) win[i] = (double)c[i];  // may run into the next row / the slack: only feeds outputs >= TX
 #pragma unroll
       for (int o = 0; o < SMF_RUN; ++o) {
         double tmp = win[o + L] * wts.wx[0];
@@ -680,9 +682,10 @@ static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata,
                               int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
                               cudaStream_t s) {
   constexpr int TX = SMF_TW - 2 * L;
-  const size_t smem = (((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH + 2 * SMF_MAXL) * sizeof(double);
+  const size_t smem = (((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH + 2 * SMF_MAXL) * sizeof(T);
   auto kernel = smooth_fast_kernel<T, L>;
-  GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024)
+    GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid3(W, H, bands, TX, SMF_TY), 256, smem, s>>>((const T*)in.dev, target, nd, has_nodata, fill,
                                                            bands, SH, SW, H, W, my, mx, wts);
   GM_LAUNCH_CHECK();

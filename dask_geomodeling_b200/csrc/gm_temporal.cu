@@ -119,6 +119,71 @@ temporal_aggregate_kernel(const S* __restrict__ src, D* __restrict__ dst, S noda
   }
 }
 
+// Median / percentile: every thread sorts the valid samples of its pixel in its own
+// shared-memory column (column-major, so the lanes of a warp touch consecutive words: no
+// bank conflicts) with a bitonic network.  The network is data independent -- all threads run
+// the same compare-exchange sequence, no divergence, no global scratch -- and costs
+// n log^2 n / 4 exchanges instead of the n^2 / 4 moves of the insertion sort of the generic
+// kernel.  Invalid samples are padded with +inf behind the valid ones.
+template <typename S, typename W, typename D>
+__global__ void temporal_sort_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                                     int stat, double q, const int* __restrict__ bin_offsets,
+                                     const int* __restrict__ frame_index, int n_bins, int64_t plane) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  W* col = reinterpret_cast<W*>(sort_smem) + threadIdx.x;
+  const int BD = blockDim.x;
+  const int64_t pix = blockIdx.x * (int64_t)BD + threadIdx.x;
+  if (pix >= plane) return;
+  const D fill = DMax<D>::value();
+  const W inf = (W)INFINITY;
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
+    int n = 0;
+    for (int f = f0; f < f1; ++f) {
+      const S v = __ldcs(src + (int64_t)frame_index[f] * plane + pix);
+      const W w = (W)v;
+      if (!(has_nodata && v == nodata) && w == w) { col[n * BD] = w; ++n; }
+    }
+    int p2 = 1;
+    while (p2 < f1 - f0) p2 <<= 1;
+    for (int i = n; i < p2; ++i) col[i * BD] = inf;
+    for (int k = 2; k <= p2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1)
+        for (int idx = 0; idx < (p2 >> 1); ++idx) {
+          const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1)), l = i | j;
+          const W a = col[i * BD], b = col[l * BD];
+          const bool up = (i & k) == 0;
+          const W lo = a < b ? a : b, hi = a < b ? b : a;
+          col[i * BD] = up ? lo : hi;
+          col[l * BD] = up ? hi : lo;
+        }
+    D out = fill;
+    if (n > 0) {
+      W result;
+      if (stat == GM_STAT_MEDIAN) {
+        const W a = col[((n - 1) / 2) * BD], b = col[(n / 2) * BD];
+        result = (n & 1) ? a : (a + b) / (W)2;
+      } else {
+        // np.nanpercentile(method="linear") in the working dtype W (see the generic kernel)
+        const W qw = (W)q / (W)100;
+        const W virt = (W)(n - 1) * qw;
+        int lo = (int)floor((double)virt);
+        if (lo < 0) lo = 0;
+        if (lo > n - 1) lo = n - 1;
+        const int hi = lo + 1 < n ? lo + 1 : n - 1;
+        const W a = col[lo * BD], b = col[hi * BD];
+        const W t = virt - (W)lo;
+        const W diff = b - a;
+        result = a + diff * t;
+        if (t >= (W)0.5) result = b - diff * ((W)1 - t);
+      }
+      const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+      if (finite) out = cast_out<W, D>(result);
+    }
+    dst[(int64_t)g * plane + pix] = out;
+  }
+}
+
 // Streaming fast path for sum / count / min / max / mean: the statistic is a template
 // argument (only the accumulators it needs exist), a thread owns VEC = 16 / sizeof(S)
 // consecutive pixels so every frame is read with 128-bit loads, and UNROLL frames are in
@@ -221,6 +286,8 @@ struct TemporalArgs {
   const void* nodata; int has_nodata; int stat; double q;
   const int* bins; const int* frames; const int* out_frame; int n_bins; int64_t plane;
   void* scratch;
+  int sort_slots = 0;     // power of two >= longest bin (shared-memory sort path)
+  int sort_threads = 0;   // threads per block on that path, 0 = use the global-scratch kernel
 };
 
 template <typename S, typename W, typename D>
@@ -246,6 +313,17 @@ static int launch_aggregate(const Staged& in, Staged& out, const TemporalArgs& a
       default: GM_STREAM(GM_STAT_MEAN); break;
     }
 #undef GM_STREAM
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
+  if ((a.stat == GM_STAT_MEDIAN || a.stat == GM_STAT_PERCENTILE) && a.sort_threads > 0) {
+    auto kernel = temporal_sort_kernel<S, W, D>;
+    const size_t smem = (size_t)a.sort_slots * a.sort_threads * sizeof(W);
+    if (smem > 48 * 1024)
+      GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned nb = (unsigned)((a.plane + a.sort_threads - 1) / a.sort_threads);
+    kernel<<<nb, a.sort_threads, smem, s>>>((const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.q,
+                                            a.bins, a.frames, a.n_bins, a.plane);
     GM_LAUNCH_CHECK();
     return 0;
   }
@@ -341,7 +419,16 @@ static int run_temporal(const GmArray* src, GmArray* dst, const void* nodata, in
   if (!rc) rc = upload(&dbins, bin_offsets, sizeof(int32_t) * (n_bins + 1), s);
   if (!rc) rc = upload(&dframes, frame_index, sizeof(int32_t) * (n_frames > 0 ? n_frames : 1), s);
   if (!rc && CUMULATIVE) rc = upload(&dout, out_frame, sizeof(int32_t) * (n_frames > 0 ? n_frames : 1), s);
-  if (!rc && needs_sort) {
+  if (needs_sort) {
+    // shared-memory sort: one column of `slots` working-dtype values per thread
+    const size_t w = work_is_double(dst->dtype) ? 8 : 4;
+    int slots = 1;
+    while (slots < longest) slots <<= 1;
+    int threads = (int)((160 * 1024) / ((size_t)slots * w)) / 32 * 32;
+    if (threads > 128) threads = 128;
+    if (threads >= 32) { a.sort_slots = slots; a.sort_threads = threads; }
+  }
+  if (!rc && needs_sort && a.sort_threads == 0) {
     const size_t w = work_is_double(dst->dtype) ? 8 : 4;
     cudaError_t e = cudaMallocAsync(&a.scratch, w * (size_t)longest * (size_t)a.plane, s);
     if (e != cudaSuccess) rc = fail(std::string("temporal scratch: ") + cudaGetErrorString(e));
