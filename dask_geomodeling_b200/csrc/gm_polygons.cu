@@ -138,7 +138,8 @@ __device__ __forceinline__ bool in_pairs(int x, const int* buf, int count) {
 // default: one span at a time (visitors that gain from batching overload this)
 template <class Visitor>
 __device__ __forceinline__ void span_batch(Visitor& vis, int n, const int* ys, const int* x0, const int* x1) {
-  for (int i = 0; i < n; ++i)
+#pragma unroll
+  for (int i = 0; i < PG_BATCH; ++i)   // entries >= n are empty spans
     if (x0[i] <= x1[i]) vis.span(ys[i], x0[i], x1[i]);
 }
 template <typename T> struct ReduceVisitor;
@@ -314,16 +315,20 @@ __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* b
       if (c == 2) {
         // the usual case, one span per row: hand up to PG_BATCH consecutive such rows to the
         // visitor together so that it can keep the raster reads of all of them in flight
+        // (fixed-index, fully unrolled: the batch stays in registers)
         int ys[PG_BATCH], xs0[PG_BATCH], xs1[PG_BATCH];
         int nb = 0;
-        while (nb < PG_BATCH && r + nb < n_rows) {
-          const int rr = r + nb;
-          if (((complex_mask >> rr) & 1u) || __shfl_sync(0xffffffffu, cnt, rr) != 2) break;
+        bool open = true;
+#pragma unroll
+        for (int e = 0; e < PG_BATCH; ++e) {
+          const int rr = (r + e) & 31;
+          const bool single = __shfl_sync(0xffffffffu, cnt, rr) == 2;
+          open = open && r + e < n_rows && !((complex_mask >> rr) & 1u) && single;
           const int xa = s_cross[warp][0][rr], xb = s_cross[warp][1][rr];
           int x0 = 1, x1 = 0;  // empty unless the span touches the raster
-          if (xa <= maxx && xb > 0) { x0 = xa < 0 ? 0 : xa; x1 = xb - 1 > maxx ? maxx : xb - 1; }
-          ys[nb] = base + rr; xs0[nb] = x0; xs1[nb] = x1;
-          ++nb;
+          if (open && xa <= maxx && xb > 0) { x0 = xa < 0 ? 0 : xa; x1 = xb - 1 > maxx ? maxx : xb - 1; }
+          ys[e] = open ? base + r + e : yy; xs0[e] = x0; xs1[e] = x1;
+          nb += open ? 1 : 0;
         }
         span_batch(vis, nb, ys, xs0, xs1);
         r += nb - 1;
@@ -450,16 +455,29 @@ struct ActiveTest {
   }
 };
 
+// min / max are tracked in the raster dtype (one FMNMX / IMNMX per value; NaN never wins,
+// as with the `d < vmin` form) and the count in 32 bits per lane; only the sum needs the
+// widening to double.  Everything is widened when the lanes are combined.
+template <typename T> __device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
+template <typename T> __device__ __forceinline__ T tmax(T a, T b) { return a > b ? a : b; }
+template <> __device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
 template <typename T>
 struct ReduceVisitor {
   const T* raster; int width; ActiveTest<T> active;
-  long long count, cells; double sum, vmin, vmax;
+  int count; long long cells; double sum; T vmin, vmax;
+  __device__ __forceinline__ void reset() {
+    count = 0; cells = 0; sum = 0.0;
+    vmin = std::numeric_limits<T>::max(); vmax = std::numeric_limits<T>::lowest();
+  }
   __device__ __forceinline__ void take(T v) {
     if (active(v)) {
-      const double d = (double)v;
-      ++count; sum += d;
-      vmin = d < vmin ? d : vmin;
-      vmax = d > vmax ? d : vmax;
+      ++count; sum += (double)v;
+      vmin = tmin<T>(vmin, v);
+      vmax = tmax<T>(vmax, v);
     }
   }
   __device__ __forceinline__ void span(int y, int x0, int x1) {
@@ -482,30 +500,37 @@ struct ReduceVisitor {
   }
 };
 
-// PG_BATCH rows x 4 requests of 128 bytes are issued before the first value is consumed
+// PG_BATCH rows x 4 requests of 128 bytes are issued before the first value is consumed.
+// Slots beyond the span (and the empty padding rows of the batch) are given the no-data
+// value, so `take` drops them without any per-slot bookkeeping.
 template <typename T>
 __device__ __forceinline__ void span_batch(ReduceVisitor<T>& vis, int n, const int* ys, const int* x0, const int* x1) {
   const int lane = threadIdx.x & 31;
+  if (!vis.active.has_nodata) {  // no sentinel to mark unused slots with: one span at a time
+#pragma unroll
+    for (int b = 0; b < PG_BATCH; ++b)
+      if (x0[b] <= x1[b]) vis.span(ys[b], x0[b], x1[b]);
+    return;
+  }
+  const T skip = vis.active.nodata;
   T v[PG_BATCH][4];
-  bool ok[PG_BATCH][4];
 #pragma unroll
   for (int b = 0; b < PG_BATCH; ++b) {
-    const T* row = vis.raster + (int64_t)(b < n ? ys[b] : 0) * vis.width;
+    const T* row = vis.raster + (int64_t)ys[b] * vis.width + lane;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int x = (b < n ? x0[b] : 1) + lane + 32 * k;
-      ok[b][k] = b < n && x <= x1[b];
-      v[b][k] = ok[b][k] ? __ldg(row + x) : T(0);
+      const int x = x0[b] + 32 * k;
+      v[b][k] = (x + lane <= x1[b]) ? __ldg(row + x) : skip;
     }
   }
 #pragma unroll
   for (int b = 0; b < PG_BATCH; ++b) {
-    if (b < n && lane == 0 && x0[b] <= x1[b]) vis.cells += x1[b] - x0[b] + 1;
+    if (lane == 0 && x0[b] <= x1[b]) vis.cells += x1[b] - x0[b] + 1;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (ok[b][k]) vis.take(v[b][k]);
+    for (int k = 0; k < 4; ++k) vis.take(v[b][k]);
   }
-  for (int b = 0; b < n; ++b) {  // rows longer than 128 cells: the rest
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b) {  // rows longer than 128 cells: the rest
     const T* row = vis.raster + (int64_t)ys[b] * vis.width;
     for (int x = x0[b] + 128 + lane; x <= x1[b]; x += 32) vis.take(__ldg(row + x));
   }
@@ -528,16 +553,19 @@ zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
     vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
     vis.active.has_threshold = thresholds != nullptr;
     vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
-    vis.count = 0; vis.cells = 0; vis.sum = 0.0; vis.vmin = DBL_MAX; vis.vmax = -DBL_MAX;
+    vis.reset();
     scan_polygon(P, p, buf, hbuf, vis);
+    long long count = vis.count;
+    // a lane that saw nothing must not contribute the dtype extremes
+    double vmin = vis.count > 0 ? (double)vis.vmin : DBL_MAX, vmax = vis.count > 0 ? (double)vis.vmax : -DBL_MAX;
     for (int o = 16; o > 0; o >>= 1) {
-      vis.count += __shfl_xor_sync(0xffffffffu, vis.count, o);
+      count += __shfl_xor_sync(0xffffffffu, count, o);
       vis.cells += __shfl_xor_sync(0xffffffffu, vis.cells, o);
       vis.sum += __shfl_xor_sync(0xffffffffu, vis.sum, o);
-      vis.vmin = fmin(vis.vmin, __shfl_xor_sync(0xffffffffu, vis.vmin, o));
-      vis.vmax = fmax(vis.vmax, __shfl_xor_sync(0xffffffffu, vis.vmax, o));
+      vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
-    if (lane == 0) { s_count[warp] = vis.count; s_cells[warp] = vis.cells; s_sum[warp] = vis.sum; s_min[warp] = vis.vmin; s_max[warp] = vis.vmax; }
+    if (lane == 0) { s_count[warp] = count; s_cells[warp] = vis.cells; s_sum[warp] = vis.sum; s_min[warp] = vmin; s_max[warp] = vmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
       GmZonalPartial r{0, 0.0, DBL_MAX, -DBL_MAX};
@@ -651,7 +679,8 @@ __device__ __forceinline__ void span_batch(GatherVisitor<T>& vis, int n, const i
         const long long pos = base + mine[b][k];
         if (pos < vis.capacity) vis.keys[pos] = KeyOf<T>::key(v[b][k]);
       }
-  for (int b = 0; b < n; ++b)  // rows longer than 128 cells: the rest
+#pragma unroll
+  for (int b = 0; b < PG_BATCH; ++b)  // rows longer than 128 cells: the rest
     if (x0[b] + 128 <= x1[b]) vis.span(ys[b], x0[b] + 128, x1[b]);
 }
 
