@@ -152,6 +152,87 @@ __device__ __forceinline__ void span_batch(ReduceVisitor<T>& vis, int n, const i
 // Visitor interface (all calls are warp-uniform):
 //   span(y, x0, x1)                       regular even-odd span, inclusive, clipped
 //   hspan(y, x0, x1, buf, count)          bottom horizontal edge on the scanline
+//
+// Generic scanline: the whole warp works on ONE row of the feature made of rings r0..r1
+// (any number of vertices / crossings, at most `cap` of which fit `buf`).
+template <class Visitor>
+__device__ __forceinline__ void generic_scanline(const PolyDev& P, int64_t r0, int64_t r1, int y, int cap,
+                                                 int* buf, int* hbuf, Visitor& vis) {
+  const int lane = threadIdx.x & 31;
+  const int maxx = P.width - 1;
+  const double dy = y + 0.5;
+  int count = 0, hcount = 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t a = P.ring_offsets[r], b = P.ring_offsets[r + 1];
+    for (int64_t base = a; base < b; base += 32) {
+      const int64_t i = base + lane;
+      bool cross = false, hs = false;
+      int xi = 0, hx1 = 0, hx2 = 0;
+      if (i < b) {
+        const int64_t ind1 = (i == a) ? b - 1 : i - 1;
+        double dy1 = P.py[ind1], dy2 = P.py[i];
+        if (!((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy))) {
+          double dx1, dx2;
+          if (dy1 < dy2) {
+            dx1 = P.px[ind1]; dx2 = P.px[i];
+            cross = true;
+          } else if (dy1 > dy2) {
+            const double t = dy1; dy1 = dy2; dy2 = t;
+            dx2 = P.px[ind1]; dx1 = P.px[i];
+            cross = true;
+          } else {
+            const double xa = P.px[ind1], xb = P.px[i];
+            if (xa > xb) {  // bottom horizontal edge: filled on its own
+              hx1 = clamp_to_int(floor(xb + 0.5));
+              hx2 = clamp_to_int(floor(xa + 0.5));
+              hs = !(hx1 > maxx || hx2 <= 0);
+            }
+          }
+          if (cross) {
+            cross = (dy < dy2 && dy >= dy1);
+            if (cross) {
+              const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+              xi = clamp_to_int(floor(intersect + 0.5));
+            }
+          }
+        }
+      }
+      const unsigned cm = __ballot_sync(0xffffffffu, cross);
+      if (cross) {
+        const int pos = count + __popc(cm & ((1u << lane) - 1u));
+        if (pos < cap) buf[pos] = xi;
+      }
+      count += __popc(cm);
+      const unsigned hm = __ballot_sync(0xffffffffu, hs);
+      if (hs) {
+        const int pos = hcount + __popc(hm & ((1u << lane) - 1u));
+        if (pos < PG_MAX_HSPANS) { hbuf[2 * pos] = hx1; hbuf[2 * pos + 1] = hx2; }
+      }
+      hcount += __popc(hm);
+    }
+  }
+  if (count > cap || hcount > PG_MAX_HSPANS) {
+    if (lane == 0) atomicExch(P.error, 1);
+    count = count > cap ? cap : count;
+    hcount = hcount > PG_MAX_HSPANS ? PG_MAX_HSPANS : hcount;
+  }
+  warp_sort(buf, count, lane);
+  for (int i = 0; i + 1 < count; i += 2) {
+    const int xa = buf[i], xb = buf[i + 1];
+    if (xa <= maxx && xb > 0) {
+      const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
+      if (x0 <= x1) vis.span(y, x0, x1);
+    }
+  }
+  __syncwarp();
+  for (int h = 0; h < hcount; ++h) {
+    const int x0 = hbuf[2 * h] < 0 ? 0 : hbuf[2 * h];
+    const int x1 = hbuf[2 * h + 1] - 1 > maxx ? maxx : hbuf[2 * h + 1] - 1;
+    if (x0 <= x1) vis.hspan(y, x0, x1, buf, count);
+  }
+  __syncwarp();
+}
+
 template <class Visitor>
 __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* buf, int* hbuf,
                                              Visitor& vis) {
@@ -169,80 +250,7 @@ __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* b
     }
     return;
   }
-  // generic scanline: the whole warp works on ONE row (any number of vertices / crossings)
-  auto generic_row = [&](int y) {
-    const double dy = y + 0.5;
-    int count = 0, hcount = 0;
-    for (int64_t r = r0; r < r1; ++r) {
-      const int64_t a = P.ring_offsets[r], b = P.ring_offsets[r + 1];
-      for (int64_t base = a; base < b; base += 32) {
-        const int64_t i = base + lane;
-        bool cross = false, hs = false;
-        int xi = 0, hx1 = 0, hx2 = 0;
-        if (i < b) {
-          const int64_t ind1 = (i == a) ? b - 1 : i - 1;
-          double dy1 = P.py[ind1], dy2 = P.py[i];
-          if (!((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy))) {
-            double dx1, dx2;
-            if (dy1 < dy2) {
-              dx1 = P.px[ind1]; dx2 = P.px[i];
-              cross = true;
-            } else if (dy1 > dy2) {
-              const double t = dy1; dy1 = dy2; dy2 = t;
-              dx2 = P.px[ind1]; dx1 = P.px[i];
-              cross = true;
-            } else {
-              const double xa = P.px[ind1], xb = P.px[i];
-              if (xa > xb) {  // bottom horizontal edge: filled on its own
-                hx1 = clamp_to_int(floor(xb + 0.5));
-                hx2 = clamp_to_int(floor(xa + 0.5));
-                hs = !(hx1 > maxx || hx2 <= 0);
-              }
-            }
-            if (cross) {
-              cross = (dy < dy2 && dy >= dy1);
-              if (cross) {
-                const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
-                xi = clamp_to_int(floor(intersect + 0.5));
-              }
-            }
-          }
-        }
-        const unsigned cm = __ballot_sync(0xffffffffu, cross);
-        if (cross) {
-          const int pos = count + __popc(cm & ((1u << lane) - 1u));
-          if (pos < P.cap) buf[pos] = xi;
-        }
-        count += __popc(cm);
-        const unsigned hm = __ballot_sync(0xffffffffu, hs);
-        if (hs) {
-          const int pos = hcount + __popc(hm & ((1u << lane) - 1u));
-          if (pos < PG_MAX_HSPANS) { hbuf[2 * pos] = hx1; hbuf[2 * pos + 1] = hx2; }
-        }
-        hcount += __popc(hm);
-      }
-    }
-    if (count > P.cap || hcount > PG_MAX_HSPANS) {
-      if (lane == 0) atomicExch(P.error, 1);
-      count = count > P.cap ? P.cap : count;
-      hcount = hcount > PG_MAX_HSPANS ? PG_MAX_HSPANS : hcount;
-    }
-    warp_sort(buf, count, lane);
-    for (int i = 0; i + 1 < count; i += 2) {
-      const int xa = buf[i], xb = buf[i + 1];
-      if (xa <= maxx && xb > 0) {
-        const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
-        if (x0 <= x1) vis.span(y, x0, x1);
-      }
-    }
-    __syncwarp();
-    for (int h = 0; h < hcount; ++h) {
-      const int x0 = hbuf[2 * h] < 0 ? 0 : hbuf[2 * h];
-      const int x1 = hbuf[2 * h + 1] - 1 > maxx ? maxx : hbuf[2 * h + 1] - 1;
-      if (x0 <= x1) vis.hspan(y, x0, x1, buf, count);
-    }
-    __syncwarp();
-    };
+  auto generic_row = [&](int y) { generic_scanline(P, r0, r1, y, P.cap, buf, hbuf, vis); };
 
   const int nv = (int)(v1 - v0);
   if (nv > PG_FAST_MAXV) {
@@ -540,14 +548,17 @@ template <typename T>
 __global__ void __launch_bounds__(PG_THREADS, 8)
 zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
                     const float* __restrict__ thresholds, GmZonalPartial* __restrict__ partial,
-                    long long* __restrict__ cells) {
+                    long long* __restrict__ cells, const int* __restrict__ work) {
+  // the polygons zonal_reduce_warp_kernel deferred: work[0] of them, listed from work[2]
   extern __shared__ int pg_smem[];
   __shared__ long long s_count[PG_WARPS], s_cells[PG_WARPS];
   __shared__ double s_sum[PG_WARPS], s_min[PG_WARPS], s_max[PG_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* buf = pg_smem + warp * P.cap;
   int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
-  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+  const int n_listed = work[0];
+  for (int item = blockIdx.x; item < n_listed; item += gridDim.x) {
+    const int64_t p = work[2 + item];
     ReduceVisitor<T> vis;
     vis.raster = raster; vis.width = P.width;
     vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
@@ -578,6 +589,258 @@ zonal_reduce_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
       cells[p] = c;
     }
     __syncthreads();
+  }
+}
+
+// ---- zonal reduce, one WARP per polygon ----------------------------------------------------
+// The usual polygon (<= ZW_MAXV vertices, <= ZW_BIG_ROWS rows, bounding box <= ZW_BIG_CELLS
+// cells) is taken by a single warp: no block barrier, no idle warps while the last rows of a
+// polygon finish, and warps fetch polygons from one atomic counter, so that neighbouring
+// polygons are in flight together.  Rows are read with 16-byte loads aligned to the raster
+// (VEC = 16 / itemsize cells per lane, one 512-byte request per row and warp), ZW_ROWS rows
+// issued before the first value is consumed; cells of a quad outside the span are masked by
+// one unsigned compare.  Everything else (many vertices, many rows, wide boxes) is appended to
+// a list that zonal_reduce_kernel (one block per polygon) works off afterwards.
+constexpr int ZW_WARPS = 8;
+constexpr int ZW_MAXV = PG_FAST_MAXV;
+constexpr int ZW_MAXC = PG_FAST_MAXC;
+constexpr int ZW_ROWS = 4;
+constexpr int ZW_BIG_ROWS = 256;
+constexpr long long ZW_BIG_CELLS = 1 << 17;
+constexpr int ZW_SUM = 1, ZW_MINMAX = 2;
+
+template <typename T, int NEED>
+struct WarpReduce {
+  static constexpr int VEC = 16 / (int)sizeof(T);
+  const T* raster; int width; ActiveTest<T> active;
+  int count; long long cells; double sum; T vmin, vmax;
+  __device__ __forceinline__ void reset() {
+    count = 0; cells = 0; sum = 0.0;
+    vmin = std::numeric_limits<T>::max(); vmax = std::numeric_limits<T>::lowest();
+  }
+  __device__ __forceinline__ void take(T v) {
+    if (active(v)) {
+      ++count;
+      if (NEED & ZW_SUM) sum += (double)v;
+      if (NEED & ZW_MINMAX) { vmin = tmin<T>(vmin, v); vmax = tmax<T>(vmax, v); }
+    }
+  }
+  // scalar walk of one span (rows that are not plain single spans)
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    const T* row = raster + (int64_t)y * width;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) cells += x1 - x0 + 1;
+    for (int x = x0 + lane; x <= x1; x += 32) take(__ldg(row + x));
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
+    const T* row = raster + (int64_t)y * width;
+    int extra = 0;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32)
+      if (!in_pairs(x, buf, n)) { take(__ldg(row + x)); ++extra; }
+    cells += extra;
+  }
+  // ZW_ROWS consecutive rows y0.., row b spans [x0[b], x1[b]] (inclusive, clipped, may be
+  // empty); `mis` = element misalignment of the raster base w.r.t. 16 bytes
+  __device__ __forceinline__ void rows(int y0, const int* x0, const int* x1, int mis) {
+    const int lane = threadIdx.x & 31;
+    int xa[ZW_ROWS], longest = 0;
+#pragma unroll
+    for (int b = 0; b < ZW_ROWS; ++b) {
+      const int64_t off = (int64_t)(y0 + b) * width + mis;       // element offset from the 16-byte grid
+      xa[b] = x0[b] - (int)((off + x0[b]) & (VEC - 1));          // quad-aligned start of the span
+      if (x0[b] <= x1[b]) longest = max(longest, x1[b] - xa[b] + 1);
+    }
+    for (int k = 0; k < longest; k += 32 * VEC) {
+      uint4 q[ZW_ROWS];
+      int x[ZW_ROWS];
+#pragma unroll
+      for (int b = 0; b < ZW_ROWS; ++b) {
+        x[b] = xa[b] + k + VEC * lane;
+        q[b] = make_uint4(0u, 0u, 0u, 0u);
+        if (x0[b] <= x1[b] && x[b] <= x1[b])
+          q[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x[b]));
+      }
+#pragma unroll
+      for (int b = 0; b < ZW_ROWS; ++b) {
+        const unsigned len = (unsigned)(x1[b] - x0[b]);          // empty rows: x0 = 1, x1 = 0 -> handled below
+        const int rel = x[b] - x0[b];
+        T e[VEC];
+        memcpy(e, &q[b], 16);
+        if (x0[b] <= x1[b]) {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if ((unsigned)(rel + j) <= len) take(e[j]);
+        }
+      }
+    }
+  }
+};
+
+template <typename T, int NEED>
+__global__ void __launch_bounds__(32 * ZW_WARPS, 4)
+zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                         const float* __restrict__ thresholds, int mis, int edge_scalar,
+                         GmZonalPartial* __restrict__ partial, long long* __restrict__ cells,
+                         int* __restrict__ work) {
+  // work[0]: length of the deferred list, work[1]: polygon counter, work[2...]: the list
+  __shared__ double s_px[ZW_WARPS][ZW_MAXV], s_py[ZW_WARPS][ZW_MAXV];
+  __shared__ int s_prev[ZW_WARPS][ZW_MAXV];
+  __shared__ __align__(16) int s_cross[ZW_WARPS][ZW_MAXC][32];
+  __shared__ int s_buf[ZW_WARPS][ZW_MAXV + 2 * PG_MAX_HSPANS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int maxx = P.width - 1;
+  double* px = s_px[warp];
+  double* py = s_py[warp];
+  int* prev = s_prev[warp];
+  int* buf = s_buf[warp];
+  int* hbuf = buf + ZW_MAXV;
+  WarpReduce<T, NEED> vis;
+  vis.raster = raster; vis.width = P.width;
+  vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
+  vis.active.has_threshold = thresholds != nullptr;
+  for (;;) {
+    int64_t p = 0;
+    if (lane == 0) p = atomicAdd(work + 1, 1);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= P.n_polygons) break;
+    const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
+    const int miny = P.miny[p], maxy = P.maxy[p];
+    int64_t v0 = 0, v1 = 0;
+    if (r1 > r0) { v0 = P.ring_offsets[r0]; v1 = P.ring_offsets[r1]; }
+    const int nv = (int)min((int64_t)(ZW_MAXV + 1), v1 - v0);
+    vis.active.threshold = thresholds ? thresholds[p] : 0.0f;
+    vis.reset();
+    bool defer = nv > ZW_MAXV || maxy - miny >= ZW_BIG_ROWS;
+    if (!defer && nv > 1 && miny <= maxy) {
+      // vertices (and each vertex' predecessor on its ring) to this warp's shared memory
+      double xmin = DBL_MAX, xmax = -DBL_MAX;
+      __syncwarp();
+      for (int i = lane; i < nv; i += 32) {
+        const double x = P.px[v0 + i];
+        px[i] = x; py[i] = P.py[v0 + i];
+        xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+        int pr = i - 1;
+        for (int64_t r = r0; r < r1; ++r)
+          if ((int64_t)i + v0 == P.ring_offsets[r]) pr = (int)(P.ring_offsets[r + 1] - v0) - 1;
+        prev[i] = pr;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+        xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+      }
+      const double wide = fmin(xmax, (double)P.width) - fmax(xmin, 0.0);
+      defer = wide * (double)(maxy - miny + 1) > (double)ZW_BIG_CELLS;
+      __syncwarp();
+    }
+    if (defer) {
+      if (lane == 0) work[2 + atomicAdd(work, 1)] = (int)p;
+      continue;
+    }
+    if (nv == 1) {  // point feature (GDALdllImagePoint): the cell that contains it
+      if (miny <= maxy) {
+        const int x = clamp_to_int(floor(P.px[v0]));
+        if (x >= 0 && x <= maxx) vis.span(miny, x, x);
+      }
+    } else if (nv > 1) {
+      for (int base = miny; base <= maxy; base += 32) {
+        const int y = base + lane;
+        const double dy = y + 0.5;
+        int cnt = 0;
+        bool complex_row = false;
+        if (y <= maxy) {
+          for (int i = 0; i < nv; ++i) {
+            const int ind1 = prev[i];
+            double dy1 = py[ind1], dy2 = py[i];
+            if ((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy)) continue;
+            double dx1, dx2;
+            if (dy1 < dy2) {
+              dx1 = px[ind1]; dx2 = px[i];
+            } else if (dy1 > dy2) {
+              const double t = dy1; dy1 = dy2; dy2 = t;
+              dx2 = px[ind1]; dx1 = px[i];
+            } else {
+              if (px[ind1] > px[i]) complex_row = true;  // bottom horizontal edge on the scanline
+              continue;
+            }
+            if (dy < dy2 && dy >= dy1) {
+              const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+              if (cnt < ZW_MAXC) s_cross[warp][cnt][lane] = clamp_to_int(floor(intersect + 0.5));
+              ++cnt;
+            }
+          }
+          if (cnt > ZW_MAXC) complex_row = true;
+          if (!complex_row)
+            for (int a = 1; a < cnt; ++a) {  // insertion sort of this lane's column
+              const int v = s_cross[warp][a][lane];
+              int j = a - 1;
+              while (j >= 0 && s_cross[warp][j][lane] > v) { s_cross[warp][j + 1][lane] = s_cross[warp][j][lane]; --j; }
+              s_cross[warp][j + 1][lane] = v;
+            }
+        }
+        // first span of the row, clipped and inclusive, for the batched 16-byte walk; rows
+        // with more spans, or on the raster's first / last line when a quad could reach
+        // outside the array, are walked span by span with scalar loads afterwards
+        const bool edge = edge_scalar && (y == 0 || y == P.height - 1);
+        const bool scalar_row = !complex_row && cnt >= 2 && (cnt > 2 || edge);
+        int fx0 = 1, fx1 = 0;
+        if (!complex_row && !scalar_row && cnt == 2) {
+          const int xa = s_cross[warp][0][lane], xb = s_cross[warp][1][lane];
+          if (xa <= maxx && xb > 0) { fx0 = xa < 0 ? 0 : xa; fx1 = xb - 1 > maxx ? maxx : xb - 1; }
+          if (fx0 <= fx1) vis.cells += fx1 - fx0 + 1; else { fx0 = 1; fx1 = 0; }
+        }
+        __syncwarp();
+        const unsigned complex_mask = __ballot_sync(0xffffffffu, complex_row);
+        unsigned scalar_mask = __ballot_sync(0xffffffffu, scalar_row);
+        const unsigned single_mask = __ballot_sync(0xffffffffu, fx0 <= fx1);
+        // the scalar rows first: they still need their raw crossings
+        while (scalar_mask) {
+          const int r = __ffs(scalar_mask) - 1;
+          scalar_mask &= scalar_mask - 1;
+          const int c = __shfl_sync(0xffffffffu, cnt, r);
+          for (int i = 0; i + 1 < c; i += 2) {
+            const int xa = s_cross[warp][i][r], xb = s_cross[warp][i + 1][r];
+            if (xa <= maxx && xb > 0) {
+              const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
+              if (x0 <= x1) vis.span(base + r, x0, x1);
+            }
+          }
+        }
+        __syncwarp();
+        s_cross[warp][0][lane] = fx0;
+        s_cross[warp][1][lane] = fx1;
+        __syncwarp();
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += ZW_ROWS) {
+          if (((single_mask >> rb) & ((1u << ZW_ROWS) - 1u)) == 0) continue;
+          int x0[ZW_ROWS], x1[ZW_ROWS];
+#pragma unroll
+          for (int b = 0; b < ZW_ROWS; ++b) { x0[b] = s_cross[warp][0][rb + b]; x1[b] = s_cross[warp][1][rb + b]; }
+          vis.rows(base + rb, x0, x1, mis);
+        }
+        unsigned cm = complex_mask;
+        while (cm) {
+          const int r = __ffs(cm) - 1;
+          cm &= cm - 1;
+          generic_scanline(P, r0, r1, base + r, ZW_MAXV, buf, hbuf, vis);
+        }
+        __syncwarp();
+      }
+    }
+    long long count = vis.count;
+    double vmin = vis.count > 0 ? (double)vis.vmin : DBL_MAX, vmax = vis.count > 0 ? (double)vis.vmax : -DBL_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+      count += __shfl_xor_sync(0xffffffffu, count, o);
+      vis.cells += __shfl_xor_sync(0xffffffffu, vis.cells, o);
+      if (NEED & ZW_SUM) vis.sum += __shfl_xor_sync(0xffffffffu, vis.sum, o);
+      if (NEED & ZW_MINMAX) {
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      }
+    }
+    if (lane == 0) {
+      partial[p] = GmZonalPartial{count, vis.sum, vmin, vmax};
+      cells[p] = vis.cells;
+    }
   }
 }
 
@@ -1113,10 +1376,10 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   T nd = T(0);
   if (has_nodata) memcpy(&nd, nodata, sizeof(T));
   void *darea = nullptr, *dthr = nullptr, *dpartial = nullptr, *dout = nullptr;
-  void *doff = nullptr, *dtotal = nullptr, *dbig = nullptr;
+  void *doff = nullptr, *dtotal = nullptr, *dbig = nullptr, *scratch_work = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
-    void* all[] = {darea, dthr, dpartial, dout, doff, dtotal, dbig};
+    void* all[] = {darea, dthr, dpartial, dout, doff, dtotal, dbig, scratch_work};
     for (void* p : all) if (p) cudaFreeAsync(p, s);
   };
 #define GM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
@@ -1142,9 +1405,32 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   if (!order_stat || partial) {
     // one pass: partials and the covered-cell counts together
     GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
+    // warps take the usual polygons one each; the rest goes through the block-per-polygon kernel
+    void* dwork = nullptr;
+    GM_TRY(cudaMallocAsync(&dwork, sizeof(int) * (size_t)(np_ + 2), s));
+    scratch_work = dwork;
+    GM_TRY(cudaMemsetAsync(dwork, 0, 2 * sizeof(int), s));
+    const int vec = 16 / (int)sizeof(T);
+    const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (uintptr_t)(vec - 1));
+    const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
+                            (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
+    const int need = partial ? (ZW_SUM | ZW_MINMAX)
+                             : (stat == GM_STAT_MIN || stat == GM_STAT_MAX) ? ZW_MINMAX : ZW_SUM;
+    int64_t wblocks = (np_ + ZW_WARPS - 1) / ZW_WARPS;
+    if (wblocks > (int64_t)sm_count() * 4) wblocks = (int64_t)sm_count() * 4;
+#define GM_ZW(NEED)                                                                              \
+    zonal_reduce_warp_kernel<T, NEED><<<(unsigned)wblocks, 32 * ZW_WARPS, 0, s>>>(                \
+        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, mis, edge_scalar,        \
+        (GmZonalPartial*)dpartial, (long long*)darea, (int*)dwork)
+    if (need == ZW_SUM) GM_ZW(ZW_SUM);
+    else if (need == ZW_MINMAX) GM_ZW(ZW_MINMAX);
+    else GM_ZW(ZW_SUM | ZW_MINMAX);
+#undef GM_ZW
+    GM_TRY(cudaGetLastError());
+    count_launch();
     zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
         u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial,
-        (long long*)darea);
+        (long long*)darea, (const int*)dwork);
     GM_TRY(cudaGetLastError());
     count_launch();
     if (!order_stat && covered) {
