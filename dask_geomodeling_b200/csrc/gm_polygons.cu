@@ -605,9 +605,10 @@ constexpr int ZW_WARPS = 8;
 constexpr int ZW_MAXV = PG_FAST_MAXV;
 constexpr int ZW_MAXC = PG_FAST_MAXC;
 constexpr int ZW_ROWS = 4;
+constexpr int ZW_MIN_BLOCKS = 4;
 constexpr int ZW_BIG_ROWS = 256;
 constexpr long long ZW_BIG_CELLS = 1 << 17;
-constexpr int ZW_SUM = 1, ZW_MINMAX = 2;
+constexpr int ZW_SUM = 1, ZW_MIN = 2, ZW_MAX = 4, ZW_ALL = 7;
 
 template <typename T, int NEED>
 struct WarpReduce {
@@ -622,7 +623,8 @@ struct WarpReduce {
     if (active(v)) {
       ++count;
       if (NEED & ZW_SUM) sum += (double)v;
-      if (NEED & ZW_MINMAX) { vmin = tmin<T>(vmin, v); vmax = tmax<T>(vmax, v); }
+      if (NEED & ZW_MIN) vmin = tmin<T>(vmin, v);
+      if (NEED & ZW_MAX) vmax = tmax<T>(vmax, v);
     }
   }
   // scalar walk of one span (rows that are not plain single spans)
@@ -639,45 +641,119 @@ struct WarpReduce {
       if (!in_pairs(x, buf, n)) { take(__ldg(row + x)); ++extra; }
     cells += extra;
   }
-  // ZW_ROWS consecutive rows y0.., row b spans [x0[b], x1[b]] (inclusive, clipped, may be
-  // empty); `mis` = element misalignment of the raster base w.r.t. 16 bytes
-  __device__ __forceinline__ void rows(int y0, const int* x0, const int* x1, int mis) {
+  // float32 rasters with a no-data value and no threshold (the usual case): the activity
+  // test and the predicated updates spelled out -- FSETP + 2 (+ F2F/DADD for the sum) or
+  // + 1 FMNMX per extreme; the compiler's own selection for `take` needs about twice that
+  __device__ __forceinline__ void take_f32(float v) {
+    const float nd = (float)active.nodata;
+    float lo = (float)vmin, hi = (float)vmax, vm = 0.0f;
+    if (NEED == ZW_SUM) {
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.neu.f32 p, %2, %3;\n\t"
+          "selp.f32 %0, %2, 0f00000000, p;\n\t"
+          "@p add.s32 %1, %1, 1;\n\t}"
+          : "=f"(vm), "+r"(count) : "f"(v), "f"(nd));
+    } else if (NEED == ZW_MIN) {
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.neu.f32 p, %2, %3;\n\t"
+          "@p min.f32 %0, %0, %2;\n\t"
+          "@p add.s32 %1, %1, 1;\n\t}"
+          : "+f"(lo), "+r"(count) : "f"(v), "f"(nd));
+    } else if (NEED == ZW_MAX) {
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.neu.f32 p, %2, %3;\n\t"
+          "@p max.f32 %0, %0, %2;\n\t"
+          "@p add.s32 %1, %1, 1;\n\t}"
+          : "+f"(hi), "+r"(count) : "f"(v), "f"(nd));
+    } else {
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.neu.f32 p, %4, %5;\n\t"
+          "selp.f32 %0, %4, 0f00000000, p;\n\t"
+          "@p min.f32 %1, %1, %4;\n\t"
+          "@p max.f32 %2, %2, %4;\n\t"
+          "@p add.s32 %3, %3, 1;\n\t}"
+          : "=f"(vm), "+f"(lo), "+f"(hi), "+r"(count) : "f"(v), "f"(nd));
+    }
+    if (NEED & ZW_SUM) sum += (double)vm;
+    if (NEED & ZW_MIN) vmin = (T)lo;
+    if (NEED & ZW_MAX) vmax = (T)hi;
+  }
+  // ZW_ROWS consecutive single-span rows y0.. are walked as one batch.  `tab` is the warp's
+  // shared row table (see the kernel): per row x0 / xe = the span [x0, xe) and xh / xt = its
+  // part [xh, xt) made of whole, 16-byte aligned quads.  The quads are read with one 16-byte
+  // load per lane and need no position test; the at most 2 (VEC - 1) cells per row in front
+  // of and behind them are read by one lane each, in the same round of loads.  `issue` only
+  // starts the loads of a batch, `consume` reduces them: the kernel issues batch i + 1
+  // before it consumes batch i, so every warp computes under its own loads.
+  static constexpr int PER = 2 * (VEC - 1);                     // edge cells per row at most
+  struct Batch { uint4 q[ZW_ROWS]; T edge; };
+  __device__ __forceinline__ bool edge_cell(int y0, const int* tab, int i, int64_t* at) const {
+    const int b = i / PER, c = i - b * PER;
+    const bool head = c < VEC - 1;
+    const int bb = b < ZW_ROWS ? b : 0;
+    const int x0 = tab[bb], xe = tab[32 + bb], xh = tab[64 + bb], xt = tab[96 + bb];
+    const int x = (head ? x0 + c : xt + c - (VEC - 1));
+    *at = (int64_t)(y0 + bb) * width + x;
+    return i < ZW_ROWS * PER && x < (head ? min(xh, xe) : xe);
+  }
+  __device__ __forceinline__ void issue(int y0, const int* tab, Batch& B) const {
     const int lane = threadIdx.x & 31;
-    int xa[ZW_ROWS], longest = 0;
 #pragma unroll
     for (int b = 0; b < ZW_ROWS; ++b) {
-      const int64_t off = (int64_t)(y0 + b) * width + mis;       // element offset from the 16-byte grid
-      xa[b] = x0[b] - (int)((off + x0[b]) & (VEC - 1));          // quad-aligned start of the span
-      if (x0[b] <= x1[b]) longest = max(longest, x1[b] - xa[b] + 1);
+      const int x = tab[64 + b] + VEC * lane;
+      B.q[b] = make_uint4(0u, 0u, 0u, 0u);
+      if (x < tab[96 + b])
+        B.q[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x));
     }
-    for (int k = 0; k < longest; k += 32 * VEC) {
-      uint4 q[ZW_ROWS];
-      int x[ZW_ROWS];
+    int64_t at;
+    B.edge = T(0);
+    if (edge_cell(y0, tab, lane, &at)) B.edge = __ldg(raster + at);
+  }
+  template <bool F32_FAST>
+  __device__ __forceinline__ void consume(int y0, const int* tab, const Batch& B) {
+    const int lane = threadIdx.x & 31;
+    int longest = 0;
 #pragma unroll
-      for (int b = 0; b < ZW_ROWS; ++b) {
-        x[b] = xa[b] + k + VEC * lane;
-        q[b] = make_uint4(0u, 0u, 0u, 0u);
-        if (x0[b] <= x1[b] && x[b] <= x1[b])
-          q[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x[b]));
-      }
-#pragma unroll
-      for (int b = 0; b < ZW_ROWS; ++b) {
-        const unsigned len = (unsigned)(x1[b] - x0[b]);          // empty rows: x0 = 1, x1 = 0 -> handled below
-        const int rel = x[b] - x0[b];
+    for (int b = 0; b < ZW_ROWS; ++b) {
+      const int x = tab[64 + b] + VEC * lane, xt = tab[96 + b];
+      longest = max(longest, xt - tab[64 + b]);
+      if (x < xt) {
         T e[VEC];
-        memcpy(e, &q[b], 16);
-        if (x0[b] <= x1[b]) {
+        memcpy(e, &B.q[b], 16);
 #pragma unroll
-          for (int j = 0; j < VEC; ++j)
-            if ((unsigned)(rel + j) <= len) take(e[j]);
+        for (int j = 0; j < VEC; ++j) {
+          if constexpr (F32_FAST && std::is_same<T, float>::value) take_f32(e[j]);
+          else take(e[j]);
         }
       }
     }
+    int64_t at;
+    if (edge_cell(y0, tab, lane, &at)) take(B.edge);
+    // what one round of loads does not cover: quads beyond the first 32 of a row, edge
+    // cells beyond the first 32 of the batch (1-byte rasters)
+    if (longest > 32 * VEC) {
+      for (int k = 32 * VEC + VEC * lane; k - VEC * lane < longest; k += 32 * VEC) {
+#pragma unroll
+        for (int b = 0; b < ZW_ROWS; ++b) {
+          const int x = tab[64 + b] + k;
+          if (x < tab[96 + b]) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x));
+            T e[VEC];
+            memcpy(e, &q, 16);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) take(e[j]);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int i = 32 + lane; i < ZW_ROWS * PER; i += 32)
+      if (edge_cell(y0, tab, i, &at)) take(__ldg(raster + at));
   }
 };
 
 template <typename T, int NEED>
-__global__ void __launch_bounds__(32 * ZW_WARPS, 4)
+__global__ void __launch_bounds__(32 * ZW_WARPS, ZW_MIN_BLOCKS)
 zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
                          const float* __restrict__ thresholds, int mis, int edge_scalar,
                          GmZonalPartial* __restrict__ partial, long long* __restrict__ cells,
@@ -698,6 +774,7 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
   vis.raster = raster; vis.width = P.width;
   vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
   vis.active.has_threshold = thresholds != nullptr;
+  const bool f32_fast = std::is_same<T, float>::value && has_nodata && thresholds == nullptr;
   for (;;) {
     int64_t p = 0;
     if (lane == 0) p = atomicAdd(work + 1, 1);
@@ -777,21 +854,29 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
               s_cross[warp][j + 1][lane] = v;
             }
         }
-        // first span of the row, clipped and inclusive, for the batched 16-byte walk; rows
-        // with more spans, or on the raster's first / last line when a quad could reach
-        // outside the array, are walked span by span with scalar loads afterwards
+        // The row table of the batched walk: first span of the row [fx0, fxe) clipped to the
+        // raster, and its part [xh, xt) made of whole quads aligned to 16 bytes.  Rows with
+        // more spans, or on the raster's first / last line when a quad could reach outside
+        // the array, are walked span by span with scalar loads.
         const bool edge = edge_scalar && (y == 0 || y == P.height - 1);
         const bool scalar_row = !complex_row && cnt >= 2 && (cnt > 2 || edge);
-        int fx0 = 1, fx1 = 0;
+        int fx0 = 0, fxe = 0, xh = 0, xt = 0;
         if (!complex_row && !scalar_row && cnt == 2) {
+          constexpr int VEC = WarpReduce<T, NEED>::VEC;
           const int xa = s_cross[warp][0][lane], xb = s_cross[warp][1][lane];
-          if (xa <= maxx && xb > 0) { fx0 = xa < 0 ? 0 : xa; fx1 = xb - 1 > maxx ? maxx : xb - 1; }
-          if (fx0 <= fx1) vis.cells += fx1 - fx0 + 1; else { fx0 = 1; fx1 = 0; }
+          if (xa <= maxx && xb > 0 && (xa < 0 ? 0 : xa) < (xb > P.width ? P.width : xb)) {
+            fx0 = xa < 0 ? 0 : xa; fxe = xb > P.width ? P.width : xb;
+            vis.cells += fxe - fx0;
+            const int64_t off = (int64_t)y * P.width + mis;      // element offset from the 16-byte grid
+            xh = fx0 + (int)((VEC - ((off + fx0) & (VEC - 1))) & (VEC - 1));
+            xt = fxe - (int)((off + fxe) & (VEC - 1));
+            if (xt < xh) xt = xh;
+          }
         }
         __syncwarp();
         const unsigned complex_mask = __ballot_sync(0xffffffffu, complex_row);
         unsigned scalar_mask = __ballot_sync(0xffffffffu, scalar_row);
-        const unsigned single_mask = __ballot_sync(0xffffffffu, fx0 <= fx1);
+        const unsigned single_mask = __ballot_sync(0xffffffffu, fx0 < fxe);
         // the scalar rows first: they still need their raw crossings
         while (scalar_mask) {
           const int r = __ffs(scalar_mask) - 1;
@@ -807,15 +892,21 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
         }
         __syncwarp();
         s_cross[warp][0][lane] = fx0;
-        s_cross[warp][1][lane] = fx1;
+        s_cross[warp][1][lane] = fxe;
+        s_cross[warp][2][lane] = xh;
+        s_cross[warp][3][lane] = xt;
         __syncwarp();
+        {
+          typename WarpReduce<T, NEED>::Batch A;
+          const int* tab = &s_cross[warp][0][0];
+          constexpr unsigned BM = (1u << ZW_ROWS) - 1u;
 #pragma unroll 1
-        for (int rb = 0; rb < 32; rb += ZW_ROWS) {
-          if (((single_mask >> rb) & ((1u << ZW_ROWS) - 1u)) == 0) continue;
-          int x0[ZW_ROWS], x1[ZW_ROWS];
-#pragma unroll
-          for (int b = 0; b < ZW_ROWS; ++b) { x0[b] = s_cross[warp][0][rb + b]; x1[b] = s_cross[warp][1][rb + b]; }
-          vis.rows(base + rb, x0, x1, mis);
+          for (int rb = 0; rb < 32; rb += ZW_ROWS) {
+            if (((single_mask >> rb) & BM) == 0) continue;
+            vis.issue(base + rb, tab + rb, A);
+            if (f32_fast) vis.template consume<true>(base + rb, tab + rb, A);
+            else vis.template consume<false>(base + rb, tab + rb, A);
+          }
         }
         unsigned cm = complex_mask;
         while (cm) {
@@ -832,10 +923,8 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
       count += __shfl_xor_sync(0xffffffffu, count, o);
       vis.cells += __shfl_xor_sync(0xffffffffu, vis.cells, o);
       if (NEED & ZW_SUM) vis.sum += __shfl_xor_sync(0xffffffffu, vis.sum, o);
-      if (NEED & ZW_MINMAX) {
-        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-      }
+      if (NEED & ZW_MIN) vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      if (NEED & ZW_MAX) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     if (lane == 0) {
       partial[p] = GmZonalPartial{count, vis.sum, vmin, vmax};
@@ -1414,17 +1503,17 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
     const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (uintptr_t)(vec - 1));
     const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
                             (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
-    const int need = partial ? (ZW_SUM | ZW_MINMAX)
-                             : (stat == GM_STAT_MIN || stat == GM_STAT_MAX) ? ZW_MINMAX : ZW_SUM;
+    const int need = partial ? ZW_ALL : stat == GM_STAT_MIN ? ZW_MIN : stat == GM_STAT_MAX ? ZW_MAX : ZW_SUM;
     int64_t wblocks = (np_ + ZW_WARPS - 1) / ZW_WARPS;
-    if (wblocks > (int64_t)sm_count() * 4) wblocks = (int64_t)sm_count() * 4;
+    if (wblocks > (int64_t)sm_count() * ZW_MIN_BLOCKS) wblocks = (int64_t)sm_count() * ZW_MIN_BLOCKS;
 #define GM_ZW(NEED)                                                                              \
     zonal_reduce_warp_kernel<T, NEED><<<(unsigned)wblocks, 32 * ZW_WARPS, 0, s>>>(                \
         u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, mis, edge_scalar,        \
         (GmZonalPartial*)dpartial, (long long*)darea, (int*)dwork)
     if (need == ZW_SUM) GM_ZW(ZW_SUM);
-    else if (need == ZW_MINMAX) GM_ZW(ZW_MINMAX);
-    else GM_ZW(ZW_SUM | ZW_MINMAX);
+    else if (need == ZW_MIN) GM_ZW(ZW_MIN);
+    else if (need == ZW_MAX) GM_ZW(ZW_MAX);
+    else GM_ZW(ZW_ALL);
 #undef GM_ZW
     GM_TRY(cudaGetLastError());
     count_launch();
