@@ -20,6 +20,7 @@
 // scratch for polygons that do not fit).
 #include "gm_common.cuh"
 #include <cfloat>
+#include <cstdlib>
 #include <limits>
 #include <type_traits>
 
@@ -430,13 +431,16 @@ struct AreaVisitor {
 };
 
 __global__ void __launch_bounds__(PG_THREADS)
-zonal_area_kernel(const PolyDev P, long long* __restrict__ area) {
+zonal_area_kernel(const PolyDev P, long long* __restrict__ area, const int* __restrict__ work) {
+  // work[0] polygons listed from work[2]
   extern __shared__ int pg_smem[];
   __shared__ long long warp_area[PG_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int* buf = pg_smem + warp * P.cap;
   int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
-  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+  const int n_listed = work[0];
+  for (int item = blockIdx.x; item < n_listed; item += gridDim.x) {
+    const int64_t p = work[2 + item];
     AreaVisitor vis{0};
     scan_polygon(P, p, buf, hbuf, vis);
     if (lane == 0) warp_area[warp] = vis.area;
@@ -1189,7 +1193,7 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
                     const float* __restrict__ thresholds, int stat, double q,
                     const long long* __restrict__ area, const long long* __restrict__ big_offset,
                     typename KeyOf<T>::type* __restrict__ big_keys, int smem_capacity,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, const int* __restrict__ work) {
   typedef typename KeyOf<T>::type K;
   extern __shared__ __align__(16) unsigned char sel_smem[];
   const int nw = SEL_THREADS / 32;
@@ -1201,7 +1205,9 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
   __shared__ int hist[256];
   __shared__ SelectScratch<K> select_scratch;
   __shared__ int cursor;
-  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+  const int n_listed = work[0];
+  for (int item = blockIdx.x; item < n_listed; item += gridDim.x) {
+    const int64_t p = work[2 + item];
     const long long a = area[p];
     K* keys = a <= smem_capacity ? smem_keys : big_keys + big_offset[p];
     if (threadIdx.x == 0) cursor = 0;
@@ -1219,6 +1225,378 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
     const float result = order_statistic<T>(keys, n, stat, q, hist, &select_scratch);
     if (threadIdx.x == 0) out[p] = result;
     __syncthreads();
+  }
+}
+
+// ---- order statistics, the usual polygon -------------------------------------------------------
+// float32 rasters, polygons of <= ZW_MAXV vertices, <= ZS_MAXROWS rows of <= ZW_MAXC crossings,
+// <= ZS_MAXSPANS spans, no horizontal bottom edge on a scanline, and whose cells fit shared
+// memory; everything else is appended to the list in `work` for zonal_select_kernel.  One
+// block per polygon:
+//   1. a thread per row finds the row's spans (same arithmetic as the scanline code);
+//   2. a block scan gives every span its slot range in shared memory, padded to whole quads;
+//   3. warps copy spans with 16-byte loads, turning cells into sortable keys on the way (cells
+//      outside the span or without data become the all-ones sentinel), 4 rows in flight;
+//   4. 32 sampled keys bracket the wanted rank; ONE counting pass over the keys (cells below
+//      the bracket are counted, cells inside it fall into 2048 equal bins of the bracket), a
+//      scan of the bins, one pass that collects the handful of keys of the bin holding the
+//      rank, and a rank count among those.  When the bracket misses (skewed data), the 8-bit
+//      radix select runs over all keys instead.
+// The order of the keys in shared memory is irrelevant, so spans are stored as they come.
+constexpr int ZS_THREADS = 256;
+constexpr int ZS_MAXROWS = 512;
+constexpr int ZS_MAXSPANS = 1024;
+constexpr int ZS_DIGIT = 11, ZS_BINS = 1 << ZS_DIGIT;
+constexpr int ZS_CAND = 2048;
+constexpr int ZS_ROWS = 8;               // rows per warp and round of loads
+constexpr int ZS_MARGIN = 8;             // sample positions either side of the wanted rank (of 32)
+constexpr unsigned ZS_EMPTY = 0xffffffffu;
+
+__global__ void __launch_bounds__(ZS_THREADS, 2)
+zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, float nodata, int has_nodata,
+                         int mis, int edge_scalar, int stat, double q, int capacity,
+                         float* __restrict__ out, long long* __restrict__ area, int* __restrict__ work) {
+  extern __shared__ __align__(16) unsigned char zs_smem[];
+  unsigned* keys = reinterpret_cast<unsigned*>(zs_smem);
+  __shared__ double s_px[ZW_MAXV], s_py[ZW_MAXV];
+  __shared__ int s_prev[ZW_MAXV];
+  __shared__ int s_y[ZS_MAXSPANS], s_x0[ZS_MAXSPANS], s_xe[ZS_MAXSPANS], s_base[ZS_MAXSPANS + 1];
+  __shared__ int s_hist[ZS_BINS];
+  __shared__ __align__(16) unsigned s_cand[ZS_CAND];
+  __shared__ int s_hist8[256];
+  __shared__ SelectScratch<unsigned> s_scratch;
+  __shared__ int s_wsum[ZS_THREADS / 32];
+  __shared__ int s_defer, s_count, s_ncand, s_blo, s_bhi, s_rlo, s_rhi, s_cells, s_nspans, s_below, s_inside;
+  __shared__ unsigned s_kmin, s_kmax, s_khi, s_lowest, s_highest1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int maxx = P.width - 1;
+  const float nanf_ = __int_as_float(0x7fc00000);
+  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+    const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
+    const int miny = P.miny[p], maxy = P.maxy[p];
+    int64_t v0 = 0, v1 = 0;
+    if (r1 > r0) { v0 = P.ring_offsets[r0]; v1 = P.ring_offsets[r1]; }
+    const int nv = (int)min((int64_t)(ZW_MAXV + 1), v1 - v0);
+    const int rows = maxy - miny + 1;
+    __syncthreads();   // the previous polygon is done with shared memory
+    if (tid == 0) {
+      s_defer = 0; s_count = 0; s_ncand = 0; s_cells = 0; s_nspans = 0; s_below = 0; s_inside = 0;
+      s_kmin = ZS_EMPTY; s_kmax = 0u; s_khi = ZS_EMPTY; s_lowest = ZS_EMPTY; s_highest1 = 0u;
+    }
+    if (rows <= 0 || nv == 0) {   // nothing under the polygon
+      if (tid == 0) { out[p] = nanf_; area[p] = 0; }
+      continue;
+    }
+    if (nv > ZW_MAXV || nv < 2 || rows > ZS_MAXROWS) {
+      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
+      continue;
+    }
+    for (int i = tid; i < nv; i += ZS_THREADS) {
+      s_px[i] = P.px[v0 + i];
+      s_py[i] = P.py[v0 + i];
+      int pr = i - 1;
+      for (int64_t r = r0; r < r1; ++r)
+        if ((int64_t)i + v0 == P.ring_offsets[r]) pr = (int)(P.ring_offsets[r + 1] - v0) - 1;
+      s_prev[i] = pr;
+    }
+    __syncthreads();
+    // 1. one thread per row: sorted crossings in registers, one table entry per span
+    int my_cells = 0;
+    for (int r = tid; r < rows; r += ZS_THREADS) {
+      const int y = miny + r;
+      const double dy = y + 0.5;
+      int cnt = 0, c[ZW_MAXC];
+#pragma unroll
+      for (int j = 0; j < ZW_MAXC; ++j) c[j] = INT_MAX;
+      bool bad = edge_scalar && (y == 0 || y == P.height - 1);
+      for (int i = 0; i < nv; ++i) {
+        const int ind1 = s_prev[i];
+        double dy1 = s_py[ind1], dy2 = s_py[i];
+        if ((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy)) continue;
+        double dx1, dx2;
+        if (dy1 < dy2) {
+          dx1 = s_px[ind1]; dx2 = s_px[i];
+        } else if (dy1 > dy2) {
+          const double t = dy1; dy1 = dy2; dy2 = t;
+          dx2 = s_px[ind1]; dx1 = s_px[i];
+        } else {
+          if (s_px[ind1] > s_px[i]) bad = true;  // bottom horizontal edge on the scanline
+          continue;
+        }
+        if (dy < dy2 && dy >= dy1) {
+          const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+          int xi = clamp_to_int(floor(intersect + 0.5));
+#pragma unroll
+          for (int j = 0; j < ZW_MAXC; ++j) {   // sorted insert: the largest value falls out
+            const int lo = min(c[j], xi);
+            xi = max(c[j], xi);
+            c[j] = lo;
+          }
+          ++cnt;
+        }
+      }
+      if (cnt > ZW_MAXC || (cnt & 1)) bad = true;
+      if (!bad) {
+#pragma unroll
+        for (int i = 0; i + 1 < ZW_MAXC; i += 2) {
+          if (i + 1 < cnt && c[i] <= maxx && c[i + 1] > 0) {
+            const int x0 = c[i] < 0 ? 0 : c[i];
+            const int xe = c[i + 1] > P.width ? P.width : c[i + 1];
+            if (x0 < xe) {
+              const int at = atomicAdd(&s_nspans, 1);
+              if (at < ZS_MAXSPANS) {
+                const int64_t off = (int64_t)y * P.width + mis;
+                const int a0 = x0 - (int)((off + x0) & 3);
+                const int ae = xe + (int)((4 - ((off + xe) & 3)) & 3);
+                s_y[at] = y; s_x0[at] = x0; s_xe[at] = xe; s_base[at] = ae - a0;
+                my_cells += xe - x0;
+              } else {
+                bad = true;
+              }
+            }
+          }
+        }
+      }
+      if (bad) s_defer = 1;
+    }
+    if (my_cells) atomicAdd(&s_cells, my_cells);
+    __syncthreads();
+    if (s_defer) {
+      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
+      continue;
+    }
+    const int spans = s_nspans;
+    // 2. exclusive scan of the slot counts (ZS_MAXSPANS / ZS_THREADS spans per thread)
+    {
+      constexpr int PERT = ZS_MAXSPANS / ZS_THREADS;
+      int v[PERT], sum = 0;
+#pragma unroll
+      for (int j = 0; j < PERT; ++j) { v[j] = PERT * tid + j < spans ? s_base[PERT * tid + j] : 0; sum += v[j]; }
+      int incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < warp; ++w) before += s_wsum[w];
+      int run = before + incl - sum;
+#pragma unroll
+      for (int j = 0; j < PERT; ++j) { if (PERT * tid + j < spans) s_base[PERT * tid + j] = run; run += v[j]; }
+      if (tid == ZS_THREADS - 1) s_base[ZS_MAXSPANS] = run;   // total
+      __syncthreads();
+    }
+    const int total = s_base[ZS_MAXSPANS];
+    if (total > capacity) {
+      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
+      continue;
+    }
+    if (tid == 0) area[p] = s_cells;
+    if (total == 0) {
+      if (tid == 0) out[p] = nanf_;
+      continue;
+    }
+    // 3. spans -> keys, ZS_ROWS spans per warp and round
+    int my_count = 0;
+    unsigned my_min = ZS_EMPTY, my_max1 = 0u;
+    for (int rb = ZS_ROWS * warp; rb < spans; rb += ZS_ROWS * (ZS_THREADS / 32)) {
+      int widest = 0;
+      int a0[ZS_ROWS], ae[ZS_ROWS];
+#pragma unroll
+      for (int b = 0; b < ZS_ROWS; ++b) {
+        const int r = rb + b;
+        a0[b] = 0; ae[b] = 0;
+        if (r < spans) {
+          const int64_t off = (int64_t)s_y[r] * P.width + mis;
+          a0[b] = s_x0[r] - (int)((off + s_x0[r]) & 3);
+          ae[b] = s_xe[r] + (int)((4 - ((off + s_xe[r]) & 3)) & 3);
+        }
+        widest = max(widest, ae[b] - a0[b]);
+      }
+      for (int k = 4 * lane; k - 4 * lane < widest; k += 128) {
+        uint4 qv[ZS_ROWS];
+#pragma unroll
+        for (int b = 0; b < ZS_ROWS; ++b) {
+          qv[b] = make_uint4(0u, 0u, 0u, 0u);
+          if (a0[b] + k < ae[b])
+            qv[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)s_y[rb + b] * P.width + (a0[b] + k)));
+        }
+#pragma unroll
+        for (int b = 0; b < ZS_ROWS; ++b) {
+          if (a0[b] + k < ae[b]) {
+            const int r = rb + b;
+            const int x0 = s_x0[r], xe = s_xe[r];
+            float e[4];
+            memcpy(e, &qv[b], 16);
+            unsigned kk[4];
+            const unsigned len = (unsigned)(xe - x0), rel = (unsigned)(a0[b] + k - x0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const bool active = rel + j < len && !(has_nodata && e[j] == nodata);
+              const unsigned key = order_f32(e[j]);   // (the NaN 0x7fffffff alone maps to the sentinel)
+              my_count += active ? 1 : 0;
+              kk[j] = active ? key : ZS_EMPTY;
+              my_min = min(my_min, kk[j]);             // the sentinel is neutral for the minimum
+              my_max1 = max(my_max1, kk[j] + 1u);      // ... and wraps to 0 here: largest key + 1
+            }
+            *reinterpret_cast<uint4*>(keys + s_base[r] + k) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+          }
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      my_count += __shfl_xor_sync(0xffffffffu, my_count, o);
+      my_min = min(my_min, __shfl_xor_sync(0xffffffffu, my_min, o));
+      my_max1 = max(my_max1, __shfl_xor_sync(0xffffffffu, my_max1, o));
+    }
+    if (lane == 0) { atomicAdd(&s_count, my_count); atomicMin(&s_lowest, my_min); atomicMax(&s_highest1, my_max1); }
+    for (int i = tid; i < ZS_BINS; i += ZS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const int n = s_count;
+    if (n == 0) {
+      if (tid == 0) out[p] = nanf_;
+      continue;
+    }
+    long long rank_lo, rank_hi;
+    double part = 0.0;
+    if (stat == GM_STAT_MEDIAN) {
+      rank_lo = (n - 1) / 2; rank_hi = n / 2;
+    } else {
+      const double frac = (double)(n - 1) * (q / 100.0);
+      rank_lo = (long long)floor(frac);
+      rank_hi = (long long)ceil(frac);
+      part = frac - floor(frac);
+    }
+    // 4. A bracket [bk_lo, bk_hi] of keys around the wanted ranks from 32 evenly spaced
+    // samples (the sentinels sort behind every key, so ranks among all `total` slots are
+    // ranks among the active cells): sample positions +- ZS_MARGIN around the rank's share.
+    if (warp == 0) {
+      const unsigned mine = keys[(int)(((long long)lane * total) / 32)];
+      int rank = 0;
+      for (int j = 0; j < 32; ++j) {
+        const unsigned o = __shfl_sync(0xffffffffu, mine, j);
+        rank += (o < mine) || (o == mine && j < lane);
+      }
+      const int lo_at = (int)((rank_lo * 32) / total) - ZS_MARGIN;
+      const int hi_at = (int)((rank_hi * 32) / total) + 1 + ZS_MARGIN;
+      if (lo_at < 0 && lane == 0) s_kmin = s_lowest;            // the smallest / largest key
+      if (hi_at > 31 && lane == 0) s_kmax = s_highest1 - 1u;
+      if (rank == lo_at) s_kmin = mine;
+      if (rank == hi_at) s_kmax = mine;
+    }
+    __syncthreads();
+    unsigned bk_lo = s_kmin, bk_hi = min(s_kmax, ZS_EMPTY - 1u);
+    if (bk_lo > bk_hi) { bk_lo = 0u; bk_hi = ZS_EMPTY - 1u; }   // sentinels in the sample: no bracket
+    // the digit: ZS_DIGIT bits of (key - bk_lo), scaled so that the bracket fills the bins
+    const int shift = max(32 - __clz(bk_hi - bk_lo) - ZS_DIGIT, 0);
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    int below = 0, inside = 0;
+    for (int i = tid; i < total / 4; i += ZS_THREADS) {
+      const uint4 v = k4[i];
+      const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        below += vv[j] < bk_lo ? 1 : 0;
+        if (vv[j] - bk_lo <= bk_hi - bk_lo) { atomicAdd(&s_hist[(vv[j] - bk_lo) >> shift], 1); ++inside; }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      below += __shfl_xor_sync(0xffffffffu, below, o);
+      inside += __shfl_xor_sync(0xffffffffu, inside, o);
+    }
+    if (lane == 0) { atomicAdd(&s_below, below); atomicAdd(&s_inside, inside); }
+    __syncthreads();
+    unsigned klo, khi;
+    const long long in_lo = rank_lo - s_below, in_hi = rank_hi - s_below;
+    if (in_lo < 0 || in_hi >= s_inside) {
+      // the samples misjudged the distribution (rare): select over everything
+      block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
+    } else {
+      {
+        constexpr int PERT = ZS_BINS / ZS_THREADS;
+        int local[PERT], sum = 0;
+#pragma unroll
+        for (int j = 0; j < PERT; ++j) { local[j] = s_hist[tid * PERT + j]; sum += local[j]; }
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += s_wsum[w];
+        const int excl = before + incl - sum;
+        if (in_lo >= excl && in_lo < excl + sum) {
+          int r = (int)in_lo - excl;
+#pragma unroll
+          for (int j = 0; j < PERT; ++j) {
+            if (r >= 0 && r < local[j]) { s_blo = tid * PERT + j; s_rlo = r; }
+            r -= local[j];
+          }
+        }
+        if (in_hi >= excl && in_hi < excl + sum) {
+          int r = (int)in_hi - excl;
+#pragma unroll
+          for (int j = 0; j < PERT; ++j) {
+            if (r >= 0 && r < local[j]) { s_bhi = tid * PERT + j; s_rhi = r; }
+            r -= local[j];
+          }
+        }
+        __syncthreads();
+      }
+      const int b_lo = s_blo, b_hi = s_bhi;
+      const int m = s_hist[b_lo];
+      if (shift == 0) {
+        klo = bk_lo + (unsigned)b_lo;          // one key per bin
+        khi = bk_lo + (unsigned)b_hi;
+      } else if (m > ZS_CAND) {
+        block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
+      } else {
+        // the keys of bin b_lo (a handful) and the smallest key above that bin
+        unsigned above = ZS_EMPTY;
+        for (int i = tid; i < total / 4; i += ZS_THREADS) {
+          const uint4 v = k4[i];
+          const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned d = (vv[j] - bk_lo) >> shift;
+            const bool in = vv[j] - bk_lo <= bk_hi - bk_lo;
+            if (in && d == (unsigned)b_lo) s_cand[atomicAdd(&s_ncand, 1)] = vv[j];
+            else if (vv[j] != ZS_EMPTY && vv[j] >= bk_lo && (!in || d > (unsigned)b_lo)) above = min(above, vv[j]);
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) above = min(above, __shfl_xor_sync(0xffffffffu, above, o));
+        if (lane == 0 && above != ZS_EMPTY) atomicMin(&s_khi, above);
+        __syncthreads();
+        const bool together = b_hi == b_lo;
+        const int want_lo = s_rlo, want_hi = together ? s_rhi : s_rlo;
+        if (m <= 32) {
+          // one candidate per lane, ranked against the others
+          if (warp == 0) {
+            const unsigned mine = lane < m ? s_cand[lane] : ZS_EMPTY;
+            int rank = 0;
+            for (int j = 0; j < m; ++j) {
+              const unsigned o = __shfl_sync(0xffffffffu, mine, j);
+              rank += (o < mine) || (o == mine && j < lane);
+            }
+            if (lane < m && rank == want_lo) s_scratch.min_key = mine;
+            if (lane < m && rank == want_hi) s_kmax = mine;
+          }
+          __syncthreads();
+          klo = s_scratch.min_key;
+          khi = s_kmax;
+        } else {
+          block_select2<unsigned>(s_cand, m, (long long)want_lo, (long long)want_hi, &klo, &khi, s_hist8, &s_scratch);
+        }
+        if (!together) khi = s_khi;
+      }
+    }
+    if (tid == 0) {
+      const float lo = unorder_f32(klo), hi = unorder_f32(khi);
+      out[p] = stat == GM_STAT_MEDIAN ? median_of<float>(lo, hi) : percentile_of<float>(lo, hi, part);
+    }
   }
 }
 
@@ -1465,10 +1843,10 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   T nd = T(0);
   if (has_nodata) memcpy(&nd, nodata, sizeof(T));
   void *darea = nullptr, *dthr = nullptr, *dpartial = nullptr, *dout = nullptr;
-  void *doff = nullptr, *dtotal = nullptr, *dbig = nullptr, *scratch_work = nullptr;
+  void *doff = nullptr, *dtotal = nullptr, *dbig = nullptr, *scratch_work = nullptr, *scratch_list = nullptr;
   int rc = 0;
   auto cleanup = [&]() {
-    void* all[] = {darea, dthr, dpartial, dout, doff, dtotal, dbig, scratch_work};
+    void* all[] = {darea, dthr, dpartial, dout, doff, dtotal, dbig, scratch_work, scratch_list};
     for (void* p : all) if (p) cudaFreeAsync(p, s);
   };
 #define GM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
@@ -1481,11 +1859,55 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   }
   const bool order_stat = stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE;
   std::vector<long long> area(np_);
+  // order statistics: the deferred list (work[0] entries from work[2]) of the polygons the
+  // fast kernel does not take -- all of them when it does not apply
+  void* dlist = nullptr;
+  int n_listed = 0;
+  std::vector<int> listed;
   if (order_stat) {
-    // pixel centres inside every polygon (no raster access): `covered` and buffer sizes
-    zonal_area_kernel<<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea);
-    GM_TRY(cudaGetLastError());
-    count_launch();
+    GM_TRY(cudaMallocAsync(&dlist, sizeof(int) * (size_t)(np_ + 2), s));
+    scratch_list = dlist;
+    const bool fast = std::is_same<T, float>::value && !thresholds && out;
+    if (fast) {
+      GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
+      GM_TRY(cudaMemsetAsync(dlist, 0, 2 * sizeof(int), s));
+      const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & 3);
+      const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
+                              (((int64_t)u.dev.height * u.dev.width + mis) % 4) != 0;
+      int dev = 0, smem_max = 0;
+      GM_TRY(cudaGetDevice(&dev));
+      GM_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      // two blocks per SM: half of the 227 KB minus the static tables (~22 k cells per polygon)
+      const int dyn = (smem_max - 2 * 37 * 1024) / 2 / 16 * 16;
+      float ndf = 0.0f;
+      memcpy(&ndf, &nd, sizeof(float) < sizeof(T) ? sizeof(float) : sizeof(T));
+      GM_TRY(cudaFuncSetAttribute(zonal_select_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      zonal_select_fast_kernel<<<poly_grid(np_), ZS_THREADS, dyn, s>>>(
+          u.dev, (const float*)raster.dev, ndf, has_nodata, mis, edge_scalar, stat, q, dyn / 4,
+          (float*)dout, (long long*)darea, (int*)dlist);
+      GM_TRY(cudaGetLastError());
+      count_launch();
+      GM_TRY(cudaMemcpyAsync(&n_listed, dlist, sizeof(int), cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaStreamSynchronize(s));
+      listed.resize(n_listed);
+      if (getenv("GM_DEBUG_ZONAL")) fprintf(stderr, "gm_zonal_stats: %d of %lld polygons deferred to the generic select\n", n_listed, (long long)np_);
+      if (n_listed > 0)
+        GM_TRY(cudaMemcpyAsync(listed.data(), (const int*)dlist + 2, sizeof(int) * n_listed, cudaMemcpyDeviceToHost, s));
+    } else {
+      n_listed = (int)np_;
+      listed.resize(np_);
+      std::vector<int> host(np_ + 2);
+      host[0] = n_listed; host[1] = 0;
+      for (int64_t p = 0; p < np_; ++p) { host[2 + p] = (int)p; listed[p] = (int)p; }
+      GM_TRY(cudaMemcpyAsync(dlist, host.data(), sizeof(int) * (np_ + 2), cudaMemcpyHostToDevice, s));
+      GM_TRY(cudaStreamSynchronize(s));
+    }
+    if (n_listed > 0) {
+      // pixel centres inside the listed polygons (no raster access): `covered` and buffer sizes
+      zonal_area_kernel<<<poly_grid(n_listed), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea, (const int*)dlist);
+      GM_TRY(cudaGetLastError());
+      count_launch();
+    }
     GM_TRY(cudaMemcpyAsync(area.data(), darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
     GM_TRY(cudaStreamSynchronize(s));
     if (covered) for (int64_t p = 0; p < np_; ++p) covered[p] = area[p];
@@ -1539,33 +1961,30 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   }
   if (order_stat && out) {
     typedef typename KeyOf<T>::type K;
-    long long max_area = 0;
-    for (int64_t p = 0; p < np_; ++p) max_area = area[p] > max_area ? area[p] : max_area;
-    const size_t head = (scan_smem(u.dev.cap, SEL_THREADS / 32) + 15) / 16 * 16;
-    const size_t budget = 200 * 1024 - head;
-    long long capacity = (long long)(budget / sizeof(K));
-    if (max_area < capacity) capacity = max_area > 0 ? max_area : 1;
-    const size_t smem_sel = head + (size_t)capacity * sizeof(K);
-    GM_TRY(cudaFuncSetAttribute(zonal_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
-    GM_TRY(cudaMallocAsync(&doff, sizeof(long long) * np_, s));
-    GM_TRY(cudaMallocAsync(&dtotal, sizeof(long long), s));
-    long long total = 0;
-    if (max_area > capacity) {
-      big_offsets_kernel<<<1, 1, 0, s>>>((const long long*)darea, np_, (int)capacity, (long long*)doff, (long long*)dtotal);
+    if (!dout) GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
+    if (n_listed > 0) {
+      long long max_area = 0;
+      for (int p : listed) max_area = area[p] > max_area ? area[p] : max_area;
+      const size_t head = (scan_smem(u.dev.cap, SEL_THREADS / 32) + 15) / 16 * 16;
+      const size_t budget = 200 * 1024 - head;
+      long long capacity = (long long)(budget / sizeof(K));
+      if (max_area < capacity) capacity = max_area > 0 ? max_area : 1;
+      const size_t smem_sel = head + (size_t)capacity * sizeof(K);
+      GM_TRY(cudaFuncSetAttribute(zonal_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+      // global key segments for the polygons that do not fit shared memory
+      std::vector<long long> offsets(np_, 0);
+      long long total = 0;
+      for (int p : listed)
+        if (area[p] > capacity) { offsets[p] = total; total += area[p]; }
+      if (upload(&doff, offsets.data(), sizeof(long long) * np_, s)) { cleanup(); return 1; }
+      GM_TRY(cudaMallocAsync(&dbig, sizeof(K) * (size_t)(total > 0 ? total : 1), s));
+      zonal_select_kernel<T><<<poly_grid(n_listed), SEL_THREADS, smem_sel, s>>>(
+          u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, stat, q,
+          (const long long*)darea, (const long long*)doff, (K*)dbig, (int)capacity, (float*)dout,
+          (const int*)dlist);
       GM_TRY(cudaGetLastError());
       count_launch();
-      GM_TRY(cudaMemcpyAsync(&total, dtotal, sizeof(long long), cudaMemcpyDeviceToHost, s));
-      GM_TRY(cudaStreamSynchronize(s));
-    } else {
-      GM_TRY(cudaMemsetAsync(doff, 0, sizeof(long long) * np_, s));
     }
-    GM_TRY(cudaMallocAsync(&dbig, sizeof(K) * (size_t)(total > 0 ? total : 1), s));
-    GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
-    zonal_select_kernel<T><<<poly_grid(np_), SEL_THREADS, smem_sel, s>>>(
-        u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, stat, q,
-        (const long long*)darea, (const long long*)doff, (K*)dbig, (int)capacity, (float*)dout);
-    GM_TRY(cudaGetLastError());
-    count_launch();
     GM_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * np_, cudaMemcpyDeviceToHost, s));
   }
   GM_TRY(cudaStreamSynchronize(s));

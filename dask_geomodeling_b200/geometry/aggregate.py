@@ -102,7 +102,9 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(agg_bbox, height, width))
     n = soup.n_polygons
     agg = np.full((depth, n), np.nan, dtype="f4")
-    covered = np.zeros(n, dtype=np.int64)
+    # page-locked result buffers: the library's device-to-host copies are then plain DMA
+    covered = _native.pinned_empty((n,), np.int64)
+    covered[:] = 0
     s = sentinel(values.dtype, no_data_value)
     holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, values.dtype)
     thresholds = None
@@ -113,7 +115,7 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     lib = _native.lib()
     for frame in range(depth):
         desc = _frame_descriptor(values, frame)
-        out = np.empty(n, dtype=np.float32)
+        out = _native.pinned_empty((n,), np.float32)
         _native.check(lib.gm_zonal_stats(
             ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
             _STAT_CODES[statistic], float(percentile or 0.0),

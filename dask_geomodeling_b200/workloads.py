@@ -77,3 +77,28 @@ def cfg2_views(ints, floats):
     r = Reclassify(source(ints, 32767), CFG2_PAIRS, select=True)
     st = Step(Clip(source(floats, F32_MAX), r), left=0, right=1, value=50.0, at=0.5)
     return IsData(st), st
+
+
+def cfg4_rings(size, grid, seed=7):
+    """BASELINE.json configs[3] polygons: one jittered 6-12-gon per cell of a ``grid`` x ``grid``
+    partition of a ``size`` x ``size`` raster (vertex radius 0.40-0.55 of the cell, so that
+    neighbours overlap a little), vertices rounded to 3 decimals + 0.0137 (never on k + 0.5).
+    Returns the list of exterior rings, (k, 2) float64 arrays, in row-major cell order."""
+    rng = np.random.default_rng(seed)
+    cell = size / grid
+    rings = []
+    for i in range(grid):
+        for j in range(grid):
+            cx, cy = (j + 0.5) * cell, (i + 0.5) * cell
+            k = int(rng.integers(6, 13))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+            rad = cell * rng.uniform(0.40, 0.55, k)
+            ring = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
+            rings.append(np.round(ring, 3) + 0.0137)
+    return rings
+
+
+def cfg4_polygons(size, grid, seed=7):
+    from . import utils
+
+    return [utils.Polygon(ring) for ring in cfg4_rings(size, grid, seed)]

@@ -103,6 +103,37 @@ def test_zonal_stats(dtype, statistic):
         np.testing.assert_array_equal(got[0], expected)
 
 
+@pytest.mark.parametrize("kind", ["uniform", "few_values", "constant", "wide_range"])
+@pytest.mark.parametrize("statistic", ["median", "p90", "p1.5"])
+def test_zonal_order_statistics_convex_float32(kind, statistic):
+    """The shared-memory select path (float32, one span per row): value distributions that
+    stress the digit placement -- few distinct values, one value, 60 binades."""
+    h, w = 333, 402   # width not a multiple of 4: rows start at every 16-byte phase
+    rng = np.random.default_rng(21)
+    nodata = float(np.finfo("f4").max)
+    if kind == "uniform":
+        frame = rng.uniform(0, 100, (h, w))
+    elif kind == "few_values":
+        frame = rng.integers(0, 4, (h, w)).astype("f8") * 2.5 - 3
+    elif kind == "constant":
+        frame = np.full((h, w), 7.25)
+    else:
+        frame = rng.normal(0, 1, (h, w)) * 10.0 ** rng.integers(-9, 9, (h, w))
+    frame = frame.astype("f4")
+    frame[rng.random((h, w)) < 0.07] = nodata
+    frame[40:60, 100:140] = nodata            # a polygon with no data at all below
+    polys = random_polygons(70, 400, seed=8)
+    polys.append([[(100.3, 40.2), (139.6, 40.2), (139.6, 59.7), (100.3, 59.7)]])
+    polys.append([[(-20.5, -30.5), (450.2, -10.1), (440.7, 380.3), (-15.3, 350.9)]])  # larger than the raster
+    bbox = (0, 0, w, h)
+    name, q = utils.parse_percentile_statistic(statistic)
+    expected, no_cells = oracle_zonal(frame, nodata, polys, bbox, name, q)
+    got, got_no_cells = geometry.aggregate.aggregate_polygons(
+        to_geometries(polys), frame[np.newaxis], nodata, bbox, workloads.PROJECTION, None, name, q)
+    assert sorted(got_no_cells) == no_cells
+    np.testing.assert_array_equal(got[0], expected)
+
+
 def test_zonal_thresholds_and_large_polygon():
     h, w = 400, 420
     rng = np.random.default_rng(12)

@@ -128,17 +128,7 @@ def main():
         r[torch.rand(1, n, n, device="cuda") < 0.02] = nodata
         rd = wrap(r)
         g = int(128 * args.scale)
-        cell = n / g
-        rng = np.random.default_rng(7)
-        polys = []
-        for i in range(g):
-            for j in range(g):
-                cx, cy = (j + 0.5) * cell, (i + 0.5) * cell
-                k = int(rng.integers(6, 13))
-                ang = np.sort(rng.uniform(0, 2 * np.pi, k))
-                rad = cell * rng.uniform(0.40, 0.55, k)
-                ring = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
-                polys.append(utils.Polygon(np.round(ring, 3) + 0.0137))
+        polys = workloads.cfg4_polygons(n, g)   # the generator bench.py and the parity tests use
         bbox = (0, 0, n, n)
         soup = utils.PolygonSoup(polys).to_device()   # CSR build (6 us / polygon) + upload kept out of the timing
         for stat, q in (("mean", None), ("max", None), ("percentile", 90.0), ("median", None)):
