@@ -39,12 +39,16 @@ BYTES_PER_PIXEL = 7  # int16 + float32 in, bool out
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=16384, help="raster edge in pixels")
     ap.add_argument("--cpu-sample-rows", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--zonal-size", type=int, default=40000, help="raster edge of the zonal leg (cfg4)")
+    ap.add_argument("--zonal-grid", type=int, default=316, help="polygons per side of the zonal leg")
+    ap.add_argument("--zonal-steps", type=int, default=10)
+    ap.add_argument("--no-zonal", action="store_true", help="skip the AggregateRaster (cfg4) leg")
     ap.add_argument("--profile", action="store_true",
                     help="kernel-resident loop only (for ncu): no e2e, no CPU baseline")
     return ap.parse_args()
@@ -230,6 +234,67 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------
+# zonal statistics leg (BASELINE.json configs[3])
+# ----------------------------------------------------------------------------
+
+
+def run_zonal(args, torch, dist, stream, rank, world, peak):
+    """AggregateRaster mean / max / p90 of ~100 k polygons over a 40000 x 40000 float32 raster
+    resident in HBM, one raster + polygon set per GPU (weak scaling; a striped single raster
+    would add one all-reduce of N-vectors).  Timed per call of
+    ``aggregate_polygons`` -- the function AggregateRaster.process hands the raster to --
+    including the download of the per-polygon results; pixels/s = H * W / time."""
+    from dask_geomodeling_b200 import _native, utils, workloads
+    from dask_geomodeling_b200.core import fusion
+    from dask_geomodeling_b200.geometry import aggregate
+
+    n, g = args.zonal_size, args.zonal_grid
+    raster = torch.empty((1, n, n), dtype=torch.float32, device="cuda")
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7 + rank)
+    rows = max(1, (1 << 27) // n)
+    for r0 in range(0, n, rows):   # chunked: bounded temporaries next to the 6.4 GB raster
+        block = raster[0, r0:r0 + rows]
+        block.uniform_(0, 100, generator=gen)
+        block[torch.rand(block.shape, device="cuda", generator=gen) < 0.02] = workloads.F32_MAX
+    rd = _native.DeviceArray((1, n, n), "f4", ptr=raster.data_ptr(), owner=raster)
+    soup = utils.PolygonSoup(workloads.cfg4_polygons(n, g, seed=7 + rank)).to_device()
+    bbox = (0, 0, n, n)
+    out = {"workload": "cfg4 AggregateRaster {0}x{0} float32, {1} polygons per GPU".format(n, soup.n_polygons),
+           "unit": "Gpixel/s", "bytes_per_pixel": 4, "steps": args.zonal_steps,
+           "timed": "aggregate_polygons call on the HBM-resident raster incl. result download"}
+    with _native.use_stream(stream.cuda_stream), fusion.device_resident():
+        for label, stat, q in (("mean", "mean", None), ("max", "max", None), ("p90", "percentile", 90.0)):
+            def call():
+                return aggregate.aggregate_polygons(soup, rd, workloads.F32_MAX, bbox,
+                                                    workloads.PROJECTION, None, stat, q)
+            for _ in range(3):
+                res, _ = call()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            before = _native.launch_count()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record(stream)
+            for _ in range(args.zonal_steps):
+                res, _ = call()
+            stop.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0]) / args.zonal_steps
+            gpx = world * n * n / ms / 1e6
+            out[label] = {"value": gpx, "ms_per_call": ms, "gpu_launches_per_call":
+                          (_native.launch_count() - before) / args.zonal_steps,
+                          "frac_of_hbm_peak": 4 * n * n / ms / 1e6 / peak,
+                          "checksum": float(np.nansum(res[0].astype(np.float64)))}
+    del raster, rd
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
 
@@ -323,6 +388,15 @@ def run_b200(args):
         del inputs, leaf_payloads, out
     assert e2e_checksum is None or e2e_checksum == checksum, "e2e result differs from the resident result"
 
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
+    else:
+        peak, peak_kind = 6650.0, "fallback"
+    zonal = None
+    if not args.profile and not args.no_zonal:
+        zonal = run_zonal(args, torch, dist, stream, rank, world, peak)
+
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,11 +406,6 @@ def run_b200(args):
         ms_per_step = elapsed_ms / args.steps
         value = world * pixels / (ms_per_step / 1e3) / 1e9
         e2e_value = world * pixels * args.e2e_steps / e2e_s / 1e9
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
-        else:
-            peak, peak_kind = 6650.0, "fallback"
         achieved = BYTES_PER_PIXEL * pixels / (ms_per_step / 1e3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -350,13 +419,18 @@ def run_b200(args):
                 "checksum_true_pixels": checksum,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size
+                         # (ncu --set full, profiles/r01b_eval_specialised_ncu_details.txt)
+                         "traffic": 1.86e9 if size == 16384 else None, "peak_kind": peak_kind,
                          "bytes_per_pixel": BYTES_PER_PIXEL, "kernel": "gm_fused (NVRTC-specialised evaluator, V=4 px x U=4 groups per thread)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if zonal is not None:
+            line["zonal"] = zonal
         if world == 1 and not args.profile:
             threads = os.cpu_count() or 1
             rows = min(args.cpu_sample_rows, size)
