@@ -154,9 +154,13 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
         fy = HillArith<T>::div((T)gy, yres);
         fx = HillArith<T>::div((T)gx, xres);
       }
-      const float xx_plus_yy = fx * fx + fy * fy;
-      const float num = sin_alt - cos_alt_zsf * (fy * cos_az - fx * sin_az);
-      const float cang = num * rsqrtf(1.0f + square_zsf * xx_plus_yy);
+      // the shading is tolerance-bound (see above): fused multiply-adds and the hardware
+      // reciprocal square root (argument >= 1, 2^-22 relative error) instead of 16 instructions
+      const float xx_plus_yy = __fmaf_rn(fx, fx, fy * fy);
+      const float num = __fmaf_rn(-cos_alt_zsf, __fmaf_rn(fy, cos_az, -(fx * sin_az)), sin_alt);
+      float inv_len;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_len) : "f"(__fmaf_rn(square_zsf, xx_plus_yy, 1.0f)));
+      const float cang = num * inv_len;
       const int grey = (int)(255.0f * cang);
       const uint8_t out = (cang <= 0.0f) ? (uint8_t)0 : (uint8_t)grey;
       if (writes && r < rows) o[(int64_t)r * W] = out;
@@ -500,6 +504,66 @@ dilate_kernel(const T* __restrict__ src, T* __restrict__ dst, int bands, int H, 
   }
 }
 
+// Tiled version: every source cell is ranked ONCE (rank = 1 + index of the cell's value in
+// `values`, 0 if it is not listed; later values win, so the output is the value of the
+// largest rank in the 7-point cross) into a byte tile in shared memory -- single-byte
+// rasters through a 256-entry table -- and an output cell then takes the maximum of five
+// bytes (plus the two time neighbours, ranked on the fly when there is more than one band).
+constexpr int DL_TX = 128, DL_TY = 16;
+
+template <typename T>
+__device__ __forceinline__ int dilate_rank(T v, const T* vals, int n, const unsigned char* lut) {
+  if constexpr (sizeof(T) == 1) {
+    return lut[(unsigned char)v];
+  } else {
+    for (int i = n - 1; i >= 0; --i)
+      if (v == vals[i]) return i + 1;
+    return 0;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dilate_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, int bands, int H, int W,
+                    const __grid_constant__ DilateValues<T> values) {
+  constexpr int TW = DL_TX + 2, TH = DL_TY + 2;
+  __shared__ unsigned char rank[TH][TW + 2];
+  __shared__ unsigned char lut[256];
+  __shared__ T vals[DILATE_MAX_VALUES];
+  const int SW = W + 2, SH = H + 2;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * DL_TX, y0 = blockIdx.y * DL_TY;
+  if (tid < values.n) vals[tid] = values.v[tid];
+  if (sizeof(T) == 1) {
+    int r = 0;
+    for (int i = 0; i < values.n; ++i)
+      if ((unsigned char)values.v[i] == (unsigned char)tid) r = i + 1;
+    lut[tid] = (unsigned char)r;
+  }
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const T* plane = src + (int64_t)b * in_plane;
+    __syncthreads();
+    for (int i = tid; i < TW * TH; i += 256) {
+      const int ty = i / TW, tx = i - ty * TW;
+      const int gy = min(y0 + ty, SH - 1), gx = min(x0 + tx, SW - 1);   // clamped: never used beyond the array
+      rank[ty][tx] = (unsigned char)dilate_rank<T>(__ldg(plane + (int64_t)gy * SW + gx), vals, values.n, lut);
+    }
+    __syncthreads();
+    for (int i = tid; i < DL_TX * DL_TY; i += 256) {
+      const int ty = i / DL_TX, tx = i - ty * DL_TX;
+      const int x = x0 + tx, y = y0 + ty;
+      if (x >= W || y >= H) continue;
+      int best = max(max(rank[ty + 1][tx], rank[ty + 1][tx + 2]), max(rank[ty][tx + 1], rank[ty + 2][tx + 1]));
+      best = max(best, (int)rank[ty + 1][tx + 1]);
+      const T* c = plane + (int64_t)(y + 1) * SW + (x + 1);
+      if (b > 0) best = max(best, dilate_rank<T>(__ldg(c - in_plane), vals, values.n, lut));
+      if (b + 1 < bands) best = max(best, dilate_rank<T>(__ldg(c + in_plane), vals, values.n, lut));
+      dst[(int64_t)b * out_plane + (int64_t)y * W + x] = best > 0 ? vals[best - 1] : __ldg(c);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Smooth (raster/spatial.py:273-307): scipy.ndimage.gaussian_filter restated
 // ---------------------------------------------------------------------------------
@@ -826,7 +890,7 @@ static int run_dilate(const Staged& in, Staged& out, const void* values, int n_v
   memset(&dv, 0, sizeof(dv));
   dv.n = n_values;
   memcpy(dv.v, values, sizeof(T) * n_values);
-  dilate_kernel<T><<<grid3(W, H, bands, 32, 8), dim3(32, 8), 0, s>>>(
+  dilate_tiled_kernel<T><<<grid3(W, H, bands, DL_TX, DL_TY), 256, 0, s>>>(
       (const T*)in.dev, (T*)out.dev, bands, H, W, dv);
   GM_LAUNCH_CHECK();
   return 0;
