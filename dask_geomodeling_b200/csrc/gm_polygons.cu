@@ -1267,7 +1267,7 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
   __shared__ SelectScratch<unsigned> s_scratch;
   __shared__ int s_wsum[ZS_THREADS / 32];
   __shared__ int s_defer, s_count, s_ncand, s_blo, s_bhi, s_rlo, s_rhi, s_cells, s_nspans, s_below, s_inside;
-  __shared__ unsigned s_kmin, s_kmax, s_khi, s_lowest, s_highest1;
+  __shared__ unsigned s_kmin, s_kmax, s_lowest, s_highest1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int maxx = P.width - 1;
   const float nanf_ = __int_as_float(0x7fc00000);
@@ -1281,7 +1281,7 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
     __syncthreads();   // the previous polygon is done with shared memory
     if (tid == 0) {
       s_defer = 0; s_count = 0; s_ncand = 0; s_cells = 0; s_nspans = 0; s_below = 0; s_inside = 0;
-      s_kmin = ZS_EMPTY; s_kmax = 0u; s_khi = ZS_EMPTY; s_lowest = ZS_EMPTY; s_highest1 = 0u;
+      s_kmin = ZS_EMPTY; s_kmax = 0u; s_lowest = ZS_EMPTY; s_highest1 = 0u;
     }
     if (rows <= 0 || nv == 0) {   // nothing under the polygon
       if (tid == 0) { out[p] = nanf_; area[p] = 0; }
@@ -1492,13 +1492,19 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
     const int shift = max(32 - __clz(bk_hi - bk_lo) - ZS_DIGIT, 0);
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
     int below = 0, inside = 0;
+    const unsigned width = bk_hi - bk_lo;
+    const unsigned hist_at = (unsigned)__cvta_generic_to_shared(s_hist);
     for (int i = tid; i < total / 4; i += ZS_THREADS) {
       const uint4 v = k4[i];
       const unsigned vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        const unsigned rel = vv[j] - bk_lo;
         below += vv[j] < bk_lo ? 1 : 0;
-        if (vv[j] - bk_lo <= bk_hi - bk_lo) { atomicAdd(&s_hist[(vv[j] - bk_lo) >> shift], 1); ++inside; }
+        inside += rel <= width ? 1 : 0;
+        // if (rel <= width) ++s_hist[rel >> shift], as one predicated shared-memory reduction
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], 1;\n\t}"
+                     :: "r"(rel), "r"(width), "r"(hist_at + ((rel >> shift) << 2)) : "memory");
       }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1551,46 +1557,45 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
       if (shift == 0) {
         klo = bk_lo + (unsigned)b_lo;          // one key per bin
         khi = bk_lo + (unsigned)b_hi;
-      } else if (m > ZS_CAND) {
-        block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
       } else {
-        // the keys of bin b_lo (a handful) and the smallest key above that bin
-        unsigned above = ZS_EMPTY;
-        for (int i = tid; i < total / 4; i += ZS_THREADS) {
-          const uint4 v = k4[i];
-          const unsigned vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned d = (vv[j] - bk_lo) >> shift;
-            const bool in = vv[j] - bk_lo <= bk_hi - bk_lo;
-            if (in && d == (unsigned)b_lo) s_cand[atomicAdd(&s_ncand, 1)] = vv[j];
-            else if (vv[j] != ZS_EMPTY && vv[j] >= bk_lo && (!in || d > (unsigned)b_lo)) above = min(above, vv[j]);
-          }
-        }
-        for (int o = 16; o > 0; o >>= 1) above = min(above, __shfl_xor_sync(0xffffffffu, above, o));
-        if (lane == 0 && above != ZS_EMPTY) atomicMin(&s_khi, above);
-        __syncthreads();
+        // the keys of bin b_lo and, when the upper rank falls into a later bin, of that bin
+        // (a handful): its smallest key is the upper neighbour
         const bool together = b_hi == b_lo;
-        const int want_lo = s_rlo, want_hi = together ? s_rhi : s_rlo;
-        if (m <= 32) {
-          // one candidate per lane, ranked against the others
-          if (warp == 0) {
-            const unsigned mine = lane < m ? s_cand[lane] : ZS_EMPTY;
-            int rank = 0;
-            for (int j = 0; j < m; ++j) {
-              const unsigned o = __shfl_sync(0xffffffffu, mine, j);
-              rank += (o < mine) || (o == mine && j < lane);
+        const int m_all = m + (together ? 0 : s_hist[b_hi]);
+        if (m_all > ZS_CAND) {
+          block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
+        } else {
+          for (int i = tid; i < total / 4; i += ZS_THREADS) {
+            const uint4 v = k4[i];
+            const unsigned vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const unsigned rel = vv[j] - bk_lo, d = rel >> shift;
+              if (rel <= width && (d == (unsigned)b_lo || d == (unsigned)b_hi)) s_cand[atomicAdd(&s_ncand, 1)] = vv[j];
             }
-            if (lane < m && rank == want_lo) s_scratch.min_key = mine;
-            if (lane < m && rank == want_hi) s_kmax = mine;
           }
           __syncthreads();
-          klo = s_scratch.min_key;
-          khi = s_kmax;
-        } else {
-          block_select2<unsigned>(s_cand, m, (long long)want_lo, (long long)want_hi, &klo, &khi, s_hist8, &s_scratch);
+          // bin b_hi's keys sort behind bin b_lo's: ranks in the union
+          const int want_lo = s_rlo, want_hi = together ? s_rhi : m;
+          if (m_all <= 32) {
+            // one candidate per lane, ranked against the others
+            if (warp == 0) {
+              const unsigned mine = lane < m_all ? s_cand[lane] : ZS_EMPTY;
+              int rank = 0;
+              for (int j = 0; j < m_all; ++j) {
+                const unsigned o = __shfl_sync(0xffffffffu, mine, j);
+                rank += (o < mine) || (o == mine && j < lane);
+              }
+              if (lane < m_all && rank == want_lo) s_scratch.min_key = mine;
+              if (lane < m_all && rank == want_hi) s_kmax = mine;
+            }
+            __syncthreads();
+            klo = s_scratch.min_key;
+            khi = s_kmax;
+          } else {
+            block_select2<unsigned>(s_cand, m_all, (long long)want_lo, (long long)want_hi, &klo, &khi, s_hist8, &s_scratch);
+          }
         }
-        if (!together) khi = s_khi;
       }
     }
     if (tid == 0) {
