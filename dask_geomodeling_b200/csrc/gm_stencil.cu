@@ -4,6 +4,7 @@
 // writes the cropped (t, H, W).
 #include "gm_common.cuh"
 #include <cfloat>
+#include <cstdlib>
 #include <cmath>
 #include <limits>
 #include <algorithm>
@@ -450,6 +451,195 @@ static int launch_moving_max_fixed(const Staged& in, Staged& out, T nd, int has_
   return 0;
 }
 
+// Register-blocked version for 4-byte rasters: the same three phases, but a thread owns FOUR
+// adjacent columns, so that every shared-memory access is a conflict-free 16-byte one.
+//   phase 2: a thread reads the 4 + 2R source values of its row segment once (4 quads at
+//            size 11) and grows the chord maxima of its four pixels in registers -- one 3-input
+//            maximum per step outwards (FMNMX3) -- storing one quad per chord-width plane;
+//   phase 3: a thread reads one quad per footprint row from the plane of that row's chord
+//            and reduces the 2R + 1 quads with 3-input maxima.
+// Shared-memory traffic per output pixel drops from 136 to 92 bytes and the instruction count
+// from ~70 to ~30 at size 11.
+template <typename T> struct Quad { T v[4]; };
+template <typename T> __device__ __forceinline__ T vmin4(const T (&v)[4]) {
+  const T a = v[0] < v[1] ? v[0] : v[1], b = v[2] < v[3] ? v[2] : v[3];
+  return a < b ? a : b;
+}
+template <typename T> __device__ __forceinline__ Quad<T> lds_quad(const T* p) {
+  Quad<T> q;
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  memcpy(&q, &u, 16);
+  return q;
+}
+template <typename T> __device__ __forceinline__ void sts_quad(T* p, const Quad<T>& q) {
+  uint4 u;
+  memcpy(&u, &q, 16);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+template <typename T, int SIZE, int D>
+__device__ __forceinline__ void chord_quads(const T* w, T (&m)[4], T* chord_row, int plane_stride) {
+  // w[0 .. 4 + 2R): the window of this segment; pixel i's centre is w[R + i]
+  constexpr int R = Disc<SIZE>::R;
+  if constexpr (D <= Disc<SIZE>::wmax()) {
+    if constexpr (D > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = vmax<T>(m[i], vmax<T>(w[R + i - D], w[R + i + D]));
+    }
+    if constexpr (Disc<SIZE>::used(D)) {
+      Quad<T> q;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q.v[i] = m[i];
+      sts_quad<T>(chord_row + Disc<SIZE>::plane_of(D) * plane_stride, q);
+    }
+    chord_quads<T, SIZE, D + 1>(w, m, chord_row, plane_stride);
+  }
+}
+
+template <typename T, int SIZE, int DY>
+__device__ __forceinline__ void disc_quads(const T* chord_px, int plane_stride, T (&best)[4]) {
+  constexpr int R = Disc<SIZE>::R;
+  if constexpr (DY <= R) {
+    constexpr int w = Disc<SIZE>::half_width(DY);
+    if constexpr (w >= 0) {
+      const Quad<T> q = lds_quad<T>(chord_px + Disc<SIZE>::plane_of(w) * plane_stride + (DY + R) * MM2_TX);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) best[i] = vmax<T>(best[i], q.v[i]);
+    }
+    disc_quads<T, SIZE, DY + 1>(chord_px, plane_stride, best);
+  }
+}
+
+template <typename T, int SIZE>
+__global__ void __launch_bounds__(256)
+moving_max_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
+                       int bands, int H, int W, int dst_aligned) {
+  static_assert(sizeof(T) == 4, "quads of four 4-byte cells");
+  extern __shared__ __align__(16) unsigned char mm_smem[];
+  constexpr int R = Disc<SIZE>::R;
+  constexpr int NQ = (4 + 2 * R + 3) / 4;                // quads per segment window
+  constexpr int TW = MM2_TX - 4 + 4 * NQ;                // tile row stride: every window in bounds
+  constexpr int TH = MM2_TY + 2 * R;
+  constexpr int PLANE = TH * MM2_TX;
+  constexpr int SEGS = MM2_TX / 4;
+  T* tile = reinterpret_cast<T*>(mm_smem);               // TH x TW
+  T* chord = tile + TH * TW;                             // n_planes x TH x MM2_TX
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SW = W + 2 * R, SH = H + 2 * R;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int x0 = blockIdx.x * MM2_TX, y0 = blockIdx.y * MM2_TY;
+  const T lowest = Lowest<T>::value();
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const T* plane = src + (int64_t)b * in_plane;
+    __syncthreads();
+    // phase 1: the tile with its halo; tiles that lie inside the array (all but the last
+    // row / column of tiles) skip every bound test
+    if (x0 + TW <= SW && y0 + TH <= SH) {
+      constexpr int ITEMS = TH * TW, PER = (ITEMS + 255) / 256;
+      const T* origin = plane + (int64_t)y0 * SW + x0;
+      T raw[PER];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        const int ty = i / TW, tx = i - ty * TW;
+        raw[k] = i < ITEMS ? __ldg(origin + (int64_t)ty * SW + tx) : lowest;
+      }
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        if (i < ITEMS) tile[i] = (has_nodata && raw[k] == nodata) ? lowest : raw[k];
+      }
+    } else {
+      constexpr int NJ = (TW + 31) / 32;
+      for (int ty = warp; ty < TH; ty += 16) {
+        T raw[2][NJ];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int gy = min(y0 + ty + 8 * h, SH - 1);
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+            raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(x0 + lane + 32 * j, SW - 1));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = ty + 8 * h;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const int tx = lane + 32 * j;
+            const bool inside = y0 + row < SH && x0 + tx < SW;
+            const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? lowest : raw[h][j];
+            if (tx < TW && row < TH) tile[row * TW + tx] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // phase 2: chord maxima of four pixels per thread
+    for (int item = threadIdx.x; item < TH * SEGS; item += 256) {
+      const int ty = item / SEGS, seg = item - ty * SEGS;
+      T w[4 * NQ];
+#pragma unroll
+      for (int k = 0; k < NQ; ++k) {
+        const Quad<T> q = lds_quad<T>(tile + ty * TW + 4 * seg + 4 * k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[4 * k + i] = q.v[i];
+      }
+      T m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) m[i] = w[R + i];
+      chord_quads<T, SIZE, 0>(w, m, chord + ty * MM2_TX + 4 * seg, PLANE);
+    }
+    __syncthreads();
+    // phase 3: the disc = one chord per footprint row
+    for (int item = threadIdx.x; item < MM2_TY * SEGS; item += 256) {
+      const int ty = item / SEGS, seg = item - ty * SEGS;
+      const int y = y0 + ty, x = x0 + 4 * seg;
+      if (y >= H || x >= W) continue;
+      T best[4] = {lowest, lowest, lowest, lowest};
+      disc_quads<T, SIZE, -R>(chord + ty * MM2_TX + 4 * seg, PLANE, best);
+      // restore no data only where the centre was no data and nothing was found (rare:
+      // one test for the quad)
+      if (has_nodata && vmin4(best) == lowest) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (best[i] == lowest && x + i < W &&
+              __ldg(plane + (int64_t)(y + R) * SW + (x + i + R)) == nodata)
+            best[i] = nodata;
+      }
+      T* o = dst + (int64_t)b * out_plane + (int64_t)y * W + x;
+      if (dst_aligned && x + 3 < W) {
+        Quad<T> q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q.v[i] = best[i];
+        uint4 u;
+        memcpy(&u, &q, 16);
+        *reinterpret_cast<uint4*>(o) = u;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x + i < W) o[i] = best[i];
+      }
+    }
+  }
+}
+
+template <typename T, int SIZE>
+static int launch_moving_max_quad(const Staged& in, Staged& out, T nd, int has_nodata, int bands,
+                                  int H, int W, cudaStream_t s) {
+  constexpr int R = Disc<SIZE>::R;
+  constexpr int NQ = (4 + 2 * R + 3) / 4;
+  constexpr int TW = MM2_TX - 4 + 4 * NQ, TH = MM2_TY + 2 * R;
+  const size_t smem = ((size_t)TW * TH + (size_t)Disc<SIZE>::n_planes() * TH * MM2_TX) * sizeof(T);
+  auto kernel = moving_max_quad_kernel<T, SIZE>;
+  if (smem > 48 * 1024)
+    GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int aligned = ((uintptr_t)out.dev % 16 == 0) && (W % 4 == 0);
+  kernel<<<grid3(W, H, bands, MM2_TX, MM2_TY), 256, smem, s>>>((const T*)in.dev, (T*)out.dev, nd,
+                                                               has_nodata, bands, H, W, aligned);
+  GM_LAUNCH_CHECK();
+  return 0;
+}
+
 // 0: launched, 1: error, -1: no compile-time footprint for this dtype / size
 template <typename T>
 static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, int has_nodata,
@@ -457,6 +647,16 @@ static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, i
   if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
                 std::is_same<T, int16_t>::value || std::is_same<T, uint8_t>::value ||
                 std::is_same<T, int32_t>::value) {
+    if constexpr (sizeof(T) == 4) {
+      if (!getenv("GM_MOVING_MAX_SCALAR")) {
+        switch (size) {
+#define GM_CASE(N) case N: return launch_moving_max_quad<T, N>(in, out, nd, has_nodata, bands, H, W, s);
+          GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
+#undef GM_CASE
+          default: break;
+        }
+      }
+    }
     switch (size) {
 #define GM_CASE(N) case N: return launch_moving_max_fixed<T, N>(in, out, nd, has_nodata, bands, H, W, s);
       GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
