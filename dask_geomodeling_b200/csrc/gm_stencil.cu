@@ -102,11 +102,11 @@ template <> __device__ __forceinline__ int16_t shfl_down_any<int16_t>(int16_t v,
 template <> __device__ __forceinline__ uint16_t shfl_down_any<uint16_t>(uint16_t v, int d) { return (uint16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
 template <> __device__ __forceinline__ int64_t shfl_down_any<int64_t>(int64_t v, int d) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, d); }
 
-template <typename T>
+template <typename T, bool EXACT_INVERSE>
 __global__ void __launch_bounds__(32 * HS_WARPS)
 hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
                        T fill, int bands, int H, int W, double xres, double yres,
-                       double inv_xres, double inv_yres, int exact_inverse,
+                       double inv_xres, double inv_yres,
                        float sin_alt, float cos_alt_zsf, float cos_az, float sin_az, float square_zsf) {
   typedef typename HillArith<T>::acc A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,6 +125,7 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
   const bool writes = lane < HS_COLS && x0 + lane < W;
   uint8_t* o = dst + (int64_t)b * out_plane + (int64_t)y0 * W + x0 + lane;
   const int rows = min(HS_ROWS, H - y0);
+  const bool full = rows == HS_ROWS;               // warp-uniform: no row of this strip is clipped
   // Loads are unconditional (row / column clamped into the array) so that a batch of
   // HS_AHEAD rows is in flight before the first value is looked at.
   const int last_row = H + 1;                      // last source row of the band
@@ -135,10 +136,17 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
   A a1 = shfl_down_any<A>(a0, 1), a2 = shfl_down_any<A>(a0, 2);
   A b1 = shfl_down_any<A>(b0, 1), b2 = shfl_down_any<A>(b0, 2);
   const A two = (A)2;
+  const T* next_row = pc + (int64_t)(y0 + 2) * SW;  // walks down with the batches of a full strip
   for (int r0 = 0; r0 < rows; r0 += HS_AHEAD) {
     T next[HS_AHEAD];
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < HS_AHEAD; ++i) next[i] = raw(y0 + r0 + i + 2);
+      for (int i = 0; i < HS_AHEAD; ++i) next[i] = __ldg(next_row + (int64_t)i * SW);
+      next_row += (int64_t)HS_AHEAD * SW;
+    } else {
+#pragma unroll
+      for (int i = 0; i < HS_AHEAD; ++i) next[i] = raw(y0 + r0 + i + 2);
+    }
 #pragma unroll
     for (int i = 0; i < HS_AHEAD; ++i) {
       const int r = r0 + i;
@@ -148,7 +156,7 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
       const A gy = ((((a0 + two * a1) + a2) - c0) - two * c1) - c2;
       const A gx = ((((a0 + two * b0) + c0) - a2) - two * b2) - c2;
       float fy, fx;
-      if (exact_inverse) {  // resolution is a power of two: v * (1 / res) == v / res bit for bit
+      if (EXACT_INVERSE) {  // resolution is a power of two: v * (1 / res) == v / res bit for bit
         fy = HillArith<T>::mul((T)gy, inv_yres);
         fx = HillArith<T>::mul((T)gx, inv_xres);
       } else {
@@ -164,7 +172,7 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
       const float cang = num * inv_len;
       const int grey = (int)(255.0f * cang);
       const uint8_t out = (cang <= 0.0f) ? (uint8_t)0 : (uint8_t)grey;
-      if (writes && r < rows) o[(int64_t)r * W] = out;
+      if (writes && (full || r < rows)) o[(int64_t)r * W] = out;
       a0 = b0; a1 = b1; a2 = b2;
       b0 = c0; b1 = c1; b2 = c2;
     }
@@ -1013,10 +1021,13 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
   const int strips_x = (W + HS_COLS - 1) / HS_COLS, strips_y = (H + HS_ROWS - 1) / HS_ROWS;
   const int64_t strips = (int64_t)bands * strips_x * strips_y;
   const unsigned blocks = (unsigned)((strips + HS_WARPS - 1) / HS_WARPS);
-  hillshade_strip_kernel<T><<<blocks, 32 * HS_WARPS, 0, s>>>(
-      (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,
-      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, exact,
-      (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf));
+#define GM_HS(EXACT)                                                                                \
+  hillshade_strip_kernel<T, EXACT><<<blocks, 32 * HS_WARPS, 0, s>>>(                                \
+      (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
+      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres,                           \
+      (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf))
+  if (exact) GM_HS(true); else GM_HS(false);
+#undef GM_HS
   GM_LAUNCH_CHECK();
   return 0;
 }
