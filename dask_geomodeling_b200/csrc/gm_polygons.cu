@@ -2060,6 +2060,84 @@ static int run_segment_select(const void* values, const int64_t* offsets, int64_
   return rc;
 }
 
+// ---- multi-GPU reduce: partials that stay in HBM between the stripe pass and the all-reduce ----
+// sums[3N] = (count, covered cells, sum) as float64 (counts are exact below 2^53) for ONE
+// sum all-reduce, extremes[2N] = (min, -max) for ONE min all-reduce.
+__global__ void zonal_pack_kernel(const GmZonalPartial* __restrict__ partial, const long long* __restrict__ cells,
+                                  int64_t n, double* __restrict__ sums, double* __restrict__ extremes) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const GmZonalPartial r = partial[p];
+  sums[p] = (double)r.count; sums[n + p] = (double)cells[p]; sums[2 * n + p] = r.sum;
+  extremes[p] = r.vmin; extremes[n + p] = -r.vmax;
+}
+
+__global__ void zonal_unpack_kernel(const double* __restrict__ sums, const double* __restrict__ extremes, int64_t n,
+                                    int stat, float* __restrict__ out, long long* __restrict__ covered) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double count = sums[p];
+  float v = __int_as_float(0x7fc00000);
+  if (count > 0.0) {
+    switch (stat) {
+      case GM_STAT_COUNT: v = (float)count; break;
+      case GM_STAT_SUM: v = (float)sums[2 * n + p]; break;
+      case GM_STAT_MEAN: v = (float)(sums[2 * n + p] / count); break;
+      case GM_STAT_MIN: v = (float)extremes[p]; break;
+      case GM_STAT_MAX: v = (float)(-extremes[n + p]); break;
+      default: break;
+    }
+  }
+  out[p] = v;
+  covered[p] = (long long)sums[n + p];
+}
+
+template <typename T>
+static int run_zonal_partials_device(PolyUpload& u, const Staged& raster, const void* nodata, int has_nodata,
+                                     const float* thresholds, double* sums, double* extremes, cudaStream_t s) {
+  const int64_t np_ = u.dev.n_polygons;
+  if (np_ == 0) return 0;
+  T nd = T(0);
+  if (has_nodata) memcpy(&nd, nodata, sizeof(T));
+  void *darea = nullptr, *dthr = nullptr, *dpartial = nullptr, *dwork = nullptr;
+  auto cleanup = [&]() {
+    void* all[] = {darea, dthr, dpartial, dwork};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+  };
+#define GM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  GM_TRY(cudaMallocAsync(&darea, sizeof(long long) * np_, s));
+  GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
+  GM_TRY(cudaMallocAsync(&dwork, sizeof(int) * (size_t)(np_ + 2), s));
+  GM_TRY(cudaMemsetAsync(dwork, 0, 2 * sizeof(int), s));
+  if (thresholds && upload(&dthr, thresholds, sizeof(float) * np_, s)) { cleanup(); return 1; }
+  const size_t smem_scan = scan_smem(u.dev.cap, PG_WARPS);
+  if (smem_scan > 48 * 1024)
+    GM_TRY(cudaFuncSetAttribute(zonal_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
+  const int vec = 16 / (int)sizeof(T);
+  const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (uintptr_t)(vec - 1));
+  const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
+                          (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
+  int64_t wblocks = (np_ + ZW_WARPS - 1) / ZW_WARPS;
+  if (wblocks > (int64_t)sm_count() * ZW_MIN_BLOCKS) wblocks = (int64_t)sm_count() * ZW_MIN_BLOCKS;
+  zonal_reduce_warp_kernel<T, ZW_ALL><<<(unsigned)wblocks, 32 * ZW_WARPS, 0, s>>>(
+      u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, mis, edge_scalar,
+      (GmZonalPartial*)dpartial, (long long*)darea, (int*)dwork);
+  GM_TRY(cudaGetLastError());
+  count_launch();
+  zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
+      u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial,
+      (long long*)darea, (const int*)dwork);
+  GM_TRY(cudaGetLastError());
+  count_launch();
+  zonal_pack_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
+      (const GmZonalPartial*)dpartial, (const long long*)darea, np_, sums, extremes);
+  GM_TRY(cudaGetLastError());
+  count_launch();
+#undef GM_TRY
+  cleanup();
+  return 0;
+}
+
 }  // namespace gm
 
 using namespace gm;
@@ -2215,4 +2293,52 @@ extern "C" int gm_zonal_stats(const GmArray* raster, const void* nodata, int has
   u.release();
   in.release();
   return rc;
+}
+
+extern "C" int gm_zonal_partials_device(const GmArray* raster, const void* nodata, int has_nodata,
+                                        const GmPolygons* polys, const double geo[6],
+                                        const float* thresholds, int64_t row_begin, int64_t row_end,
+                                        double* sums, double* extremes, void* stream) {
+  if (ensure_init()) return 1;
+  if (!raster || !polys || !sums || !extremes) return fail("gm_zonal_partials_device: null argument");
+  if (raster->shape[0] != 1) return fail("gm_zonal_partials_device: one frame per call");
+  cudaStream_t s = resolve_stream(stream);
+  const int H = (int)raster->shape[1], W = (int)raster->shape[2];
+  if (row_begin < 0) row_begin = 0;
+  if (row_end > H || row_end <= 0) row_end = H;
+  Staged in;
+  PolyUpload u;
+  int rc = in.open_input(*raster, s);
+  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s);
+  if (!rc) {
+    GM_RASTER_DISPATCH(raster->dtype,
+                       run_zonal_partials_device<T>(u, in, nodata, has_nodata, thresholds, sums, extremes, s),
+                       "gm_zonal_partials_device")
+  }
+  if (!rc) rc = check_overflow(u, s);
+  u.release();
+  in.release();
+  return rc;
+}
+
+extern "C" int gm_zonal_finalize_device(const double* sums, const double* extremes, int64_t n_polygons,
+                                        int stat, float* out, int64_t* covered, void* stream) {
+  if (ensure_init()) return 1;
+  if (!sums || !extremes || !out || !covered) return fail("gm_zonal_finalize_device: null argument");
+  if (n_polygons == 0) return 0;
+  cudaStream_t s = resolve_stream(stream);
+  void *dout = nullptr, *dcov = nullptr;
+  GM_CUDA(cudaMallocAsync(&dout, sizeof(float) * n_polygons, s));
+  GM_CUDA(cudaMallocAsync(&dcov, sizeof(long long) * n_polygons, s));
+  zonal_unpack_kernel<<<(unsigned)((n_polygons + 255) / 256), 256, 0, s>>>(sums, extremes, n_polygons, stat,
+                                                                          (float*)dout, (long long*)dcov);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) count_launch();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(float) * n_polygons, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(covered, dcov, sizeof(long long) * n_polygons, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(dout, s);
+  cudaFreeAsync(dcov, s);
+  if (e != cudaSuccess) return fail(std::string("gm_zonal_finalize_device: ") + cudaGetErrorString(e));
+  return 0;
 }

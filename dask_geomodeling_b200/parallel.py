@@ -317,11 +317,16 @@ def zonal_striped(geometries, local, no_data_value, bbox, height, rows, statisti
         agg, no_cells = aggregate_polygons(soup, local, no_data_value, stripe_bbox, None, threshold_values,
                                            statistic, percentile)
         return agg[0], no_cells
+    order_stat = statistic in ("median", "percentile")
+    if not order_stat and n > 0 and _dist().get_backend(group) == "nccl" and _native.is_device(local):
+        return _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, threshold_values,
+                                     group, r1 > r0)
+    if order_stat and n > 0:
+        return _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statistic, percentile,
+                                    threshold_values, group)
     partial = np.zeros(n, dtype=PARTIAL_DTYPE)
     partial["vmin"], partial["vmax"] = np.finfo(np.float64).max, -np.finfo(np.float64).max
     covered = np.zeros(n, dtype=np.int64)
-    order_stat = statistic in ("median", "percentile")
-    counts = values = None
     if r1 > r0 and n > 0:
         _, h, w = local.shape
         geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, h, w))
@@ -337,18 +342,276 @@ def zonal_striped(geometries, local, no_data_value, bbox, height, rows, statisti
             ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
             _STAT_CODES["sum"], 0.0, None if thresholds is None else thresholds.ctypes.data, 0, h,
             None, covered.ctypes.data, partial.ctypes.data, _native.current_stream()))
-        if order_stat:
-            counts, values = _native.zonal_values(desc, nodata_ptr, int(s is not None), polys, geo,
-                                                  thresholds, partial["count"])
     partial, covered = allreduce_partials(partial, covered, group)
-    no_cells = np.nonzero(covered == 0)[0].tolist()
-    if not order_stat:
-        return finalize_partials(partial, statistic), no_cells
+    return finalize_partials(partial, statistic), np.nonzero(covered == 0)[0].tolist()
+
+
+def _zonal_order_by_exchange(soup, local, no_data_value, stripe_bbox, has_rows, statistic, percentile,
+                             threshold_values, group):
+    """Median / percentile of polygons that reach beyond a neighbouring stripe: every rank
+    extracts the active values of its rows (gm_zonal_values), the segments are routed to the
+    polygons' owner ranks ``p % world`` and selected there (gm_segment_order_stat)."""
+    import ctypes
+
+    from . import _native, utils
+    from .geometry.aggregate import _STAT_CODES, _frame_descriptor
+    from .raster._program import sentinel
+
+    n = soup.n_polygons
+    partial = np.zeros(n, dtype=PARTIAL_DTYPE)
+    covered = np.zeros(n, dtype=np.int64)
+    counts = values = None
+    if has_rows and n > 0:
+        _, h, w = local.shape
+        geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, h, w))
+        s = sentinel(local.dtype, no_data_value)
+        holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, local.dtype)
+        thresholds = None
+        if threshold_values is not None:
+            thresholds = np.ascontiguousarray(threshold_values, dtype=np.float32)
+        polys = soup.as_struct()
+        desc = _frame_descriptor(local, 0)
+        _native.check(_native.lib().gm_zonal_stats(
+            ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
+            _STAT_CODES["sum"], 0.0, None if thresholds is None else thresholds.ctypes.data, 0, h,
+            None, covered.ctypes.data, partial.ctypes.data, _native.current_stream()))
+        counts, values = _native.zonal_values(desc, nodata_ptr, int(s is not None), polys, geo,
+                                              thresholds, partial["count"])
     if counts is None:
-        counts, values = np.zeros(n, dtype=np.int64), np.zeros(0, dtype=np.asarray(local[:0]).dtype if not _native.is_device(local) else local.dtype)
+        counts = np.zeros(n, dtype=np.int64)
+        values = np.zeros(0, dtype=local.dtype)
     owned, offsets, merged = exchange_segments(counts, values, group)
     mine = segment_order_statistic(merged, offsets, statistic, percentile)
-    return _gather_owned(mine, owned, n, group), no_cells
+    return _gather_owned(mine, owned, n, group)
+
+
+def _polygon_rows(soup, bbox, height):
+    """(top, bottom) raster rows of the full grid that every polygon can touch, one row of
+    slack either side; polygons without vertices get (height, -1).  Cached on the soup."""
+    key = (tuple(bbox), int(height))
+    cached = getattr(soup, "_row_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    n = soup.n_polygons
+    y1, y2 = bbox[1], bbox[3]
+    dy = (y2 - y1) / height
+    starts = soup.ring_offsets[soup.poly_offsets[:-1]]
+    ends = soup.ring_offsets[soup.poly_offsets[1:]]
+    top = np.full(n, height, dtype=np.int64)
+    bottom = np.full(n, -1, dtype=np.int64)
+    filled = np.nonzero(ends > starts)[0]
+    if len(filled):
+        py = (y2 - soup.xy[:, 1]) / dy
+        top[filled] = np.floor(np.minimum.reduceat(py, starts[filled])).astype(np.int64) - 1
+        bottom[filled] = np.floor(np.maximum.reduceat(py, starts[filled])).astype(np.int64) + 1
+    soup._row_cache = (key, (top, bottom))
+    return top, bottom
+
+
+def _stripe_ownership(soup, bbox, height, world):
+    """Which rank selects which polygon when the raster is cut in `world` row stripes (cached
+    on the soup): owner = the stripe holding the polygon's first row; `near` polygons cross
+    into the next stripe only, `far` ones reach beyond it; per rank the rows it needs from
+    its southern neighbour (`halo`) and how many of its own last rows its crossers span."""
+    key = (tuple(bbox), int(height), int(world))
+    cached = getattr(soup, "_owner_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    stops = np.array([b[1] for b in stripe_rows(height, world)], dtype=np.int64)
+    top, bottom = _polygon_rows(soup, bbox, height)
+    top_c, bottom_c = np.clip(top, 0, height - 1), np.clip(bottom, 0, height - 1)
+    outside = (bottom < 0) | (top > height - 1)
+    owner = np.searchsorted(stops, top_c, side="right")
+    owner[outside] = 0
+    crosses = ~outside & (bottom_c >= stops[owner])
+    next_stop = stops[np.minimum(owner + 1, world - 1)]
+    far = crosses & ((owner == world - 1) | (bottom_c >= next_stop))
+    near = crosses & ~far
+    halo = np.zeros(world, dtype=np.int64)
+    keep = np.zeros(world, dtype=np.int64)
+    if near.any():
+        np.maximum.at(halo, owner[near], bottom_c[near] + 1 - stops[owner[near]])
+        np.maximum.at(keep, owner[near], stops[owner[near]] - top_c[near])
+    result = (owner, near, far, crosses, halo, keep)
+    soup._owner_cache = (key, result)
+    return result
+
+
+def _as_tensor(local):
+    """numpy / DeviceArray / torch tensor -> torch tensor sharing the memory."""
+    import torch
+
+    from . import _native
+
+    if hasattr(local, "data_ptr"):
+        return local
+    if _native.is_device(local):
+        owner = local
+        while isinstance(owner, _native.DeviceArray):
+            if hasattr(owner._owner, "data_ptr"):
+                return owner._owner.reshape(local.shape)
+            if owner._owner is None:
+                break
+            owner = owner._owner
+
+        class _View(object):
+            __cuda_array_interface__ = {"shape": local.shape, "typestr": local.dtype.str,
+                                        "data": (local.ptr, False), "version": 2}
+
+        view = torch.as_tensor(_View(), device="cuda")
+        view._keepalive = local
+        return view
+    return torch.from_numpy(np.ascontiguousarray(local))
+
+
+def _order_stat_call(soup, payload, no_data_value, bbox, threshold_values, statistic, percentile):
+    """gm_zonal_stats median / percentile of ALL polygons over one raster: (out, covered)."""
+    import ctypes
+
+    from . import _native, utils
+    from .geometry.aggregate import _STAT_CODES, _frame_descriptor
+    from .raster._program import sentinel
+
+    n = soup.n_polygons
+    _, h, w = payload.shape
+    geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(bbox, h, w))
+    s = sentinel(payload.dtype, no_data_value)
+    holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, payload.dtype)
+    thresholds = None
+    if threshold_values is not None:
+        thresholds = np.ascontiguousarray(threshold_values, dtype=np.float32)
+    polys = soup.as_struct()
+    if not _native.is_device(payload):
+        payload = np.ascontiguousarray(payload)
+    desc = _frame_descriptor(payload, 0)
+    out = _native.pinned_empty((n,), np.float32)
+    covered = _native.pinned_empty((n,), np.int64)
+    covered[:] = 0
+    _native.check(_native.lib().gm_zonal_stats(
+        ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
+        _STAT_CODES[statistic], float(percentile or 0.0),
+        None if thresholds is None else thresholds.ctypes.data, 0, h,
+        out.ctypes.data, covered.ctypes.data, None, _native.current_stream()))
+    return out, covered
+
+
+def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statistic, percentile,
+                         threshold_values, group):
+    """Median / percentile over a raster sharded in row stripes.
+
+    Every polygon is OWNED by the rank whose stripe holds its first row.  A polygon that lies
+    inside one stripe is selected there by the single-GPU kernel; one that crosses into the
+    next stripe is selected by its owner on a boundary strip = the owner's last rows + the
+    rows it needs from its southern neighbour (one ncclSend/ncclRecv of a few hundred rows).
+    Only polygons that reach beyond the neighbouring stripe go through the value exchange
+    (`_zonal_order_by_exchange`).  The owners' results are all-gathered."""
+    import torch
+
+    rank, world = _world(group)
+    dist = _dist()
+    n = soup.n_polygons
+    r0, r1 = rows
+    x1, y1, x2, y2 = bbox
+    dy = (y2 - y1) / height
+    owner, near, far, crosses, halo, keep = _stripe_ownership(soup, bbox, height, world)
+    tensor = _as_tensor(local) if r1 > r0 else None
+    stripe_bbox = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
+    out = np.full(n, np.nan, dtype=np.float32)
+    covered = np.zeros(n, dtype=np.int64)
+    if r1 > r0:
+        got, cov = _order_stat_call(soup, local, no_data_value, stripe_bbox, threshold_values, statistic, percentile)
+        mine = (owner == rank) & ~crosses
+        out[mine] = got[mine]
+        covered[:] = cov
+    # boundary rows: my first rows go north, the southern neighbour's first rows come here
+    # (NCCL moves device memory, gloo host memory; the strip is assembled next to the stripe)
+    link = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    ops, recv = [], None
+    if rank > 0 and halo[rank - 1] > 0:
+        send = tensor[:, :int(halo[rank - 1])].to(link).contiguous()
+        ops.append(dist.P2POp(dist.isend, send, rank - 1, group))
+    if rank < world - 1 and halo[rank] > 0:
+        recv = torch.empty((1, int(halo[rank]), tensor.shape[2]), dtype=tensor.dtype, device=link)
+        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    if recv is not None:
+        k = int(keep[rank])
+        strip = torch.cat([tensor[:, r1 - r0 - k:], recv.to(tensor.device)], dim=1).contiguous()
+        strip_bbox = (x1, y2 - (r1 + int(halo[rank])) * dy, x2, y2 - (r1 - k) * dy)
+        if strip.is_cuda:
+            torch.cuda.current_stream().synchronize()   # the strip is complete before the library reads it
+        got, _ = _order_stat_call(soup, _as_payload(strip), no_data_value, strip_bbox, threshold_values,
+                                  statistic, percentile)
+        mine = (owner == rank) & near
+        out[mine] = got[mine]
+    # owners publish their results; covered cells add up over the stripes
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    gathered = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(out).to(dev), group=group)
+    gathered = torch.stack(gathered).cpu().numpy()
+    result = gathered[owner, np.arange(n)]
+    cov = torch.from_numpy(covered).to(dev)
+    dist.all_reduce(cov, op=dist.ReduceOp.SUM, group=group)
+    covered = cov.cpu().numpy()
+    if far.any():   # same on every rank: the collectives inside line up
+        ids = np.nonzero(far)[0]
+        sub = soup.subset(ids)
+        sub_thresholds = None if threshold_values is None else np.asarray(threshold_values)[ids]
+        result[ids] = _zonal_order_by_exchange(sub, local, no_data_value, stripe_bbox, r1 > r0, statistic,
+                                               percentile, sub_thresholds, group)
+    return result, np.nonzero(covered == 0)[0].tolist()
+
+
+def _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, threshold_values, group, has_rows):
+    """count / sum / mean / min / max of a striped raster with everything but the final N
+    results in HBM: stripe partials (gm_zonal_partials_device), one SUM and one MIN
+    all-reduce over NVLink, statistic + download (gm_zonal_finalize_device)."""
+    import ctypes
+
+    import torch
+
+    from . import _native, utils
+    from .geometry.aggregate import _STAT_CODES, _frame_descriptor
+    from .raster._program import sentinel
+
+    dist = _dist()
+    n = soup.n_polygons
+    lib = _native.lib()
+    stream = _native.current_stream()
+    torch_stream = torch.cuda.current_stream().cuda_stream
+    same_stream = stream is not None and int(stream) == int(torch_stream)
+    big = float(np.finfo(np.float64).max)
+    sums = torch.zeros(3 * n, dtype=torch.float64, device="cuda")
+    extremes = torch.full((2 * n,), big, dtype=torch.float64, device="cuda")
+    if has_rows:
+        _, h, w = local.shape
+        geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, h, w))
+        s = sentinel(local.dtype, no_data_value)
+        holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, local.dtype)
+        thresholds = None
+        if threshold_values is not None:
+            thresholds = np.ascontiguousarray(threshold_values, dtype=np.float32)
+        polys = soup.as_struct()
+        desc = _frame_descriptor(local, 0)
+        if not same_stream:
+            torch.cuda.current_stream().synchronize()   # the tensors above are ready
+        _native.check(lib.gm_zonal_partials_device(
+            ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
+            None if thresholds is None else thresholds.ctypes.data, 0, h,
+            sums.data_ptr(), extremes.data_ptr(), stream))
+        if not same_stream:
+            _native.synchronize()
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(extremes, op=dist.ReduceOp.MIN, group=group)
+    if not same_stream:
+        torch.cuda.current_stream().synchronize()
+    out = _native.pinned_empty((n,), np.float32)
+    covered = _native.pinned_empty((n,), np.int64)
+    _native.check(lib.gm_zonal_finalize_device(sums.data_ptr(), extremes.data_ptr(), n, _STAT_CODES[statistic],
+                                               out.ctypes.data, covered.ctypes.data, stream))
+    return out, np.nonzero(covered == 0)[0].tolist()
 
 
 # ---------------------------------------------------------------------------

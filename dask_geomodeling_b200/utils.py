@@ -498,6 +498,21 @@ class PolygonSoup(object):
     def n_polygons(self):
         return len(self.poly_offsets) - 1
 
+    def subset(self, ids):
+        """The soup of the polygons `ids` (in that order)."""
+        ids = np.asarray(ids, dtype=np.int64)
+        sub = PolygonSoup([])
+        ring_a, ring_b = self.poly_offsets[ids], self.poly_offsets[ids + 1]
+        rings = np.concatenate([np.arange(a, b) for a, b in zip(ring_a, ring_b)]) if len(ids) else np.zeros(0, np.int64)
+        rings = rings.astype(np.int64)
+        v_a, v_b = self.ring_offsets[rings], self.ring_offsets[rings + 1]
+        sub.xy = np.ascontiguousarray(
+            np.concatenate([self.xy[a:b] for a, b in zip(v_a, v_b)]) if len(rings) else np.zeros((0, 2)),
+            dtype=np.float64)
+        sub.ring_offsets = np.concatenate([[0], np.cumsum(v_b - v_a)]).astype(np.int64)
+        sub.poly_offsets = np.concatenate([[0], np.cumsum(ring_b - ring_a)]).astype(np.int64)
+        return sub
+
     def as_struct(self):
         from ._native import GmPolygons
 

@@ -105,7 +105,9 @@ def test_stencils_with_halo_exchange():
     spawn(_stencil_worker)
 
 
-def _zonal_worker(rank, world):
+def _zonal_worker(rank, world, on_device=False):
+    import torch
+
     from dask_geomodeling_b200 import geometry, parallel, utils, workloads
 
     rng = np.random.default_rng(21)
@@ -118,13 +120,15 @@ def _zonal_worker(rank, world):
         cx, cy = rng.uniform(0, w), rng.uniform(0, h)
         k = int(rng.integers(3, 11))
         ang = np.sort(rng.uniform(0, 2 * np.pi, k))
-        rad = rng.uniform(3, 60)
+        rad = rng.uniform(3, 60)   # up to 120 rows: crosses one stripe boundary, or two with three ranks
         ring = np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], axis=1)
         polys.append(utils.Polygon(np.round(ring, 3) + 0.0137))
     polys.append(utils.Polygon([(5.01, 5.01), (5.02, 5.01), (5.02, 5.02)]))  # covers no cell centre
     bbox = (0, 0, w, h)
     r0, r1 = parallel.stripe_rows(h, world)[rank]
     local = np.ascontiguousarray(frame[:, r0:r1])
+    if on_device:   # stripes resident in HBM: partials and boundary rows never touch the host
+        local = torch.from_numpy(local).cuda()
     for stat, q in (("mean", None), ("max", None), ("count", None), ("sum", None), ("min", None),
                     ("median", None), ("percentile", 90.0), ("percentile", 12.5)):
         expected, expected_no_cells = geometry.aggregate.aggregate_polygons(
@@ -137,5 +141,18 @@ def _zonal_worker(rank, world):
             np.testing.assert_array_equal(got, expected[0])
 
 
+def _zonal_worker_device(rank, world):
+    _zonal_worker(rank, world, on_device=True)
+
+
 def test_zonal_statistics_in_stripes():
     spawn(_zonal_worker)
+
+
+def test_zonal_statistics_in_stripes_resident():
+    spawn(_zonal_worker_device)
+
+
+def test_zonal_statistics_in_three_stripes():
+    # polygons that reach beyond the neighbouring stripe take the value-exchange path
+    spawn(_zonal_worker, world=3)
