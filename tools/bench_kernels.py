@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default="")
+    ap.add_argument("--temporal-frames", type=int, default=64, help="365 = cfg5")
+    ap.add_argument("--temporal-size", type=int, default=4096, help="8192 = cfg5 (98 GB of float32 at 365 frames)")
+    ap.add_argument("--temporal-stats", default="sum,max,mean,median")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
 
@@ -104,14 +107,16 @@ def main():
 
     # ---- temporal (cfg5 shape scaled: 64 x 4096 x 4096) ------------------------------------
     if not only or any(o.startswith(("temporal", "cumulative")) for o in only):
-        T, m = 64, int(4096 * args.scale)
-        stack = torch.rand(T, m, m, device="cuda") * 100
-        stack[torch.rand(T, m, m, device="cuda") < 0.03] = nodata
+        T, m = args.temporal_frames, int(args.temporal_size * args.scale)
+        stack = torch.empty(T, m, m, device="cuda")
+        for t in range(T):   # frame by frame: no second stack-sized temporary
+            stack[t].uniform_(0, 100)
+            stack[t][torch.rand(m, m, device="cuda") < 0.03] = nodata
         sd = wrap(stack)
         from datetime import datetime, timedelta
 
         times = [datetime(2000, 1, 1) + timedelta(days=i) for i in range(T)]
-        for stat in ("sum", "max", "mean", "median"):
+        for stat in [x for x in args.temporal_stats.split(",") if x]:
             out_dtype = "f4"
             kwargs = dict(mode="vals", start=times[-1], stop=None, frequency=None, timezone=None,
                           closed=None, label=None, dtype=out_dtype, statistic=stat)
