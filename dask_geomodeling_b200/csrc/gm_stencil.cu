@@ -877,27 +877,48 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
   for (int b = blockIdx.z; b < bands; b += gridDim.z) {
     const T* plane = src + (int64_t)b * in_plane;
     __syncthreads();
-    // unconditional (clamped) loads, two tile rows = eight requests per thread per round
-    for (int ty = warp; ty < TH; ty += 16) {
-      T raw[2][SMF_TW / 32];
+    // source tile.  Tiles whose staged window lies inside the array (all but the outermost
+    // ring of tiles) need no clamping and no inside test: straight rows, pointer steps
+    const int wy0 = y0 + my - L, wx0 = x0 + mx - L;          // window origin in the source
+    if (wy0 >= 0 && wx0 >= 0 && wy0 + TH <= SH && wx0 + SMF_TW <= SW) {
+      const T* p = plane + (int64_t)(wy0 + warp) * SW + wx0 + lane;
+      constexpr int ROUNDS = (TH + 7) / 8;
+#pragma unroll 2
+      for (int k = 0; k < ROUNDS; ++k) {
+        const int row = warp + 8 * k;
+        T raw[SMF_TW / 32];
+        if (row < TH) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int gy = min(max(y0 + my - L + ty + 8 * h, 0), SH - 1);
+          for (int j = 0; j < SMF_TW / 32; ++j) raw[j] = __ldg(p + 32 * j);
 #pragma unroll
-        for (int j = 0; j < SMF_TW / 32; ++j)
-          raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(max(x0 + mx - L + lane + 32 * j, 0), SW - 1));
+          for (int j = 0; j < SMF_TW / 32; ++j)
+            tile[row * SMF_PITCH + lane + 32 * j] = (has_nodata && raw[j] == nodata) ? fill : raw[j];
+        }
+        p += (int64_t)8 * SW;
       }
+    } else {
+      // unconditional (clamped) loads, two tile rows = eight requests per thread per round
+      for (int ty = warp; ty < TH; ty += 16) {
+        T raw[2][SMF_TW / 32];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = ty + 8 * h;
-        const int gy = y0 + my - L + row;
+        for (int h = 0; h < 2; ++h) {
+          const int gy = min(max(y0 + my - L + ty + 8 * h, 0), SH - 1);
 #pragma unroll
-        for (int j = 0; j < SMF_TW / 32; ++j) {
-          const int tx = lane + 32 * j;
-          const int gx = x0 + mx - L + tx;
-          const bool inside = gy >= 0 && gy < SH && gx >= 0 && gx < SW;
-          const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? fill : raw[h][j];
-          if (row < TH) tile[row * SMF_PITCH + tx] = v;
+          for (int j = 0; j < SMF_TW / 32; ++j)
+            raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(max(x0 + mx - L + lane + 32 * j, 0), SW - 1));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = ty + 8 * h;
+          const int gy = y0 + my - L + row;
+#pragma unroll
+          for (int j = 0; j < SMF_TW / 32; ++j) {
+            const int tx = lane + 32 * j;
+            const int gx = x0 + mx - L + tx;
+            const bool inside = gy >= 0 && gy < SH && gx >= 0 && gx < SW;
+            const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? fill : raw[h][j];
+            if (row < TH) tile[row * SMF_PITCH + tx] = v;
+          }
         }
       }
     }
@@ -938,17 +959,28 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
       }
     }
     __syncthreads();
-    for (int ty = warp; ty < SMF_TY; ty += 8) {
-      const int y = y0 + ty;
-      if (y >= H) break;
-      for (int tx = lane; tx < TX; tx += 32) {
-        const int x = x0 + tx;
-        if (x < W) dst[(int64_t)b * out_plane + (int64_t)y * W + x] = stage[ty * TX + tx];
+    if (x0 + TX <= W && y0 + SMF_TY <= H) {   // the tile's outputs lie inside the array
+      T* o = dst + (int64_t)b * out_plane + (int64_t)(y0 + warp) * W + x0 + lane;
+#pragma unroll
+      for (int k = 0; k < SMF_TY / 8; ++k) {
+        const T* st = stage + (warp + 8 * k) * TX + lane;
+#pragma unroll
+        for (int j = 0; j < (TX + 31) / 32; ++j)
+          if (lane + 32 * j < TX) o[32 * j] = st[32 * j];
+        o += (int64_t)8 * W;
+      }
+    } else {
+      for (int ty = warp; ty < SMF_TY; ty += 8) {
+        const int y = y0 + ty;
+        if (y >= H) break;
+        for (int tx = lane; tx < TX; tx += 32) {
+          const int x = x0 + tx;
+          if (x < W) dst[(int64_t)b * out_plane + (int64_t)y * W + x] = stage[ty * TX + tx];
+        }
       }
     }
   }
 }
-
 template <typename T, int L>
 static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
                               int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,

@@ -101,10 +101,12 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     polys = soup.as_struct()
     geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(agg_bbox, height, width))
     n = soup.n_polygons
-    agg = np.full((depth, n), np.nan, dtype="f4")
     # page-locked result buffers: the library's device-to-host copies are then plain DMA
+    # (one row per frame; the library writes every entry of `out` and `covered`)
+    agg = _native.pinned_empty((depth, n), np.float32)
     covered = _native.pinned_empty((n,), np.int64)
-    covered[:] = 0
+    if n == 0 or depth == 0:
+        covered[:] = 0
     s = sentinel(values.dtype, no_data_value)
     holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, values.dtype)
     thresholds = None
@@ -115,13 +117,12 @@ def aggregate_polygons(geometries, values, no_data_value, agg_bbox, agg_srs, thr
     lib = _native.lib()
     for frame in range(depth):
         desc = _frame_descriptor(values, frame)
-        out = _native.pinned_empty((n,), np.float32)
+        out = agg[frame]
         _native.check(lib.gm_zonal_stats(
             ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
             _STAT_CODES[statistic], float(percentile or 0.0),
             None if thresholds is None else thresholds.ctypes.data, 0, height,
             out.ctypes.data, covered.ctypes.data, None, _native.current_stream()))
-        agg[frame] = out
     return agg, np.nonzero(covered == 0)[0].tolist()
 
 
