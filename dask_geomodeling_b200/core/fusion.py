@@ -232,6 +232,41 @@ def streamed_fused_process(plan, *sources):
     return {"values": out, "no_data_value": results[0].nodata}
 
 
+# Programs compiled for a fused group, keyed by the group's structure (task names are block
+# tokens, so a view asked again -- another tile, another time -- finds its program here;
+# lowering an expression costs about as much as launching it on a 1024 x 1024 tile).
+_compiled_plans = {}
+
+
+def _freeze(value):
+    import numpy as np
+
+    if isinstance(value, np.ndarray):
+        return ("ndarray", value.shape, value.dtype.str, value.tobytes())
+    if isinstance(value, dict):
+        return tuple(sorted((k, _freeze(v)) for k, v in value.items()))
+    if isinstance(value, (list, tuple)):
+        return tuple(_freeze(v) for v in value)
+    if isinstance(value, float) and value != value:
+        return ("nan",)
+    hash(value)
+    return (type(value).__name__, value)
+
+
+def _plan_key(plan, leaves):
+    """Hashable identity of (expression, leaf dtypes / no data); None when some literal of
+    the plan cannot be hashed."""
+    try:
+        nodes = tuple(
+            (name, getattr(func, "__module__", ""), getattr(func, "__qualname__", repr(func)),
+             tuple((kind, _freeze(value)) for kind, value in spec))
+            for name, (func, spec) in sorted(plan["nodes"].items()))
+        types = tuple((str(v.dtype), _freeze(nd)) for v, nd in leaves)
+        return (plan["root"], nodes, types)
+    except TypeError:
+        return None
+
+
 def _payload_is_raster(data):
     return isinstance(data, dict) and "values" in data
 
@@ -246,9 +281,17 @@ def fused_process(plan, *leaf_data):
     nodes = plan["nodes"]
     if all(_payload_is_raster(d) for d in leaf_data):
         try:
-            root = build_expression(plan)
             leaves = [(d["values"], d.get("no_data_value")) for d in leaf_data]
-            (values, dtype, nodata), = _program.evaluate([root], leaves, _state.keep_on_device())
+            key = _plan_key(plan, leaves)
+            compiled = _compiled_plans.get(key) if key is not None else None
+            if compiled is None:
+                compiled = _program.compile_expression(
+                    [build_expression(plan)], [(v.dtype, nd) for v, nd in leaves])
+                if key is not None:
+                    if len(_compiled_plans) >= 256:
+                        _compiled_plans.pop(next(iter(_compiled_plans)))
+                    _compiled_plans[key] = compiled
+            (values, dtype, nodata), = _program.evaluate(None, leaves, _state.keep_on_device(), compiled)
             return {"values": values, "no_data_value": nodata}
         except _program.FusionLimit:
             pass  # too large for one program: evaluate block by block below

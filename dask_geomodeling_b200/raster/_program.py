@@ -768,10 +768,11 @@ def run_program(prog, inputs, out_dtypes, shape, keep_on_device):
     return outputs
 
 
-def evaluate(roots, leaves, keep_on_device=False):
+def evaluate(roots, leaves, keep_on_device=False, compiled=None):
     """Evaluate expression roots over ``leaves`` = [(values, no_data_value), ...].
 
-    Returns [(values, dtype, no_data_value), ...] per root.
+    Returns [(values, dtype, no_data_value), ...] per root.  ``compiled`` = the result of an
+    earlier ``compile_expression`` for the same roots and leaf types (see core/fusion.py).
     """
     shapes = [tuple(v.shape) for v, _ in leaves]
     shape = shapes[0]
@@ -779,7 +780,9 @@ def evaluate(roots, leaves, keep_on_device=False):
     if any(s != shape for s in shapes):
         shape = np.broadcast_shapes(*shapes)
         arrays = [np.ascontiguousarray(np.broadcast_to(np.asarray(a), shape)) for a in arrays]
-    prog, comp, results = compile_expression(roots, [(v.dtype, nd) for v, nd in leaves])
+    if compiled is None:
+        compiled = compile_expression(roots, [(v.dtype, nd) for v, nd in leaves])
+    prog, comp, results = compiled
     outs = run_program(prog, arrays, [t.dtype for t in results], shape, keep_on_device)
     del comp  # tables stay alive until the (synchronous) upload inside the call is done
     return [(o, t.dtype, t.nodata) for o, t in zip(outs, results)]
