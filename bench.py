@@ -233,12 +233,40 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_zonal_throughput(size=4096, grid=32, statistic="mean", q=None):
+    """The reference's aggregate_polygons (geometry/aggregate.py:113-203) as the oracle restates
+    it: bucketize the polygons into sets of disjoint boxes, burn one label raster per bucket
+    (GDAL fill rule, oracle/polyfill.c) and reduce with scipy.ndimage labelled statistics.
+    One thread, like the reference's process function.  Returns (Gpixel/s, seconds)."""
+    from dask_geomodeling_b200 import workloads
+    from dask_geomodeling_b200.geometry.aggregate import bucketize
+    from oracle import polyfill
+    from oracle import raster as R
+
+    rng = np.random.default_rng(11)
+    frame = rng.uniform(0, 100, (size, size)).astype(np.float32)
+    frame[rng.random((size, size)) < 0.02] = workloads.F32_MAX
+    rings = workloads.cfg4_rings(size, grid)
+    bbox = (0, 0, size, size)
+    t0 = time.perf_counter()
+    boxes = [(r[:, 0].min(), r[:, 1].min(), r[:, 0].max(), r[:, 1].max()) for r in rings]
+    label_sets = []
+    for ids in bucketize(boxes):
+        labels = polyfill.burn_index([[rings[i]] for i in ids], bbox, size, size)
+        labelled = labels != np.iinfo(np.int32).max
+        labels[labelled] = np.asarray(ids, dtype=np.int32)[labels[labelled]]
+        label_sets.append((labels, ids))
+    R.zonal_from_labels(frame, workloads.F32_MAX, label_sets, len(rings), statistic, q)
+    seconds = time.perf_counter() - t0
+    return size * size / seconds / 1e9, seconds
+
+
 # ----------------------------------------------------------------------------
 # zonal statistics leg (BASELINE.json configs[3])
 # ----------------------------------------------------------------------------
 
 
-def run_zonal(args, torch, dist, stream, rank, world, peak):
+def run_zonal(args, torch, dist, stream, rank, world, peak, host_raster):
     """AggregateRaster mean / max / p90 of ~100 k polygons over a 40000 x 40000 float32 raster
     resident in HBM, one raster + polygon set per GPU (weak scaling; a striped single raster
     would add one all-reduce of N-vectors).  Timed per call of
@@ -291,6 +319,46 @@ def run_zonal(args, torch, dist, stream, rank, world, peak):
                           "checksum": float(np.nansum(res[0].astype(np.float64)))}
     del raster, rd
     torch.cuda.empty_cache()
+
+    # end to end through the Block API: host raster (the cfg2 float32 raster, 1 GiB) in a
+    # MemorySource, polygons in a MemoryGeometrySource, AggregateRaster.get_data per request --
+    # raster upload over PCIe, zonal kernels and the result frame inside the timed region
+    from dask_geomodeling_b200 import geometry, raster as raster_blocks
+    from dask_geomodeling_b200._compat import config as gm_config
+
+    size = host_raster.shape[-1]
+    grid = max(1, size // 128)
+    src = raster_blocks.MemorySource(host_raster, workloads.F32_MAX, workloads.PROJECTION, pixel_size=1.0,
+                                     pixel_origin=(0, size))
+    source = geometry.MemoryGeometrySource(workloads.cfg4_polygons(size, grid, seed=7 + rank), None,
+                                           workloads.PROJECTION)
+    request = dict(mode="intersects", projection=workloads.PROJECTION, geometry=utils.box(0, 0, size, size))
+    e2e = {"workload": "AggregateRaster.get_data, host raster {0}x{0} float32 + {1} polygons per GPU".format(
+        size, grid * grid), "unit": "Gpixel/s", "h2d_bytes_per_step": int(host_raster.nbytes), "steps": 3}
+    with gm_config.set({"geomodeling.raster-limit": 4 * size * size}):
+        for label in ("mean", "p90"):
+            view = geometry.AggregateRaster(source=source, raster=src, statistic=label)
+            for _ in range(2):
+                frame = view.get_data(**request)["features"]
+            _native.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                frame = view.get_data(**request)["features"]
+            _native.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            seconds = float(t[0]) / 3
+            e2e[label] = {"value": world * size * size / seconds / 1e9, "ms_per_request": seconds * 1e3,
+                          "d2h_bytes_per_step": 4 * len(frame), "checksum": float(np.nansum(frame["agg"].values.astype(np.float64)))}
+    out["e2e"] = e2e
+    if world == 1:
+        gpx, seconds = cpu_zonal_throughput()
+        out["cpu_baseline"] = {"value": gpx, "unit": "Gpixel/s", "cores": 1, "kind": "port",
+                               "sample": "mean of 1024 polygons over 4096 x 4096 float32 (cfg4 scaled), "
+                                         "bucketize + GDAL-rule labels + scipy labelled mean, {:.1f} s".format(seconds)}
     return out
 
 
@@ -395,7 +463,7 @@ def run_b200(args):
         peak, peak_kind = 6650.0, "fallback"
     zonal = None
     if not args.profile and not args.no_zonal:
-        zonal = run_zonal(args, torch, dist, stream, rank, world, peak)
+        zonal = run_zonal(args, torch, dist, stream, rank, world, peak, floats)
 
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -268,8 +268,23 @@ class AggregateRaster(GeometryBlock):
         result = features.copy()
         req_srs, agg_srs = process_kwargs["req_srs"], process_kwargs["agg_srs"]
         column = features["geometry"]
+        soup = None
         if hasattr(column, "to_crs"):
             agg_geometries = list(column.to_crs(agg_srs))
+        elif utils.same_projection(req_srs, agg_srs):
+            agg_geometries = column.values
+            prepared = features.attrs.get("polygon_soup")
+            prepared = prepared.value if prepared is not None else None
+            if (prepared is not None and len(prepared[1]) == len(features) and len(features)
+                    and agg_geometries[0] is prepared[2][prepared[1][0]]
+                    and agg_geometries[-1] is prepared[2][prepared[1][-1]]):
+                # the frame still holds the source's geometries: reuse their CSR form
+                # (kept resident in HBM when it is the source's full set)
+                full, positions, _ = prepared
+                if len(positions) == full.n_polygons:
+                    soup = full.to_device()
+                else:
+                    soup = full.subset(positions)
         else:
             agg_geometries = [utils.shapely_transform(g, req_srs, agg_srs) for g in column]
 
@@ -287,8 +302,8 @@ class AggregateRaster(GeometryBlock):
             return {"features": result, "projection": req_srs}
 
         agg, no_cells = aggregate_polygons(
-            agg_geometries, values, no_data_value, process_kwargs["agg_bbox"], agg_srs, thresholds,
-            statistic, percentile)
+            soup if soup is not None else agg_geometries, values, no_data_value,
+            process_kwargs["agg_bbox"], agg_srs, thresholds, statistic, percentile)
         if no_cells:
             # geometries that touch no cell centre are sampled at their centroid
             agg[:, no_cells] = aggregate_points(

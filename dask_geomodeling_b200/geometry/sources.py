@@ -27,6 +27,54 @@ def _as_geometry(item):
     return utils.Polygon(rings[0], rings[1:])   # shell + holes
 
 
+class Literal(object):
+    """Wrapper that carries a large list through the compute graph as ONE literal: the graph
+    runtime walks plain lists element by element (they may hold task keys) and hands
+    ``process`` a copy, which costs a pass over 100 k geometries per request and loses the
+    identity the cache below is keyed on.  Copies of frames that carry one (``DataFrame.attrs``
+    is deep-copied by pandas) share it."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __copy__(self):
+        return self
+
+
+def _unwrap(x):
+    return x.value if isinstance(x, Literal) else x
+
+
+_PREPARED = {}   # id(polygons) -> (polygons, geometries, soup, bounds); a few sources at most
+
+
+def _bounds(soup, geometries):
+    """Bounding boxes from the CSR arrays; geometries without rings (points) are asked."""
+    bounds = soup.bounds()
+    for i in np.nonzero(np.isnan(bounds[:, 0]))[0]:
+        if hasattr(geometries[i], "bounds") and not getattr(geometries[i], "is_empty", False):
+            bounds[i] = geometries[i].bounds
+    return bounds
+
+
+def _prepared(polygons):
+    """Geometry objects, CSR soup and bounding boxes of a polygon list, built once per list
+    object (the list is an argument of the block, i.e. it lives as long as the view)."""
+    hit = _PREPARED.get(id(polygons))
+    if hit is not None and hit[0] is polygons and len(hit[1]) == len(polygons):
+        return hit[1], hit[2], hit[3]
+    geometries = [_as_geometry(p) for p in polygons]
+    soup = utils.PolygonSoup(geometries)
+    bounds = _bounds(soup, geometries)
+    if len(_PREPARED) >= 8:
+        _PREPARED.pop(next(iter(_PREPARED)))
+    _PREPARED[id(polygons)] = (polygons, geometries, soup, bounds)
+    return geometries, soup, bounds
+
+
 class MemoryGeometrySource(GeometryBlock):
     """Features held in memory.
 
@@ -53,19 +101,26 @@ class MemoryGeometrySource(GeometryBlock):
         return result
 
     def get_sources_and_requests(self, **request):
-        return [(self.polygons, None), (self.properties, None), (self.projection, None), (request, None)]
+        literals = getattr(self, "_literals", None)
+        if literals is None:
+            literals = self._literals = (Literal(self.polygons), Literal(self.properties))
+        return [(literals[0], None), (literals[1], None), (self.projection, None), (request, None)]
 
     @staticmethod
     def process(polygons, properties, projection, request):
+        polygons, properties = _unwrap(polygons), _unwrap(properties)
         limit = request.get("limit")
         if limit is not None:
             polygons = polygons[:limit]
             properties = properties[:limit] if properties is not None else None
         mode = request.get("mode", "intersects")
-        geometries = [_as_geometry(p) for p in polygons]
-        if not utils.same_projection(projection, request["projection"]):
-            geometries = [utils.shapely_transform(g, projection, request["projection"]) for g in geometries]
-        bounds = np.array([g.bounds for g in geometries], dtype=np.float64).reshape(-1, 4)
+        same = utils.same_projection(projection, request["projection"])
+        geometries, soup, bounds = _prepared(polygons) if same else (None, None, None)
+        if geometries is None:
+            geometries = [utils.shapely_transform(_as_geometry(p), projection, request["projection"])
+                          for p in polygons]
+            soup = utils.PolygonSoup(geometries)
+            bounds = _bounds(soup, geometries)
         if mode == "extent":
             extent = None
             if len(geometries):
@@ -80,6 +135,7 @@ class MemoryGeometrySource(GeometryBlock):
         else:
             df.index.name = "id"
         window = request.get("geometry")
+        positions = np.arange(len(geometries))
         if window is not None and mode in ("intersects", "centroid"):
             x1, y1, x2, y2 = window.bounds
             if mode == "intersects":  # bounding boxes decide (no GEOS here)
@@ -88,4 +144,8 @@ class MemoryGeometrySource(GeometryBlock):
                 c = np.array([(g.centroid.x, g.centroid.y) for g in geometries])
                 keep = (c[:, 0] >= x1) & (c[:, 0] <= x2) & (c[:, 1] >= y1) & (c[:, 1] <= y2)
             df = df[keep]
+            positions = positions[keep]
+        # the CSR form of the geometries travels with the frame, so that consumers on the GPU
+        # path (AggregateRaster, Rasterize) need not walk the geometry objects again
+        df.attrs["polygon_soup"] = Literal((soup, positions, geometries))
         return {"features": df, "projection": request["projection"]}

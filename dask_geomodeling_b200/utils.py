@@ -477,6 +477,20 @@ def point_in_rings(rings, x, y):
     return inside
 
 
+def _expand_ranges(starts, counts):
+    """Concatenation of arange(starts[i], starts[i] + counts[i]) without a Python loop."""
+    starts, counts = np.asarray(starts, dtype=np.int64), np.asarray(counts, dtype=np.int64)
+    total = int(counts.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.int64)
+    keep = counts > 0
+    starts, counts = starts[keep], counts[keep]
+    first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    steps = np.ones(total, dtype=np.int64)
+    steps[first] = starts - np.concatenate([[0], starts[:-1] + counts[:-1] - 1])
+    return np.cumsum(steps)
+
+
 class PolygonSoup(object):
     """CSR layout the CUDA rasteriser consumes: interleaved xy, ring offsets,
     polygon -> ring offsets (GmPolygons in include/geokernels.h)."""
@@ -499,19 +513,30 @@ class PolygonSoup(object):
         return len(self.poly_offsets) - 1
 
     def subset(self, ids):
-        """The soup of the polygons `ids` (in that order)."""
+        """The soup of the polygons `ids` (in that order); index arithmetic only."""
         ids = np.asarray(ids, dtype=np.int64)
         sub = PolygonSoup([])
-        ring_a, ring_b = self.poly_offsets[ids], self.poly_offsets[ids + 1]
-        rings = np.concatenate([np.arange(a, b) for a, b in zip(ring_a, ring_b)]) if len(ids) else np.zeros(0, np.int64)
-        rings = rings.astype(np.int64)
-        v_a, v_b = self.ring_offsets[rings], self.ring_offsets[rings + 1]
-        sub.xy = np.ascontiguousarray(
-            np.concatenate([self.xy[a:b] for a, b in zip(v_a, v_b)]) if len(rings) else np.zeros((0, 2)),
-            dtype=np.float64)
-        sub.ring_offsets = np.concatenate([[0], np.cumsum(v_b - v_a)]).astype(np.int64)
-        sub.poly_offsets = np.concatenate([[0], np.cumsum(ring_b - ring_a)]).astype(np.int64)
+        if len(ids) == 0:
+            return sub
+        ring_a, ring_n = self.poly_offsets[ids], self.poly_offsets[ids + 1] - self.poly_offsets[ids]
+        rings = _expand_ranges(ring_a, ring_n)
+        v_a, v_n = self.ring_offsets[rings], self.ring_offsets[rings + 1] - self.ring_offsets[rings]
+        sub.xy = np.ascontiguousarray(self.xy[_expand_ranges(v_a, v_n)], dtype=np.float64).reshape(-1, 2)
+        sub.ring_offsets = np.concatenate([[0], np.cumsum(v_n)]).astype(np.int64)
+        sub.poly_offsets = np.concatenate([[0], np.cumsum(ring_n)]).astype(np.int64)
         return sub
+
+    def bounds(self):
+        """(n, 4) array of (xmin, ymin, xmax, ymax) per polygon (NaN for empty ones)."""
+        n = self.n_polygons
+        out = np.full((n, 4), np.nan)
+        starts = self.ring_offsets[self.poly_offsets[:-1]]
+        ends = self.ring_offsets[self.poly_offsets[1:]]
+        filled = np.nonzero(ends > starts)[0]
+        if len(filled):
+            out[filled, :2] = np.minimum.reduceat(self.xy, starts[filled], axis=0)
+            out[filled, 2:] = np.maximum.reduceat(self.xy, starts[filled], axis=0)
+        return out
 
     def as_struct(self):
         from ._native import GmPolygons
