@@ -579,7 +579,7 @@ def _finalize_rasterize_result(array, no_data_value):
     return {"values": array, "no_data_value": no_data_value}
 
 
-def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None):
+def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None, soup=None):
     """Burn geometries into a ``(1, height, width)`` raster.
 
     Same contract as the reference (utils.py:638-756): no values / bool values
@@ -587,7 +587,8 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None)
     values -> float64 with float64-max as no data (non-finite values dropped).
     A cell is burned when its centre lies inside the polygon; later geometries
     overwrite earlier ones.  A point bbox returns the value of the last
-    geometry containing the point.
+    geometry containing the point.  ``soup`` = the PolygonSoup of ``geoseries`` when the
+    caller already has it (geometry/sources.py prepares it once per polygon list).
     """
     import pandas as pd
     from . import _native
@@ -598,10 +599,13 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None)
     if values is not None and not isinstance(values, pd.Series):
         values = pd.Series(np.asarray(values), index=None if geoseries is None else geoseries.index)
 
+    positions = None if geoseries is None else np.arange(len(geoseries))
+    if soup is not None and (geoseries is None or soup.n_polygons != len(geoseries)):
+        soup = None
     if values is None or values.dtype == bool:
         dtype, no_data_value = np.uint8, 0
         if values is not None and geoseries is not None:
-            geoseries = geoseries[values.values]
+            geoseries, positions = geoseries[values.values], positions[values.values]
         values = None
     elif str(values.dtype) == "category":
         values = pd.Series(np.asarray(values), index=values.index)
@@ -612,7 +616,7 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None)
             no_data_value = get_dtype_max(dtype)
             if geoseries is not None:
                 finite = np.isfinite(values.values)
-                geoseries, values = geoseries[finite], values[finite]
+                geoseries, values, positions = geoseries[finite], values[finite], positions[finite]
         elif np.issubdtype(values.dtype, np.integer):
             dtype = np.int32
             no_data_value = get_dtype_max(dtype)
@@ -625,7 +629,7 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None)
         )
 
     present = ~geoseries.isnull().values
-    geoseries = geoseries[present]
+    geoseries, positions = geoseries[present], positions[present]
     if values is not None:
         values = values[present]
 
@@ -640,7 +644,10 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None)
             array[:] = True if values is None else values.values[np.nonzero(hits)[0][-1]]
         return _finalize_rasterize_result(array, no_data_value)
 
-    soup = PolygonSoup(geoseries.values)
+    if soup is None:
+        soup = PolygonSoup(geoseries.values)
+    elif len(positions) != soup.n_polygons:
+        soup = soup.subset(positions)
     burn = (
         np.ones(soup.n_polygons, dtype=dtype)
         if values is None
