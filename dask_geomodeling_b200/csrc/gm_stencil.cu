@@ -179,6 +179,112 @@ hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T n
   }
 }
 
+// Four output columns per lane: the arithmetic per pixel is what it is (the reference's float32
+// expression), but the work around it -- loads, shuffles, address steps, byte stores, loop
+// control -- is shared by four pixels: a lane loads source columns 4m .. 4m+3 of a row, takes
+// columns 4m+4, 4m+5 from its right-hand neighbour (two shuffles per row instead of two per
+// pixel), and writes its four grey levels as ONE 32-bit store.  A warp covers 124 output
+// columns per strip (lane 31 only feeds lane 30).
+constexpr int HQ_COLS = 124;   // output columns per warp
+constexpr int HQ_ROWS = 64;
+constexpr int HQ_AHEAD = 4;    // source rows fetched per batch (16 loads in flight per lane)
+
+template <typename T, bool EXACT_INVERSE>
+__global__ void __launch_bounds__(32 * HS_WARPS)
+hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
+                      T fill, int bands, int H, int W, double xres, double yres,
+                      double inv_xres, double inv_yres, int dst_aligned,
+                      float sin_alt, float cos_alt_zsf, float cos_az, float sin_az, float square_zsf) {
+  typedef typename HillArith<T>::acc A;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int SW = W + 2;
+  const int64_t in_plane = (int64_t)(H + 2) * SW, out_plane = (int64_t)H * W;
+  const int strips_x = (W + HQ_COLS - 1) / HQ_COLS;
+  const int strips_y = (H + HQ_ROWS - 1) / HQ_ROWS;
+  const int64_t strip = (int64_t)blockIdx.x * HS_WARPS + warp;
+  if (strip >= (int64_t)bands * strips_y * strips_x) return;
+  const int sx = (int)(strip % strips_x);
+  const int sy = (int)((strip / strips_x) % strips_y);
+  const int b = (int)(strip / ((int64_t)strips_x * strips_y));
+  const int x0 = sx * HQ_COLS + 4 * lane, y0 = sy * HQ_ROWS;   // first output column of this lane
+  const int rows = min(HQ_ROWS, H - y0);
+  const int last_row = H + 1, last_col = SW - 1;
+  const T* base = src + (int64_t)b * in_plane;
+  // source columns of this lane, clamped into the array (clamped values only feed outputs
+  // that are not written)
+  int col[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) col[j] = min(x0 + j, last_col);
+  auto clean = [&](T v) -> A { return (A)((has_nodata && v == nodata) ? fill : v); };
+  auto load_row = [&](int row, A (&w)[6]) {
+    const T* p = base + (int64_t)min(row, last_row) * SW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = clean(__ldg(p + col[j]));
+    w[4] = shfl_down_any<A>(w[0], 1);
+    w[5] = shfl_down_any<A>(w[1], 1);
+  };
+  A a[6], m[6];
+  load_row(y0, a);
+  load_row(y0 + 1, m);
+  const A two = (A)2;
+  const bool lane_writes = lane < 31 && x0 < W;
+  const bool whole_quad = dst_aligned && x0 + 3 < W;
+  uint8_t* o = dst + (int64_t)b * out_plane + (int64_t)y0 * W + x0;
+  for (int r0 = 0; r0 < rows; r0 += HQ_AHEAD) {
+    T next[HQ_AHEAD][4];
+#pragma unroll
+    for (int i = 0; i < HQ_AHEAD; ++i) {
+      const T* p = base + (int64_t)min(y0 + r0 + i + 2, last_row) * SW;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) next[i][j] = __ldg(p + col[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < HQ_AHEAD; ++i) {
+      const int r = r0 + i;
+      A c[6];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[j] = clean(next[i][j]);
+      c[4] = shfl_down_any<A>(c[0], 1);
+      c[5] = shfl_down_any<A>(c[1], 1);
+      unsigned packed = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // s0 s1 s2 = a[j..j+2] ; s3 . s5 = m[j], m[j+2] ; s6 s7 s8 = c[j..j+2]
+        const A gy = ((((a[j] + two * a[j + 1]) + a[j + 2]) - c[j]) - two * c[j + 1]) - c[j + 2];
+        const A gx = ((((a[j] + two * m[j]) + c[j]) - a[j + 2]) - two * m[j + 2]) - c[j + 2];
+        float fy, fx;
+        if (EXACT_INVERSE) {
+          fy = HillArith<T>::mul((T)gy, inv_yres);
+          fx = HillArith<T>::mul((T)gx, inv_xres);
+        } else {
+          fy = HillArith<T>::div((T)gy, yres);
+          fx = HillArith<T>::div((T)gx, xres);
+        }
+        const float xx_plus_yy = __fmaf_rn(fx, fx, fy * fy);
+        const float num = __fmaf_rn(-cos_alt_zsf, __fmaf_rn(fy, cos_az, -(fx * sin_az)), sin_alt);
+        float inv_len;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_len) : "f"(__fmaf_rn(square_zsf, xx_plus_yy, 1.0f)));
+        const float cang = num * inv_len;
+        const int grey = (int)(255.0f * cang);
+        const unsigned out = (cang <= 0.0f) ? 0u : ((unsigned)grey & 0xffu);
+        packed |= out << (8 * j);
+      }
+      if (lane_writes && r < rows) {
+        uint8_t* q = o + (int64_t)r * W;
+        if (whole_quad) {
+          *reinterpret_cast<unsigned*>(q) = packed;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (x0 + j < W) q[j] = (uint8_t)(packed >> (8 * j));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { a[j] = m[j]; m[j] = c[j]; }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // MovingMax (raster/spatial.py:192-213): circular footprint, chord per row
 // ---------------------------------------------------------------------------------
@@ -1053,6 +1159,21 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
   const int strips_x = (W + HS_COLS - 1) / HS_COLS, strips_y = (H + HS_ROWS - 1) / HS_ROWS;
   const int64_t strips = (int64_t)bands * strips_x * strips_y;
   const unsigned blocks = (unsigned)((strips + HS_WARPS - 1) / HS_WARPS);
+  if (!getenv("GM_HILLSHADE_STRIP")) {
+    const int qx = (W + HQ_COLS - 1) / HQ_COLS, qy = (H + HQ_ROWS - 1) / HQ_ROWS;
+    const int64_t qstrips = (int64_t)bands * qx * qy;
+    const unsigned qblocks = (unsigned)((qstrips + HS_WARPS - 1) / HS_WARPS);
+    const int aligned = ((uintptr_t)out.dev % 4 == 0) && (W % 4 == 0);
+#define GM_HQ(EXACT)                                                                                \
+    hillshade_quad_kernel<T, EXACT><<<qblocks, 32 * HS_WARPS, 0, s>>>(                                \
+        (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
+        cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, aligned,                  \
+        (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf))
+    if (exact) GM_HQ(true); else GM_HQ(false);
+#undef GM_HQ
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
 #define GM_HS(EXACT)                                                                                \
   hillshade_strip_kernel<T, EXACT><<<blocks, 32 * HS_WARPS, 0, s>>>(                                \
       (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
