@@ -190,7 +190,7 @@ constexpr int HQ_ROWS = 64;
 constexpr int HQ_AHEAD = 4;    // source rows fetched per batch (16 loads in flight per lane)
 
 template <typename T, bool EXACT_INVERSE>
-__global__ void __launch_bounds__(32 * HS_WARPS)
+__global__ void __launch_bounds__(32 * HS_WARPS, 4)
 hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
                       T fill, int bands, int H, int W, double xres, double yres,
                       double inv_xres, double inv_yres, int dst_aligned,
