@@ -4,3 +4,4 @@ from .misc import *  # NOQA
 from .sources import *  # NOQA
 from .spatial import *  # NOQA
 from .temporal import *  # NOQA
+from .parallelize import *  # NOQA

@@ -4,7 +4,7 @@ sizes, plus the fusion bookkeeping (root key kept, one launch)."""
 import numpy as np
 import pytest
 
-from dask_geomodeling_b200 import _native, workloads
+from dask_geomodeling_b200 import _native, raster, workloads
 from dask_geomodeling_b200.core import fusion
 from dask_geomodeling_b200._compat import config
 from oracle import workloads as oracle_workloads
@@ -118,3 +118,26 @@ def test_streamed_chain_window_and_bands(small_stream_chunks):
     got = view.get_data(**request)
     assert got["values"].shape == (3, 300, 260)
     np.testing.assert_array_equal(got["values"], expected[0])
+
+
+@pytest.mark.parametrize("tile_size", [64, [100, 37], 1024])
+def test_raster_tiler_equals_untiled(tile_size):
+    # reference raster/parallelize.py:43-125 (tests/test_raster_parallelize.py): tiles are
+    # independent requests, the stitched result equals the plain request
+    size = 200
+    a, b = workloads.cfg1_arrays(size)
+    view = workloads.cfg1_view(a, b)
+    request = workloads.request(size, size)
+    request.update(bbox=(10, 20, 190, 170), width=180, height=150)
+    expected = view.get_data(**request)
+    tiled = raster.RasterTiler(view, tile_size)
+    got = tiled.get_data(**request)
+    assert got["values"].dtype == expected["values"].dtype
+    np.testing.assert_array_equal(got["values"], expected["values"])
+    assert got["no_data_value"] == expected["no_data_value"]
+    assert tiled.get_data(**dict(request, mode="meta")) == view.get_data(**dict(request, mode="meta"))
+    # a stencil whose request margin equals its reach tiles exactly as well (Smooth does not:
+    # its Gaussian reaches beyond the margin it requests, in the reference too)
+    stencil = raster.MovingMax(workloads.source(a, workloads.F32_MAX), 7)
+    plain = stencil.get_data(**request)
+    np.testing.assert_array_equal(raster.RasterTiler(stencil, [64, 50]).get_data(**request)["values"], plain["values"])
