@@ -1245,14 +1245,14 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
 // The order of the keys in shared memory is irrelevant, so spans are stored as they come.
 constexpr int ZS_THREADS = 256;
 constexpr int ZS_MAXROWS = 512;
-constexpr int ZS_MAXSPANS = 1024;
-constexpr int ZS_DIGIT = 11, ZS_BINS = 1 << ZS_DIGIT;
-constexpr int ZS_CAND = 2048;
+constexpr int ZS_MAXSPANS = 512;
+constexpr int ZS_DIGIT = 10, ZS_BINS = 1 << ZS_DIGIT;
+constexpr int ZS_CAND = 256;
 constexpr int ZS_ROWS = 8;               // rows per warp and round of loads
 constexpr int ZS_MARGIN = 8;             // sample positions either side of the wanted rank (of 32)
 constexpr unsigned ZS_EMPTY = 0xffffffffu;
 
-__global__ void __launch_bounds__(ZS_THREADS, 2)
+__global__ void __launch_bounds__(ZS_THREADS, 3)
 zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, float nodata, int has_nodata,
                          int mis, int edge_scalar, int stat, double q, int capacity,
                          float* __restrict__ out, long long* __restrict__ area, int* __restrict__ work) {
@@ -1882,8 +1882,8 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       int dev = 0, smem_max = 0;
       GM_TRY(cudaGetDevice(&dev));
       GM_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      // two blocks per SM: half of the 227 KB minus the static tables (~22 k cells per polygon)
-      const int dyn = (smem_max - 2 * 37 * 1024) / 2 / 16 * 16;
+      // three blocks per SM: a third of the 227 KB minus the static tables (~15 k cells per polygon)
+      const int dyn = (smem_max - 3 * 18 * 1024) / 3 / 16 * 16;
       float ndf = 0.0f;
       memcpy(&ndf, &nd, sizeof(float) < sizeof(T) ? sizeof(float) : sizeof(T));
       GM_TRY(cudaFuncSetAttribute(zonal_select_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
