@@ -43,55 +43,7 @@ template <typename T> struct HillArith {  // integer rasters: arithmetic wraps i
   static __device__ __forceinline__ float mul(T v, double inv) { return (float)((double)v * inv); }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-hillshade_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
-                 T fill, int bands, int H, int W, double xres, double yres,
-                 float sin_alt, float cos_alt_zsf, float az, float square_zsf) {
-  typedef typename HillArith<T>::acc A;
-  const int SW = W + 2;
-  const int64_t in_plane = (int64_t)(H + 2) * SW, out_plane = (int64_t)H * W;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
-  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
-    const T* p = src + (int64_t)b * in_plane + (int64_t)y * SW + x;
-    A s[9];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        T v = __ldg(p + r * SW + c);
-        if (has_nodata && v == nodata) v = fill;
-        s[r * 3 + c] = (A)v;
-      }
-    const A two = (A)2;
-    const A gy = ((((s[0] + two * s[1]) + s[2]) - s[6]) - two * s[7]) - s[8];
-    const A gx = ((((s[0] + two * s[3]) + s[6]) - s[2]) - two * s[5]) - s[8];
-    const float fy = HillArith<T>::div((T)gy, yres), fx = HillArith<T>::div((T)gx, xres);
-    const float xx_plus_yy = fx * fx + fy * fy;
-    const float aspect = atan2f(fy, fx);
-    const float num = sin_alt - (cos_alt_zsf * sqrtf(xx_plus_yy)) * sinf(aspect - az);
-    const float cang = num / sqrtf(1.0f + square_zsf * xx_plus_yy);
-    uint8_t out = 0;
-    if (!(cang <= 0.0f)) out = (uint8_t)(int)(255.0f * cang);
-    dst[(int64_t)b * out_plane + (int64_t)y * W + x] = out;
-  }
-}
-
-
-// Strip version (used for every dtype): a warp walks down a strip of 30 output columns,
-// each lane loading ONE source value per row (one coalesced 128-byte request) and getting
-// its two right-hand neighbours by shuffle, with the three live rows kept in registers:
-// 1.03 loads per pixel instead of 9.  The Horn gradient and the two divisions are the
-// reference's float32 expression; the shading uses the identity
-//   sqrt(x^2+y^2) * sin(atan2(y, x) - az) = y*cos(az) - x*sin(az)
-// and one rsqrt (a few ulp from the reference expression: SURVEY.md Appendix A-13 measured
-// <= 1 grey level on 4e-5 of the pixels for this form; the parity test allows 1e-3).
-constexpr int HS_COLS = 30;    // output columns per warp
-constexpr int HS_ROWS = 64;    // output rows per warp
 constexpr int HS_WARPS = 8;
-constexpr int HS_AHEAD = 8;   // source rows fetched per batch
 
 template <typename A> __device__ __forceinline__ A shfl_down_any(A v, int d) {
   return __shfl_down_sync(0xffffffffu, v, d);
@@ -102,89 +54,17 @@ template <> __device__ __forceinline__ int16_t shfl_down_any<int16_t>(int16_t v,
 template <> __device__ __forceinline__ uint16_t shfl_down_any<uint16_t>(uint16_t v, int d) { return (uint16_t)__shfl_down_sync(0xffffffffu, (int)v, d); }
 template <> __device__ __forceinline__ int64_t shfl_down_any<int64_t>(int64_t v, int d) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)v, d); }
 
-template <typename T, bool EXACT_INVERSE>
-__global__ void __launch_bounds__(32 * HS_WARPS)
-hillshade_strip_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
-                       T fill, int bands, int H, int W, double xres, double yres,
-                       double inv_xres, double inv_yres,
-                       float sin_alt, float cos_alt_zsf, float cos_az, float sin_az, float square_zsf) {
-  typedef typename HillArith<T>::acc A;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int SW = W + 2;
-  const int64_t in_plane = (int64_t)(H + 2) * SW, out_plane = (int64_t)H * W;
-  const int strips_x = (W + HS_COLS - 1) / HS_COLS;
-  const int64_t strip = (int64_t)blockIdx.x * HS_WARPS + warp;   // (band, y strip, x strip)
-  const int strips_y = (H + HS_ROWS - 1) / HS_ROWS;
-  if (strip >= (int64_t)bands * strips_y * strips_x) return;
-  const int sx = (int)(strip % strips_x);
-  const int sy = (int)((strip / strips_x) % strips_y);
-  const int b = (int)(strip / ((int64_t)strips_x * strips_y));
-  const int x0 = sx * HS_COLS, y0 = sy * HS_ROWS;
-  const int col = x0 + lane;                       // source column of this lane
-  const bool col_ok = col < SW;
-  const bool writes = lane < HS_COLS && x0 + lane < W;
-  uint8_t* o = dst + (int64_t)b * out_plane + (int64_t)y0 * W + x0 + lane;
-  const int rows = min(HS_ROWS, H - y0);
-  const bool full = rows == HS_ROWS;               // warp-uniform: no row of this strip is clipped
-  // Loads are unconditional (row / column clamped into the array) so that a batch of
-  // HS_AHEAD rows is in flight before the first value is looked at.
-  const int last_row = H + 1;                      // last source row of the band
-  const T* pc = src + (int64_t)b * in_plane + (col_ok ? col : SW - 1);
-  auto raw = [&](int row) -> T { return __ldg(pc + (int64_t)min(row, last_row) * SW); };
-  auto clean = [&](T v) -> A { return (A)((has_nodata && v == nodata) ? fill : v); };
-  A a0 = clean(raw(y0)), b0 = clean(raw(y0 + 1));
-  A a1 = shfl_down_any<A>(a0, 1), a2 = shfl_down_any<A>(a0, 2);
-  A b1 = shfl_down_any<A>(b0, 1), b2 = shfl_down_any<A>(b0, 2);
-  const A two = (A)2;
-  const T* next_row = pc + (int64_t)(y0 + 2) * SW;  // walks down with the batches of a full strip
-  for (int r0 = 0; r0 < rows; r0 += HS_AHEAD) {
-    T next[HS_AHEAD];
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < HS_AHEAD; ++i) next[i] = __ldg(next_row + (int64_t)i * SW);
-      next_row += (int64_t)HS_AHEAD * SW;
-    } else {
-#pragma unroll
-      for (int i = 0; i < HS_AHEAD; ++i) next[i] = raw(y0 + r0 + i + 2);
-    }
-#pragma unroll
-    for (int i = 0; i < HS_AHEAD; ++i) {
-      const int r = r0 + i;
-      const A c0 = clean(next[i]);
-      const A c1 = shfl_down_any<A>(c0, 1), c2 = shfl_down_any<A>(c0, 2);
-      // s0 s1 s2 = a0 a1 a2 ; s3 s4 s5 = b0 b1 b2 ; s6 s7 s8 = c0 c1 c2
-      const A gy = ((((a0 + two * a1) + a2) - c0) - two * c1) - c2;
-      const A gx = ((((a0 + two * b0) + c0) - a2) - two * b2) - c2;
-      float fy, fx;
-      if (EXACT_INVERSE) {  // resolution is a power of two: v * (1 / res) == v / res bit for bit
-        fy = HillArith<T>::mul((T)gy, inv_yres);
-        fx = HillArith<T>::mul((T)gx, inv_xres);
-      } else {
-        fy = HillArith<T>::div((T)gy, yres);
-        fx = HillArith<T>::div((T)gx, xres);
-      }
-      // the shading is tolerance-bound (see above): fused multiply-adds and the hardware
-      // reciprocal square root (argument >= 1, 2^-22 relative error) instead of 16 instructions
-      const float xx_plus_yy = __fmaf_rn(fx, fx, fy * fy);
-      const float num = __fmaf_rn(-cos_alt_zsf, __fmaf_rn(fy, cos_az, -(fx * sin_az)), sin_alt);
-      float inv_len;
-      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_len) : "f"(__fmaf_rn(square_zsf, xx_plus_yy, 1.0f)));
-      const float cang = num * inv_len;
-      const int grey = (int)(255.0f * cang);
-      const uint8_t out = (cang <= 0.0f) ? (uint8_t)0 : (uint8_t)grey;
-      if (writes && (full || r < rows)) o[(int64_t)r * W] = out;
-      a0 = b0; a1 = b1; a2 = b2;
-      b0 = c0; b1 = c1; b2 = c2;
-    }
-  }
-}
-
 // Four output columns per lane: the arithmetic per pixel is what it is (the reference's float32
 // expression), but the work around it -- loads, shuffles, address steps, byte stores, loop
 // control -- is shared by four pixels: a lane loads source columns 4m .. 4m+3 of a row, takes
 // columns 4m+4, 4m+5 from its right-hand neighbour (two shuffles per row instead of two per
 // pixel), and writes its four grey levels as ONE 32-bit store.  A warp covers 124 output
-// columns per strip (lane 31 only feeds lane 30).
+// columns per strip (lane 31 only feeds lane 30).  The Horn gradient and the two divisions
+// are the reference's float32 expression; the shading uses the identity
+//   sqrt(x^2+y^2) * sin(atan2(y, x) - az) = y*cos(az) - x*sin(az),
+// fused multiply-adds and one hardware reciprocal square root (argument >= 1, 2^-22 relative
+// error) -- a few ulp from the reference expression: SURVEY.md Appendix A-13 measured <= 1
+// grey level on 4e-5 of the pixels for this form; the parity tests allow 1e-3.
 constexpr int HQ_COLS = 124;   // output columns per warp
 constexpr int HQ_ROWS = 64;
 constexpr int HQ_AHEAD = 4;    // source rows fetched per batch (16 loads in flight per lane)
@@ -762,13 +642,11 @@ static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, i
                 std::is_same<T, int16_t>::value || std::is_same<T, uint8_t>::value ||
                 std::is_same<T, int32_t>::value) {
     if constexpr (sizeof(T) == 4) {
-      if (!getenv("GM_MOVING_MAX_SCALAR")) {
-        switch (size) {
+      switch (size) {
 #define GM_CASE(N) case N: return launch_moving_max_quad<T, N>(in, out, nd, has_nodata, bands, H, W, s);
-          GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
+        GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
 #undef GM_CASE
-          default: break;
-        }
+        default: break;
       }
     }
     switch (size) {
@@ -787,38 +665,7 @@ static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, i
 constexpr int DILATE_MAX_VALUES = 64;
 template <typename T> struct DilateValues { T v[DILATE_MAX_VALUES]; int n; };
 
-template <typename T>
-__global__ void __launch_bounds__(256)
-dilate_kernel(const T* __restrict__ src, T* __restrict__ dst, int bands, int H, int W,
-              const __grid_constant__ DilateValues<T> values) {
-  const int SW = W + 2, SH = H + 2;
-  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= W || y >= H) return;
-  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
-    const T* c = src + (int64_t)b * in_plane + (int64_t)(y + 1) * SW + (x + 1);
-    T nb[7];
-    bool ok[7];
-    nb[0] = c[0]; ok[0] = true;
-    nb[1] = c[-1]; ok[1] = true;      // the halo is part of the array: always in bounds
-    nb[2] = c[1]; ok[2] = true;
-    nb[3] = c[-SW]; ok[3] = true;
-    nb[4] = c[SW]; ok[4] = true;
-    ok[5] = b > 0; nb[5] = ok[5] ? c[-in_plane] : c[0];
-    ok[6] = b + 1 < bands; nb[6] = ok[6] ? c[in_plane] : c[0];
-    int best = -1;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      if (!ok[k]) continue;
-      for (int i = values.n - 1; i > best; --i)
-        if (nb[k] == values.v[i]) { best = i; break; }
-    }
-    dst[(int64_t)b * out_plane + (int64_t)y * W + x] = best >= 0 ? values.v[best] : nb[0];
-  }
-}
-
-// Tiled version: every source cell is ranked ONCE (rank = 1 + index of the cell's value in
+// Every source cell is ranked ONCE (rank = 1 + index of the cell's value in
 // `values`, 0 if it is not listed; later values win, so the output is the value of the
 // largest rank in the 7-point cross) into a byte tile in shared memory -- single-byte
 // rasters through a 256-entry table -- and an output cell then takes the maximum of five
@@ -1156,31 +1003,17 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
   auto pow2 = [](double v) { int e; return v > 0 && std::frexp(v, &e) == 0.5 && e > -100 && e < 100; };
   const bool is_f32 = std::is_same<T, float>::value;
   const int exact = pow2(is_f32 ? (double)(float)xres : xres) && pow2(is_f32 ? (double)(float)yres : yres);
-  const int strips_x = (W + HS_COLS - 1) / HS_COLS, strips_y = (H + HS_ROWS - 1) / HS_ROWS;
-  const int64_t strips = (int64_t)bands * strips_x * strips_y;
-  const unsigned blocks = (unsigned)((strips + HS_WARPS - 1) / HS_WARPS);
-  if (!getenv("GM_HILLSHADE_STRIP")) {
-    const int qx = (W + HQ_COLS - 1) / HQ_COLS, qy = (H + HQ_ROWS - 1) / HQ_ROWS;
-    const int64_t qstrips = (int64_t)bands * qx * qy;
-    const unsigned qblocks = (unsigned)((qstrips + HS_WARPS - 1) / HS_WARPS);
-    const int aligned = ((uintptr_t)out.dev % 4 == 0) && (W % 4 == 0);
+  const int qx = (W + HQ_COLS - 1) / HQ_COLS, qy = (H + HQ_ROWS - 1) / HQ_ROWS;
+  const int64_t qstrips = (int64_t)bands * qx * qy;
+  const unsigned qblocks = (unsigned)((qstrips + HS_WARPS - 1) / HS_WARPS);
+  const int aligned = ((uintptr_t)out.dev % 4 == 0) && (W % 4 == 0);
 #define GM_HQ(EXACT)                                                                                \
-    hillshade_quad_kernel<T, EXACT><<<qblocks, 32 * HS_WARPS, 0, s>>>(                                \
-        (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
-        cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, aligned,                  \
-        (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf))
-    if (exact) GM_HQ(true); else GM_HQ(false);
-#undef GM_HQ
-    GM_LAUNCH_CHECK();
-    return 0;
-  }
-#define GM_HS(EXACT)                                                                                \
-  hillshade_strip_kernel<T, EXACT><<<blocks, 32 * HS_WARPS, 0, s>>>(                                \
+  hillshade_quad_kernel<T, EXACT><<<qblocks, 32 * HS_WARPS, 0, s>>>(                                \
       (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
-      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres,                           \
+      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, aligned,                  \
       (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf))
-  if (exact) GM_HS(true); else GM_HS(false);
-#undef GM_HS
+  if (exact) GM_HQ(true); else GM_HQ(false);
+#undef GM_HQ
   GM_LAUNCH_CHECK();
   return 0;
 }
