@@ -7,6 +7,7 @@
 // dtype (float32 or float64 = result_type(float32, out dtype)), which is what
 // NumPy's axis-0 reductions do, so sums are bit-identical.
 #include "gm_common.cuh"
+#include <type_traits>
 #include <cfloat>
 #include <limits>
 
@@ -184,6 +185,95 @@ __global__ void temporal_sort_kernel(const S* __restrict__ src, D* __restrict__ 
   }
 }
 
+// Median / percentile of bins of at most 64 frames: the samples of a pixel live in REGISTERS
+// (P = 16, 32 or 64 slots, invalid ones = +inf) and the bitonic network is fully unrolled --
+// every compare-exchange is two FMNMX on registers instead of two loads, two stores and the
+// selects of the shared-memory version (672 exchanges at P = 64: 1.3 k instead of 6.7 k
+// instructions per pixel).  The two order statistics are picked with unrolled predicated moves
+// (a dynamically indexed register array would go to local memory).
+template <typename W> __device__ __forceinline__ W wmin(W a, W b) { return a < b ? a : b; }
+template <typename W> __device__ __forceinline__ W wmax(W a, W b) { return a < b ? b : a; }
+template <> __device__ __forceinline__ float wmin<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ float wmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double wmin<double>(double a, double b) { return fmin(a, b); }
+template <> __device__ __forceinline__ double wmax<double>(double a, double b) { return fmax(a, b); }
+
+template <typename S, typename W, typename D, int P>
+__global__ void __launch_bounds__(128)
+temporal_sort_reg_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                         int stat, double q, const int* __restrict__ bin_offsets,
+                         const int* __restrict__ frame_index, int n_bins, int64_t plane) {
+  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (pix >= plane) return;
+  const D fill = DMax<D>::value();
+  const W inf = (W)INFINITY;
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], len = bin_offsets[g + 1] - f0;
+    W w[P];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      w[i] = inf;
+      if (i < len) {
+        const S v = __ldcs(src + (int64_t)frame_index[f0 + i] * plane + pix);
+        const W x = (W)v;
+        const bool ok = !(has_nodata && v == nodata) && x == x;
+        w[i] = ok ? x : inf;
+        n += ok ? 1 : 0;
+      }
+    }
+    // +inf never is a NaN, so fmin / fmax order the slots like the `a < b` exchange
+#pragma unroll
+    for (int k = 2; k <= P; k <<= 1)
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1)
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          const int l = i ^ j;
+          if (l > i) {
+            const W a = w[i], b = w[l];
+            const bool up = (i & k) == 0;
+            w[i] = up ? wmin<W>(a, b) : wmax<W>(a, b);
+            w[l] = up ? wmax<W>(a, b) : wmin<W>(a, b);
+          }
+        }
+    D out = fill;
+    if (n > 0) {
+      int lo, hi;
+      W t = (W)0;
+      if (stat == GM_STAT_MEDIAN) {
+        lo = (n - 1) / 2; hi = n / 2;
+      } else {
+        const W qw = (W)q / (W)100;
+        const W virt = (W)(n - 1) * qw;
+        lo = (int)floor((double)virt);
+        if (lo < 0) lo = 0;
+        if (lo > n - 1) lo = n - 1;
+        hi = lo + 1 < n ? lo + 1 : n - 1;
+        t = virt - (W)lo;
+      }
+      W a = (W)0, b = (W)0;
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        a = i == lo ? w[i] : a;
+        b = i == hi ? w[i] : b;
+      }
+      W result;
+      if (stat == GM_STAT_MEDIAN) {
+        result = (n & 1) ? a : (a + b) / (W)2;
+      } else {
+        // np.nanpercentile(method="linear") in the working dtype W (see the generic kernel)
+        const W diff = b - a;
+        result = a + diff * t;
+        if (t >= (W)0.5) result = b - diff * ((W)1 - t);
+      }
+      const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+      if (finite) out = cast_out<W, D>(result);
+    }
+    dst[(int64_t)g * plane + pix] = out;
+  }
+}
+
 // Streaming fast path for sum / count / min / max / mean: the statistic is a template
 // argument (only the accumulators it needs exist), a thread owns VEC = 16 / sizeof(S)
 // consecutive pixels so every frame is read with 128-bit loads, and UNROLL frames are in
@@ -315,6 +405,23 @@ static int launch_aggregate(const Staged& in, Staged& out, const TemporalArgs& a
 #undef GM_STREAM
     GM_LAUNCH_CHECK();
     return 0;
+  }
+  // register-resident network: float32 working dtype over the usual source dtypes (the fully
+  // unrolled networks are expensive to compile, so only these are instantiated)
+  if constexpr (std::is_same<W, float>::value && std::is_same<D, float>::value &&
+                (std::is_same<S, float>::value || std::is_same<S, int16_t>::value ||
+                 std::is_same<S, uint8_t>::value)) {
+    if ((a.stat == GM_STAT_MEDIAN || a.stat == GM_STAT_PERCENTILE) && a.sort_slots > 0 && a.sort_slots <= 64) {
+      const unsigned nb = (unsigned)((a.plane + 127) / 128);
+#define GM_SORT_REG(P)                                                                         \
+      temporal_sort_reg_kernel<S, W, D, P><<<nb, 128, 0, s>>>(                                  \
+          (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.q, a.bins, a.frames, a.n_bins, a.plane)
+      if (a.sort_slots <= 32) GM_SORT_REG(32);
+      else GM_SORT_REG(64);
+#undef GM_SORT_REG
+      GM_LAUNCH_CHECK();
+      return 0;
+    }
   }
   if ((a.stat == GM_STAT_MEDIAN || a.stat == GM_STAT_PERCENTILE) && a.sort_threads > 0) {
     auto kernel = temporal_sort_kernel<S, W, D>;
