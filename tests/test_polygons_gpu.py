@@ -134,6 +134,32 @@ def test_zonal_order_statistics_convex_float32(kind, statistic):
     np.testing.assert_array_equal(got[0], expected)
 
 
+@pytest.mark.parametrize("dtype", ["f4", "i2"])
+@pytest.mark.parametrize("statistic", ["sum", "count", "max", "mean", "median", "p90"])
+def test_zonal_stats_raster_without_nodata(dtype, statistic):
+    """No no-data value at all: every cell under a polygon is active (the float32 paths that
+    mark unused slots with the sentinel must not be taken)."""
+    h, w = 97, 131
+    rng = np.random.default_rng(31)
+    frame = (rng.uniform(-50, 100, (h, w)) if dtype == "f4" else rng.integers(-50, 100, (h, w))).astype(dtype)
+    polys = random_polygons(30, 130, seed=13, concave=True)
+    bbox = (0, 0, w, h)
+    name, q = utils.parse_percentile_statistic(statistic)
+    label_sets = []
+    for i, rings in enumerate(polys):
+        labels = polyfill.burn_index([rings], bbox, h, w)
+        label_sets.append((np.where(labels == 0, i, np.iinfo(np.int32).max).astype(np.int32), [i]))
+    # a value no cell holds stands in for "no no-data value" in the oracle
+    expected, no_cells = R.zonal_from_labels(frame, frame.dtype.type(-12345), label_sets, len(polys), name, q)
+    got, got_no_cells = geometry.aggregate.aggregate_polygons(
+        to_geometries(polys), frame[np.newaxis], None, bbox, workloads.PROJECTION, None, name, q)
+    assert sorted(got_no_cells) == no_cells
+    if name in ("sum", "mean"):
+        np.testing.assert_allclose(got[0], expected, rtol=1e-6, equal_nan=True)
+    else:
+        np.testing.assert_array_equal(got[0], expected)
+
+
 def test_zonal_thresholds_and_large_polygon():
     h, w = 400, 420
     rng = np.random.default_rng(12)
