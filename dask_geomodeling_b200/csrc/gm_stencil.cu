@@ -725,6 +725,99 @@ dilate_tiled_kernel(const T* __restrict__ src, T* __restrict__ dst, int bands, i
   }
 }
 
+// Single-byte rasters (the usual class rasters): four cells per thread, packed in one word.
+// Ranks and original bytes are staged as words (4-byte left pad, so that an output word and
+// its upper / lower neighbours are aligned word loads; the left / right neighbours are two
+// byte permutes of adjacent words), the 5-point maximum is four bytewise maxima, and a word
+// whose cross holds no listed value is copied through.
+constexpr int DP_TX = 256, DP_TY = 16;            // outputs per block
+constexpr int DP_WORDS = DP_TX / 4 + 2;           // words per staged row (one pad word each side)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dilate_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int bands, int H, int W, int dst_aligned,
+                     const __grid_constant__ DilateValues<T> values) {
+  static_assert(sizeof(T) == 1, "bytes");
+  __shared__ unsigned rank[DP_TY + 2][DP_WORDS];
+  __shared__ unsigned orig[DP_TY][DP_TX / 4];
+  __shared__ unsigned char lut[256];
+  __shared__ unsigned char vals[DILATE_MAX_VALUES + 1];
+  const unsigned char* s8 = reinterpret_cast<const unsigned char*>(src);
+  unsigned char* d8 = reinterpret_cast<unsigned char*>(dst);
+  const int SW = W + 2, SH = H + 2;
+  const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * DP_TX, y0 = blockIdx.y * DP_TY;
+  {
+    int r = 0;
+    for (int i = 0; i < values.n; ++i)
+      if ((unsigned char)values.v[i] == (unsigned char)tid) r = i + 1;
+    lut[tid] = (unsigned char)r;
+    if (tid <= values.n) vals[tid] = tid ? (unsigned char)values.v[tid - 1] : 0;
+  }
+  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+    const unsigned char* plane = s8 + (int64_t)b * in_plane;
+    __syncthreads();
+    // staged byte j of a row <-> source column x0 - 3 + j (output column c sits at byte c + 4)
+    for (int task = tid; task < (DP_TY + 2) * DP_WORDS; task += 256) {
+      const int ty = task / DP_WORDS, wx = task - ty * DP_WORDS;
+      const int gy = y0 + ty;
+      unsigned ranks = 0, bytes = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int gx = x0 - 3 + 4 * wx + k;
+        if (gy < SH && gx >= 0 && gx < SW) {
+          const unsigned v = plane[(int64_t)gy * SW + gx];
+          ranks |= (unsigned)lut[v] << (8 * k);
+          bytes |= v << (8 * k);
+        }
+      }
+      rank[ty][wx] = ranks;
+      if (ty >= 1 && ty <= DP_TY && wx >= 1 && wx <= DP_TX / 4) orig[ty - 1][wx - 1] = bytes;
+    }
+    __syncthreads();
+    for (int task = tid; task < DP_TY * (DP_TX / 4); task += 256) {
+      const int ty = task / (DP_TX / 4), wx = task - ty * (DP_TX / 4);
+      const int y = y0 + ty, x = x0 + 4 * wx;
+      if (y >= H || x >= W) continue;
+      const unsigned c = rank[ty + 1][wx + 1];
+      const unsigned left = __byte_perm(rank[ty + 1][wx], c, 0x6543);       // ranks of columns x-1 .. x+2
+      const unsigned right = __byte_perm(c, rank[ty + 1][wx + 2], 0x4321);  // ranks of columns x+1 .. x+4
+      unsigned best = __vmaxu4(__vmaxu4(c, rank[ty][wx + 1]), __vmaxu4(rank[ty + 2][wx + 1], __vmaxu4(left, right)));
+      unsigned out = orig[ty][wx];
+      if (bands > 1) {   // the time neighbours of the 3-D cross, ranked on the fly
+        unsigned tn = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (x + k < W) {
+            const int64_t at = (int64_t)(y + 1) * SW + (x + k + 1);
+            unsigned r = 0;
+            if (b > 0) r = lut[plane[at - in_plane]];
+            if (b + 1 < bands) r = max(r, (unsigned)lut[plane[at + in_plane]]);
+            tn |= r << (8 * k);
+          }
+        }
+        best = __vmaxu4(best, tn);
+      }
+      if (best) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned r = (best >> (8 * k)) & 0xffu;
+          if (r) out = (out & ~(0xffu << (8 * k))) | ((unsigned)vals[r] << (8 * k));
+        }
+      }
+      unsigned char* o = d8 + (int64_t)b * out_plane + (int64_t)y * W + x;
+      if (dst_aligned && x + 3 < W) {
+        *reinterpret_cast<unsigned*>(o) = out;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (x + k < W) o[k] = (unsigned char)(out >> (8 * k));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Smooth (raster/spatial.py:273-307): scipy.ndimage.gaussian_filter restated
 // ---------------------------------------------------------------------------------
@@ -1087,6 +1180,13 @@ static int run_dilate(const Staged& in, Staged& out, const void* values, int n_v
   memset(&dv, 0, sizeof(dv));
   dv.n = n_values;
   memcpy(dv.v, values, sizeof(T) * n_values);
+  if constexpr (sizeof(T) == 1) {
+    const int aligned = ((uintptr_t)out.dev % 4 == 0) && (W % 4 == 0);
+    dilate_packed_kernel<T><<<grid3(W, H, bands, DP_TX, DP_TY), 256, 0, s>>>(
+        (const T*)in.dev, (T*)out.dev, bands, H, W, aligned, dv);
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
   dilate_tiled_kernel<T><<<grid3(W, H, bands, DL_TX, DL_TY), 256, 0, s>>>(
       (const T*)in.dev, (T*)out.dev, bands, H, W, dv);
   GM_LAUNCH_CHECK();
