@@ -1278,18 +1278,20 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
     if (r1 > r0) { v0 = P.ring_offsets[r0]; v1 = P.ring_offsets[r1]; }
     const int nv = (int)min((int64_t)(ZW_MAXV + 1), v1 - v0);
     const int rows = maxy - miny + 1;
-    __syncthreads();   // the previous polygon is done with shared memory
-    if (tid == 0) {
-      s_defer = 0; s_count = 0; s_ncand = 0; s_cells = 0; s_nspans = 0; s_below = 0; s_inside = 0;
-      s_kmin = ZS_EMPTY; s_kmax = 0u; s_lowest = ZS_EMPTY; s_highest1 = 0u;
-    }
-    if (rows <= 0 || nv == 0) {   // nothing under the polygon
+    // polygons without rows here (another stripe, outside the raster) and polygons for the
+    // generic kernel leave before any shared memory is touched: no barrier for them
+    if (rows <= 0 || nv == 0) {
       if (tid == 0) { out[p] = nanf_; area[p] = 0; }
       continue;
     }
     if (nv > ZW_MAXV || nv < 2 || rows > ZS_MAXROWS) {
       if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
       continue;
+    }
+    __syncthreads();   // the previous polygon is done with shared memory
+    if (tid == 0) {
+      s_defer = 0; s_count = 0; s_ncand = 0; s_cells = 0; s_nspans = 0; s_below = 0; s_inside = 0;
+      s_kmin = ZS_EMPTY; s_kmax = 0u; s_lowest = ZS_EMPTY; s_highest1 = 0u;
     }
     for (int i = tid; i < nv; i += ZS_THREADS) {
       s_px[i] = P.px[v0 + i];

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--polygons", type=int, default=100000)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--only", default="")
+    ap.add_argument("--profile-p90", action="store_true", help="cProfile of the striped p90 call on rank 0")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
 
@@ -134,6 +135,17 @@ def main():
             measure("zonal_%s_%dpolys" % ("p90" if q else stat, len(polys)),
                     lambda stat=stat, q=q: parallel.zonal_striped(soup, r, nodata, bbox, n, (r0, r1), stat, q),
                     px, px * 4)
+        if args.profile_p90:
+            import cProfile
+            import pstats
+
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(5):
+                parallel.zonal_striped(soup, r, nodata, bbox, n, (r0, r1), "percentile", 90.0)
+            pr.disable()
+            if rank == 0:
+                pstats.Stats(pr).sort_stats("tottime").print_stats(22)
     if world > 1:
         dist.destroy_process_group()
 
