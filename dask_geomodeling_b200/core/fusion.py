@@ -164,6 +164,8 @@ def _streamable_source(task):
 def _worth_streaming(sources):
     if not config.get("geomodeling.stream", True):
         return False
+    if int(config.get("geomodeling.device-cache-bytes", 0) or 0) > 0:
+        return False   # sources stay resident in HBM: nothing to pipeline after the first request
     first = sources[0]
     bands = first["bands"][1] - first["bands"][0]
     if any(kw["bands"][1] - kw["bands"][0] != bands or kw["height"] != first["height"]

@@ -49,6 +49,38 @@ def window_geometry(geo_transform, bbox, height, width):
     return col0, col_step, row0, row_step
 
 
+_RESIDENT = {}         # id(host array) -> DeviceArray of the whole array
+_RESIDENT_BYTES = [0]
+
+
+def _drop_resident(key, nbytes):
+    if _RESIDENT.pop(key, None) is not None:
+        _RESIDENT_BYTES[0] -= nbytes
+
+
+def resident_copy(array):
+    """The HBM copy of a MemorySource array when ``geomodeling.device-cache-bytes`` allows one
+    (uploaded on first use, dropped when the host array is garbage collected); else None."""
+    import weakref
+
+    budget = int(config.get("geomodeling.device-cache-bytes", 0) or 0)
+    if budget <= 0:
+        return None
+    key = id(array)
+    hit = _RESIDENT.get(key)
+    if hit is not None and hit.shape == array.shape and hit.dtype == array.dtype:
+        _native.STATS["resident_hits"] = _native.STATS.get("resident_hits", 0) + 1
+        return hit
+    if not array.flags.c_contiguous or _RESIDENT_BYTES[0] + array.nbytes > budget:
+        return None
+    copy = _native.DeviceArray.from_host(array)
+    _native.synchronize()
+    _RESIDENT[key] = copy
+    _RESIDENT_BYTES[0] += array.nbytes
+    weakref.finalize(array, _drop_resident, key, array.nbytes)
+    return copy
+
+
 def resample_window(array, bands, geo_transform, no_data_value, bbox, height, width, keep_on_device,
                     row_range=None):
     """Nearest-neighbour resample of ``array[bands[0]:bands[1]]`` into the request grid.
@@ -71,8 +103,20 @@ def resample_window(array, bands, geo_transform, no_data_value, bbox, height, wi
     out = _native.DeviceArray((n_bands, height, width), dtype)
     nodata_holder, nodata_ptr = _native.scalar_ptr(no_data_value, dtype)
     win_h, win_w = max(r_hi - r_lo, 0), max(c_hi - c_lo, 0)
+    resident = None
+    if win_h > 0 and win_w > 0 and n_bands > 0:
+        resident = resident_copy(array)
     if win_h == 0 or win_w == 0 or n_bands == 0:
         _native.check(lib.gm_fill(out.ptr, _native.dtype_code(dtype), nodata_ptr, out.size, stream))
+    elif resident is not None:
+        # the whole source is in HBM: one gather from it (no upload), same arithmetic
+        view = _native.DeviceArray((n_bands, src_h, src_w), dtype,
+                                   ptr=resident.ptr + b0 * src_h * src_w * dtype.itemsize, owner=resident)
+        src_desc = _native.as_gm_array(view)
+        dst_desc = _native.as_gm_array(out)
+        _native.check(lib.gm_resample_nn(
+            ctypes.byref(src_desc), ctypes.byref(dst_desc), nodata_ptr,
+            col0, col_step, row0, row_step, stream))
     else:
         item = dtype.itemsize
         exact = (

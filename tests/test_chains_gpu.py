@@ -141,3 +141,24 @@ def test_raster_tiler_equals_untiled(tile_size):
     stencil = raster.MovingMax(workloads.source(a, workloads.F32_MAX), 7)
     plain = stencil.get_data(**request)
     np.testing.assert_array_equal(raster.RasterTiler(stencil, [64, 50]).get_data(**request)["values"], plain["values"])
+
+
+def test_device_cache_serves_later_requests_from_hbm():
+    # geomodeling.device-cache-bytes: the MemorySource arrays are uploaded once, later requests
+    # (other windows included) gather from the resident copy and give the same results
+    size = 300
+    ints, floats = workloads.cfg2_arrays(size, chunk=128)
+    isdata, step = workloads.cfg2_views(ints, floats)
+    whole = workloads.request(size, size)
+    window = workloads.request(size, size)
+    window.update(bbox=(-20, 35, 210, 330), width=230, height=295)   # partly outside the source
+    expected = [step.get_data(**whole), step.get_data(**window), isdata.get_data(**window)]
+    before = _native.STATS.get("resident_hits", 0)
+    with config.set({"geomodeling.device-cache-bytes": 1 << 30}):
+        for _ in range(2):
+            got = [step.get_data(**whole), step.get_data(**window), isdata.get_data(**window)]
+            for g, e in zip(got, expected):
+                assert g["values"].dtype == e["values"].dtype
+                np.testing.assert_array_equal(g["values"], e["values"])
+                assert g["no_data_value"] == e["no_data_value"]
+    assert _native.STATS.get("resident_hits", 0) >= before + 8
