@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--temporal-frames", type=int, default=64, help="365 = cfg5")
     ap.add_argument("--temporal-size", type=int, default=4096, help="8192 = cfg5 (98 GB of float32 at 365 frames)")
     ap.add_argument("--temporal-stats", default="sum,max,mean,median")
+    ap.add_argument("--temporal-dtype", default="f4", choices=["f4", "i2"])
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
 
@@ -108,22 +109,29 @@ def main():
     # ---- temporal (cfg5 shape scaled: 64 x 4096 x 4096) ------------------------------------
     if not only or any(o.startswith(("temporal", "cumulative")) for o in only):
         T, m = args.temporal_frames, int(args.temporal_size * args.scale)
-        stack = torch.empty(T, m, m, device="cuda")
+        tdtype = args.temporal_dtype
+        tnodata = nodata if tdtype == "f4" else 32767
+        stack = torch.empty(T, m, m, device="cuda", dtype=torch.float32 if tdtype == "f4" else torch.int16)
         for t in range(T):   # frame by frame: no second stack-sized temporary
-            stack[t].uniform_(0, 100)
-            stack[t][torch.rand(m, m, device="cuda") < 0.03] = nodata
+            if tdtype == "f4":
+                stack[t].uniform_(0, 100)
+            else:
+                stack[t].random_(0, 3000)
+            stack[t][torch.rand(m, m, device="cuda") < 0.03] = tnodata
         sd = wrap(stack)
         from datetime import datetime, timedelta
 
         times = [datetime(2000, 1, 1) + timedelta(days=i) for i in range(T)]
         for stat in [x for x in args.temporal_stats.split(",") if x]:
-            out_dtype = "f4"
+            # dtype_for_statistic (utils.py:826-845): min/max keep the dtype, sums of integers are int32
+            out_dtype = "f4" if tdtype == "f4" or stat in ("mean", "median") else ("i2" if stat in ("min", "max") else "i4")
             kwargs = dict(mode="vals", start=times[-1], stop=None, frequency=None, timezone=None,
                           closed=None, label=None, dtype=out_dtype, statistic=stat)
-            measure("temporal_%s_f32_T%d" % (stat, T),
+            item = 4 if tdtype == "f4" else 2
+            measure("temporal_%s_%s_T%d" % (stat, "f32" if tdtype == "f4" else "i16", T),
                     lambda kwargs=kwargs: raster.TemporalAggregate.process(
-                        kwargs, {"time": times}, {"values": sd, "no_data_value": nodata}),
-                    T * m * m, (T + 1) * m * m * 4, iters=max(2, args.iters // 2))
+                        kwargs, {"time": times}, {"values": sd, "no_data_value": tnodata}),
+                    T * m * m, T * m * m * item + m * m * np.dtype(out_dtype).itemsize, iters=max(2, args.iters // 2))
         del stack, sd
         torch.cuda.empty_cache()
 
