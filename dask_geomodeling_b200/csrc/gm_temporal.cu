@@ -302,20 +302,44 @@ temporal_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata,
   const D fill = (STAT == GM_STAT_SUM || STAT == GM_STAT_COUNT) ? (D)0 : DMax<D>::value();
   for (int g = 0; g < n_bins; ++g) {
     const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
-    W acc[VEC];
+    // Integer sources: minima / maxima are taken in the source dtype and sums that the reference
+    // accumulates in float64 are accumulated in int64 -- both exact, hence identical to the
+    // sequential float arithmetic, without one int -> float conversion per sample.
+    constexpr bool INT_EXACT = std::is_integral<S>::value &&
+        (STAT == GM_STAT_MIN || STAT == GM_STAT_MAX || (STAT == GM_STAT_SUM && std::is_same<W, double>::value));
+    // sums in int64; extremes in int (sources below 4 bytes) or the source dtype itself
+    typedef typename std::conditional<(sizeof(S) < 4), int, S>::type Extreme;
+    typedef typename std::conditional<STAT == GM_STAT_SUM, long long, Extreme>::type IntAcc;
+    typedef typename std::conditional<INT_EXACT, IntAcc, W>::type A;
+    A acc[VEC];
     int cnt[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { acc[i] = (STAT == GM_STAT_MIN || STAT == GM_STAT_MAX) ? nan_<W>() : (W)0; cnt[i] = 0; }
+    for (int i = 0; i < VEC; ++i) {
+      if constexpr (INT_EXACT)
+        acc[i] = STAT == GM_STAT_MIN ? std::numeric_limits<A>::max()
+                                     : STAT == GM_STAT_MAX ? std::numeric_limits<A>::lowest() : (A)0;
+      else acc[i] = (STAT == GM_STAT_MIN || STAT == GM_STAT_MAX) ? nan_<W>() : (W)0;
+      cnt[i] = 0;
+    }
     auto take = [&](const V& x) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const S v = x.v[i];
-        const W w = (W)v;
-        const bool valid = !(has_nodata && v == nodata) && (w == w);
-        if (STAT == GM_STAT_SUM || STAT == GM_STAT_MEAN) acc[i] = valid ? acc[i] + w : acc[i];
-        if (STAT == GM_STAT_MIN) acc[i] = (valid && (acc[i] != acc[i] || w < acc[i])) ? w : acc[i];
-        if (STAT == GM_STAT_MAX) acc[i] = (valid && (acc[i] != acc[i] || w > acc[i])) ? w : acc[i];
-        if (STAT == GM_STAT_COUNT || STAT == GM_STAT_MEAN) cnt[i] += valid ? 1 : 0;
+        if constexpr (INT_EXACT) {
+          const bool valid = !(has_nodata && v == nodata);
+          const A w = (A)v;
+          if (STAT == GM_STAT_SUM) acc[i] += valid ? w : (A)0;
+          if (STAT == GM_STAT_MIN) acc[i] = valid ? (w < acc[i] ? w : acc[i]) : acc[i];
+          if (STAT == GM_STAT_MAX) acc[i] = valid ? (w > acc[i] ? w : acc[i]) : acc[i];
+          if (STAT != GM_STAT_SUM) cnt[i] += valid ? 1 : 0;
+        } else {
+          const W w = (W)v;
+          const bool valid = !(has_nodata && v == nodata) && (w == w);
+          if (STAT == GM_STAT_SUM || STAT == GM_STAT_MEAN) acc[i] = valid ? acc[i] + w : acc[i];
+          if (STAT == GM_STAT_MIN) acc[i] = (valid && (acc[i] != acc[i] || w < acc[i])) ? w : acc[i];
+          if (STAT == GM_STAT_MAX) acc[i] = (valid && (acc[i] != acc[i] || w > acc[i])) ? w : acc[i];
+          if (STAT == GM_STAT_COUNT || STAT == GM_STAT_MEAN) cnt[i] += valid ? 1 : 0;
+        }
       }
     };
     int f = f0;
@@ -324,8 +348,22 @@ temporal_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata,
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
         x[u] = load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f + u] * plane + pix));
+      if constexpr (INT_EXACT && STAT == GM_STAT_SUM && sizeof(S) <= 2) {
+        // four samples of at most 16 bits add up in 32 bits; one 64-bit add per round
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) take(x[u]);
+        for (int i = 0; i < VEC; ++i) {
+          int part = 0;
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const S v = x[u].v[i];
+            part += (has_nodata && v == nodata) ? 0 : (int)v;
+          }
+          acc[i] += part;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) take(x[u]);
+      }
     }
     for (; f < f1; ++f)
       take(load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f] * plane + pix)));
@@ -335,7 +373,8 @@ temporal_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata,
       W result;
       if (STAT == GM_STAT_COUNT) result = (W)(int64_t)cnt[i];
       else if (STAT == GM_STAT_MEAN) result = (W)((double)acc[i] / (double)(int64_t)cnt[i]);
-      else result = acc[i];
+      else if (INT_EXACT && STAT != GM_STAT_SUM && cnt[i] == 0) result = nan_<W>();   // no valid sample
+      else result = (W)acc[i];
       const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
       o[i] = (f1 > f0 && finite) ? cast_out<W, D>(result) : fill;
     }
