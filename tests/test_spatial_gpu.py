@@ -94,3 +94,41 @@ def test_blocks_through_get_data():
     ]:
         got = view.get_data(**req)
         np.testing.assert_array_equal(got["values"], oracle(a))
+
+
+# output shapes around the kernels' tile and strip edges: one cell, widths that are not
+# multiples of four, one column more / less than a strip (124) or a tile (64, 114, 128, 256)
+EDGE_SHAPES = [(1, 1), (2, 3), (5, 7), (17, 123), (3, 124), (66, 125), (33, 129), (16, 257), (65, 64)]
+
+
+@pytest.mark.parametrize("shape", EDGE_SHAPES)
+def test_stencils_at_tile_edges(shape):
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    # HillShade: halo 1
+    values, nodata = dem((1, h + 2, w + 2), 11, nodata_fraction=0.05)
+    kwargs = dict(resolution=(1.0, 1.0), altitude=45.0, azimuth=315.0, fill=0)
+    expected, _ = R.hillshade(values, nodata, (1.0, 1.0), 45.0, 315.0, 0)
+    got = raster.HillShade.process({"values": values, "no_data_value": nodata}, kwargs)["values"]
+    assert got.shape == (1, h, w)
+    delta = np.abs(got.astype(int) - expected.astype(int))
+    assert delta.max() <= 1 and (delta > 0).sum() <= max(1, int(1e-3 * delta.size))
+    # MovingMax 11 and 3 (float32: the four-columns-per-thread kernel), int16 (one column)
+    for size, dtype in ((11, "f4"), (3, "f4"), (5, "i4"), (7, "i2")):
+        r = size // 2
+        values, nodata = dem((2, h + 2 * r, w + 2 * r), 12, dtype=dtype, nodata_fraction=0.3)
+        expected, _ = R.moving_max(values, nodata, size)
+        got = raster.MovingMax.process({"values": values, "no_data_value": nodata}, size)["values"]
+        np.testing.assert_array_equal(got, expected)
+    # Smooth size 5 (margin 5)
+    values, nodata = dem((1, h + 10, w + 10), 13)
+    expected, _ = R.smooth(values, nodata, (5.0, 5.0), 0, "exact")
+    got = raster.Smooth.process({"values": values, "no_data_value": nodata},
+                                dict(smooth_mode="exact", fill=0, size=[5.0, 5.0]))["values"]
+    np.testing.assert_array_equal(got, expected)
+    # Dilate on bytes (packed kernel) and int16 (tiled kernel), two bands
+    for dtype in ("u1", "i2"):
+        cells = rng.integers(0, 6, (2, h + 2, w + 2)).astype(dtype)
+        expected, _ = R.dilate(cells, R.dtype_max(dtype), [3, 1, 5])
+        got = raster.Dilate.process({"values": cells, "no_data_value": R.dtype_max(dtype)}, [3, 1, 5])["values"]
+        np.testing.assert_array_equal(got, expected)
