@@ -616,17 +616,25 @@ constexpr int ZW_SUM = 1, ZW_MIN = 2, ZW_MAX = 4, ZW_ALL = 7;
 
 template <typename T, int NEED>
 struct WarpReduce {
-  static constexpr int VEC = 16 / (int)sizeof(T);
+  // a lane's load: 16 bytes of 4- and 8-byte cells, 8 bytes of 2-byte cells, 4 bytes of
+  // 1-byte cells -- four cells per lane (two doubles), so that a row of ~100 cells is one
+  // load per lane with at most 3 edge cells either side
+  static constexpr int QBYTES = sizeof(T) >= 4 ? 16 : sizeof(T) == 2 ? 8 : 4;
+  static constexpr int VEC = QBYTES / (int)sizeof(T);
+  typedef typename std::conditional<QBYTES == 16, uint4,
+          typename std::conditional<QBYTES == 8, uint2, unsigned>::type>::type Quad;
+  // integer cells: the sum is exact in int64 (no int -> double conversion per cell)
+  typedef typename std::conditional<std::is_integral<T>::value, long long, double>::type Sum;
   const T* raster; int width; ActiveTest<T> active;
-  int count; long long cells; double sum; T vmin, vmax;
+  int count; long long cells; Sum sum; T vmin, vmax;
   __device__ __forceinline__ void reset() {
-    count = 0; cells = 0; sum = 0.0;
+    count = 0; cells = 0; sum = 0;
     vmin = std::numeric_limits<T>::max(); vmax = std::numeric_limits<T>::lowest();
   }
   __device__ __forceinline__ void take(T v) {
     if (active(v)) {
       ++count;
-      if (NEED & ZW_SUM) sum += (double)v;
+      if (NEED & ZW_SUM) sum += (Sum)v;
       if (NEED & ZW_MIN) vmin = tmin<T>(vmin, v);
       if (NEED & ZW_MAX) vmax = tmax<T>(vmax, v);
     }
@@ -678,7 +686,7 @@ struct WarpReduce {
           "@p add.s32 %3, %3, 1;\n\t}"
           : "=f"(vm), "+f"(lo), "+f"(hi), "+r"(count) : "f"(v), "f"(nd));
     }
-    if (NEED & ZW_SUM) sum += (double)vm;
+    if (NEED & ZW_SUM) sum += (Sum)vm;
     if (NEED & ZW_MIN) vmin = (T)lo;
     if (NEED & ZW_MAX) vmax = (T)hi;
   }
@@ -690,7 +698,7 @@ struct WarpReduce {
   // starts the loads of a batch, `consume` reduces them: the kernel issues batch i + 1
   // before it consumes batch i, so every warp computes under its own loads.
   static constexpr int PER = 2 * (VEC - 1);                     // edge cells per row at most
-  struct Batch { uint4 q[ZW_ROWS]; T edge; };
+  struct Batch { Quad q[ZW_ROWS]; T edge; };
   __device__ __forceinline__ bool edge_cell(int y0, const int* tab, int i, int64_t* at) const {
     const int b = i / PER, c = i - b * PER;
     const bool head = c < VEC - 1;
@@ -705,9 +713,9 @@ struct WarpReduce {
 #pragma unroll
     for (int b = 0; b < ZW_ROWS; ++b) {
       const int x = tab[64 + b] + VEC * lane;
-      B.q[b] = make_uint4(0u, 0u, 0u, 0u);
+      B.q[b] = Quad();
       if (x < tab[96 + b])
-        B.q[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x));
+        B.q[b] = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)(y0 + b) * width + x));
     }
     int64_t at;
     B.edge = T(0);
@@ -723,7 +731,7 @@ struct WarpReduce {
       longest = max(longest, xt - tab[64 + b]);
       if (x < xt) {
         T e[VEC];
-        memcpy(e, &B.q[b], 16);
+        memcpy(e, &B.q[b], QBYTES);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           if constexpr (F32_FAST && std::is_same<T, float>::value) take_f32(e[j]);
@@ -741,9 +749,9 @@ struct WarpReduce {
         for (int b = 0; b < ZW_ROWS; ++b) {
           const int x = tab[64 + b] + k;
           if (x < tab[96 + b]) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)(y0 + b) * width + x));
+            const Quad q = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)(y0 + b) * width + x));
             T e[VEC];
-            memcpy(e, &q, 16);
+            memcpy(e, &q, QBYTES);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) take(e[j]);
           }
@@ -931,7 +939,7 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
       if (NEED & ZW_MAX) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
     if (lane == 0) {
-      partial[p] = GmZonalPartial{count, vis.sum, vmin, vmax};
+      partial[p] = GmZonalPartial{count, (double)vis.sum, vmin, vmax};
       cells[p] = vis.cells;
     }
   }
@@ -1928,7 +1936,7 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
     GM_TRY(cudaMallocAsync(&dwork, sizeof(int) * (size_t)(np_ + 2), s));
     scratch_work = dwork;
     GM_TRY(cudaMemsetAsync(dwork, 0, 2 * sizeof(int), s));
-    const int vec = 16 / (int)sizeof(T);
+    const int vec = WarpReduce<T, ZW_ALL>::VEC;
     const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (uintptr_t)(vec - 1));
     const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
                             (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
@@ -2115,7 +2123,7 @@ static int run_zonal_partials_device(PolyUpload& u, const Staged& raster, const 
   const size_t smem_scan = scan_smem(u.dev.cap, PG_WARPS);
   if (smem_scan > 48 * 1024)
     GM_TRY(cudaFuncSetAttribute(zonal_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
-  const int vec = 16 / (int)sizeof(T);
+  const int vec = WarpReduce<T, ZW_ALL>::VEC;
   const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (uintptr_t)(vec - 1));
   const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
                           (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
