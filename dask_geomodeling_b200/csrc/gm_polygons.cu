@@ -1260,8 +1260,23 @@ constexpr int ZS_ROWS = 8;               // rows per warp and round of loads
 constexpr int ZS_MARGIN = 8;             // sample positions either side of the wanted rank (of 32)
 constexpr unsigned ZS_EMPTY = 0xffffffffu;
 
+// 32-bit sortable keys of the dtypes this kernel takes (float32 and integers up to 4 bytes)
+template <typename T> struct Key32 {
+  static __device__ __forceinline__ unsigned key(T v) {
+    return std::is_signed<T>::value ? ((unsigned)(int)v ^ 0x80000000u) : (unsigned)v;
+  }
+  static __device__ __forceinline__ T value(unsigned k) {
+    return std::is_signed<T>::value ? (T)(int)(k ^ 0x80000000u) : (T)k;
+  }
+};
+template <> struct Key32<float> {
+  static __device__ __forceinline__ unsigned key(float v) { return order_f32(v); }
+  static __device__ __forceinline__ float value(unsigned k) { return unorder_f32(k); }
+};
+
+template <typename T>
 __global__ void __launch_bounds__(ZS_THREADS, 3)
-zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, float nodata, int has_nodata,
+zonal_select_fast_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
                          int mis, int edge_scalar, int stat, double q, int capacity,
                          float* __restrict__ out, long long* __restrict__ area, int* __restrict__ work) {
   extern __shared__ __align__(16) unsigned char zs_smem[];
@@ -1276,6 +1291,10 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
   __shared__ int s_wsum[ZS_THREADS / 32];
   __shared__ int s_defer, s_count, s_ncand, s_blo, s_bhi, s_rlo, s_rhi, s_cells, s_nspans, s_below, s_inside;
   __shared__ unsigned s_kmin, s_kmax, s_lowest, s_highest1;
+  // four cells per lane and load whatever the dtype: 16 bytes of 4-byte cells, 8 of int16, 4 of bytes
+  constexpr int VEC = 4;
+  typedef typename std::conditional<sizeof(T) == 4, uint4,
+          typename std::conditional<sizeof(T) == 2, uint2, unsigned>::type>::type Quad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int maxx = P.width - 1;
   const float nanf_ = __int_as_float(0x7fc00000);
@@ -1356,9 +1375,10 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
               const int at = atomicAdd(&s_nspans, 1);
               if (at < ZS_MAXSPANS) {
                 const int64_t off = (int64_t)y * P.width + mis;
-                const int a0 = x0 - (int)((off + x0) & 3);
-                const int ae = xe + (int)((4 - ((off + xe) & 3)) & 3);
-                s_y[at] = y; s_x0[at] = x0; s_xe[at] = xe; s_base[at] = ae - a0;
+                // slots: the 4-key groups of the span's quads that overlap the span
+                const int a0 = x0 - (int)((off + x0) & (VEC - 1));
+                s_y[at] = y; s_x0[at] = x0; s_xe[at] = xe;
+                s_base[at] = ((xe - a0 + 3) & ~3) - ((x0 - a0) & ~3);
                 my_cells += xe - x0;
               } else {
                 bad = true;
@@ -1419,38 +1439,42 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
         a0[b] = 0; ae[b] = 0;
         if (r < spans) {
           const int64_t off = (int64_t)s_y[r] * P.width + mis;
-          a0[b] = s_x0[r] - (int)((off + s_x0[r]) & 3);
-          ae[b] = s_xe[r] + (int)((4 - ((off + s_xe[r]) & 3)) & 3);
+          a0[b] = s_x0[r] - (int)((off + s_x0[r]) & (VEC - 1));
+          ae[b] = s_xe[r] + (int)((VEC - ((off + s_xe[r]) & (VEC - 1))) & (VEC - 1));
         }
         widest = max(widest, ae[b] - a0[b]);
       }
-      for (int k = 4 * lane; k - 4 * lane < widest; k += 128) {
-        uint4 qv[ZS_ROWS];
+      for (int k = VEC * lane; k - VEC * lane < widest; k += 32 * VEC) {
+        Quad qv[ZS_ROWS];
 #pragma unroll
         for (int b = 0; b < ZS_ROWS; ++b) {
-          qv[b] = make_uint4(0u, 0u, 0u, 0u);
+          qv[b] = Quad();
           if (a0[b] + k < ae[b])
-            qv[b] = __ldg(reinterpret_cast<const uint4*>(raster + (int64_t)s_y[rb + b] * P.width + (a0[b] + k)));
+            qv[b] = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)s_y[rb + b] * P.width + (a0[b] + k)));
         }
 #pragma unroll
         for (int b = 0; b < ZS_ROWS; ++b) {
           if (a0[b] + k < ae[b]) {
             const int r = rb + b;
             const int x0 = s_x0[r], xe = s_xe[r];
-            float e[4];
-            memcpy(e, &qv[b], 16);
-            unsigned kk[4];
+            T e[VEC];
+            memcpy(e, &qv[b], sizeof(Quad));
+            unsigned kk[VEC];
             const unsigned len = (unsigned)(xe - x0), rel = (unsigned)(a0[b] + k - x0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < VEC; ++j) {
               const bool active = rel + j < len && !(has_nodata && e[j] == nodata);
-              const unsigned key = order_f32(e[j]);   // (the NaN 0x7fffffff alone maps to the sentinel)
+              const unsigned key = Key32<T>::key(e[j]);   // (the float NaN 0x7fffffff alone maps to the sentinel)
               my_count += active ? 1 : 0;
               kk[j] = active ? key : ZS_EMPTY;
               my_min = min(my_min, kk[j]);             // the sentinel is neutral for the minimum
               my_max1 = max(my_max1, kk[j] + 1u);      // ... and wraps to 0 here: largest key + 1
             }
-            *reinterpret_cast<uint4*>(keys + s_base[r] + k) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+            const int g0 = (x0 - a0[b]) & ~3, g1 = (xe - a0[b] + 3) & ~3;   // 4-key groups that overlap the span
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4)
+              if (VEC == 4 || (k + j >= g0 && k + j < g1))
+                *reinterpret_cast<uint4*>(keys + s_base[r] + (k + j - g0)) = make_uint4(kk[j], kk[j + 1], kk[j + 2], kk[j + 3]);
           }
         }
       }
@@ -1609,8 +1633,8 @@ zonal_select_fast_kernel(const PolyDev P, const float* __restrict__ raster, floa
       }
     }
     if (tid == 0) {
-      const float lo = unorder_f32(klo), hi = unorder_f32(khi);
-      out[p] = stat == GM_STAT_MEDIAN ? median_of<float>(lo, hi) : percentile_of<float>(lo, hi, part);
+      const T lo = Key32<T>::value(klo), hi = Key32<T>::value(khi);
+      out[p] = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
     }
   }
 }
@@ -1882,24 +1906,30 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   if (order_stat) {
     GM_TRY(cudaMallocAsync(&dlist, sizeof(int) * (size_t)(np_ + 2), s));
     scratch_list = dlist;
-    const bool fast = std::is_same<T, float>::value && !thresholds && out;
+    // float32 and integers up to 4 bytes; the all-ones key is the kernel's "no cell" mark, so a
+    // 4-byte integer raster qualifies only when the value with that key (the dtype maximum) is
+    // its no-data value
+    bool fast = sizeof(T) <= 4 && !thresholds && out;
+    if (std::is_integral<T>::value && sizeof(T) == 4)
+      fast = fast && has_nodata && nd == std::numeric_limits<T>::max();
     if (fast) {
       GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
       GM_TRY(cudaMemsetAsync(dlist, 0, 2 * sizeof(int), s));
-      const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & 3);
+      constexpr int svec = 4;   // the kernel's cells per load
+      const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (svec - 1));
       const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
-                              (((int64_t)u.dev.height * u.dev.width + mis) % 4) != 0;
+                              (((int64_t)u.dev.height * u.dev.width + mis) % svec) != 0;
       int dev = 0, smem_max = 0;
       GM_TRY(cudaGetDevice(&dev));
       GM_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
       // three blocks per SM: a third of the 227 KB minus the static tables (~15 k cells per polygon)
       const int dyn = (smem_max - 3 * 18 * 1024) / 3 / 16 * 16;
-      float ndf = 0.0f;
-      memcpy(&ndf, &nd, sizeof(float) < sizeof(T) ? sizeof(float) : sizeof(T));
-      GM_TRY(cudaFuncSetAttribute(zonal_select_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      zonal_select_fast_kernel<<<poly_grid(np_), ZS_THREADS, dyn, s>>>(
-          u.dev, (const float*)raster.dev, ndf, has_nodata, mis, edge_scalar, stat, q, dyn / 4,
-          (float*)dout, (long long*)darea, (int*)dlist);
+      if constexpr (sizeof(T) <= 4) {
+        GM_TRY(cudaFuncSetAttribute(zonal_select_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        zonal_select_fast_kernel<T><<<poly_grid(np_), ZS_THREADS, dyn, s>>>(
+            u.dev, (const T*)raster.dev, nd, has_nodata, mis, edge_scalar, stat, q, dyn / 4,
+            (float*)dout, (long long*)darea, (int*)dlist);
+      }
       GM_TRY(cudaGetLastError());
       count_launch();
       GM_TRY(cudaMemcpyAsync(&n_listed, dlist, sizeof(int), cudaMemcpyDeviceToHost, s));
