@@ -379,6 +379,11 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print on file
+    # descriptor 1 while the job runs (NCCL announces its version there) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     os.environ.setdefault("GM_DEVICE", str(local_rank))
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -513,7 +518,8 @@ def run_b200(args):
                 "sample": "first {} rows x {} cols of the same inputs, best of 3 ({:.2f} s)".format(
                     rows, size, best),
             }
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
