@@ -1,7 +1,11 @@
-from .base import RasterBlock  # NOQA
-from .elemwise import *  # NOQA
-from .misc import *  # NOQA
-from .sources import *  # NOQA
-from .spatial import *  # NOQA
-from .temporal import *  # NOQA
-from .parallelize import *  # NOQA
+"""Raster blocks of the CUDA path: element-wise and misc blocks (fused into single launches),
+stencils, temporal aggregation, in-memory sources and the request tiler."""
+from . import elemwise, misc, parallelize, sources, spatial, temporal
+from .base import RasterBlock
+
+__all__ = ["RasterBlock"]
+for _module in (elemwise, misc, sources, spatial, temporal, parallelize):
+    for _name in _module.__all__:
+        globals()[_name] = getattr(_module, _name)
+    __all__ += list(_module.__all__)
+del _module, _name
