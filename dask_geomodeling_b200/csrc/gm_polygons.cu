@@ -1897,7 +1897,10 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
     GM_TRY(cudaFuncSetAttribute(zonal_reduce_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_scan));
   }
   const bool order_stat = stat == GM_STAT_MEDIAN || stat == GM_STAT_PERCENTILE;
-  std::vector<long long> area(np_);
+  // covered cells per polygon on the host: straight into the caller's (page-locked) `covered`
+  std::vector<long long> area_store;
+  long long* area = reinterpret_cast<long long*>(covered);
+  if (order_stat && !area) { area_store.resize(np_); area = area_store.data(); }
   // order statistics: the deferred list (work[0] entries from work[2]) of the polygons the
   // fast kernel does not take -- all of them when it does not apply
   void* dlist = nullptr;
@@ -1953,9 +1956,8 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       GM_TRY(cudaGetLastError());
       count_launch();
     }
-    GM_TRY(cudaMemcpyAsync(area.data(), darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+    GM_TRY(cudaMemcpyAsync(area, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
     GM_TRY(cudaStreamSynchronize(s));
-    if (covered) for (int64_t p = 0; p < np_; ++p) covered[p] = area[p];
   }
 
   if (!order_stat || partial) {
