@@ -110,9 +110,16 @@ def optimize(graph, name):
     return out
 
 
-def build_expression(plan):
-    """Expression DAG (raster/_program.Node) of a fused group."""
-    from ..raster._program import Leaf
+def build_expression(plan, n_leaves=None, extra_leaves=None):
+    """Expression DAG (raster/_program.Node) of a fused group.
+
+    ndarray literals of math / comparison / logic tasks are raster operands
+    (raster/elemwise.py:235-299 accepts them like the reference): each becomes an extra
+    leaf without a no data value, numbered from ``n_leaves`` on and appended to
+    ``extra_leaves``; without that list such a group raises FusionLimit."""
+    import numpy as np
+
+    from ..raster._program import FusionLimit, Leaf
 
     nodes = plan["nodes"]
     built = {}
@@ -127,6 +134,11 @@ def build_expression(plan):
                 operands.append(build(value))
             elif kind == "leaf":
                 operands.append(Leaf(value))
+            elif isinstance(value, np.ndarray) and getattr(func, "_gm_array_operands", False):
+                if extra_leaves is None or n_leaves is None:
+                    raise FusionLimit("array operand in a fused group")
+                operands.append(Leaf(n_leaves + len(extra_leaves)))
+                extra_leaves.append(value)
             else:
                 operands.append(value)
         built[key] = func._gm_lower(operands)
@@ -203,7 +215,7 @@ def streamed_fused_process(plan, *sources):
     leaf_types = [(np.dtype(kw["dtype"]), kw["fillvalue"].item()) for kw in sources]
     try:
         prog, compiler, results = _program.compile_expression([build_expression(plan)], leaf_types)
-    except _program.FusionLimit:
+    except (_program.FusionLimit, KeyError, NotImplementedError, TypeError):
         return fallback()
     out_dtype = results[0].dtype
     out = _native.pinned_empty((bands, height, width), out_dtype)
@@ -284,11 +296,23 @@ def fused_process(plan, *leaf_data):
     if all(_payload_is_raster(d) for d in leaf_data):
         try:
             leaves = [(d["values"], d.get("no_data_value")) for d in leaf_data]
+            arrays = plan.get("array_operands")
+            if arrays is None:
+                # ndarray operands of the group (found once per plan; they are literals of
+                # the graph, so their identity is part of the plan)
+                arrays = []
+                expression = build_expression(plan, len(leaves), arrays)
+                plan["array_operands"] = arrays
+            else:
+                expression = None
+            leaves += [(a, None) for a in arrays]
             key = _plan_key(plan, leaves)
             compiled = _compiled_plans.get(key) if key is not None else None
             if compiled is None:
+                if expression is None:
+                    expression = build_expression(plan, len(leaf_data), [])
                 compiled = _program.compile_expression(
-                    [build_expression(plan)], [(v.dtype, nd) for v, nd in leaves])
+                    [expression], [(v.dtype, nd) for v, nd in leaves])
                 if key is not None:
                     if len(_compiled_plans) >= 256:
                         _compiled_plans.pop(next(iter(_compiled_plans)))
@@ -297,6 +321,10 @@ def fused_process(plan, *leaf_data):
             return {"values": values, "no_data_value": nodata}
         except _program.FusionLimit:
             pass  # too large for one program: evaluate block by block below
+        except (KeyError, NotImplementedError, TypeError):
+            # an operand form the fused lowering does not know: the blocks' own process
+            # functions below decide (and raise the reference's errors where it would)
+            pass
 
     cache = {}
 

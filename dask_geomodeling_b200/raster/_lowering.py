@@ -62,6 +62,7 @@ def math_process(name):
 
     math_process_func.__name__ = name + "_process"
     math_process_func._gm_lower = lower
+    math_process_func._gm_array_operands = True   # ndarray literals are raster operands
     return math_process_func
 
 

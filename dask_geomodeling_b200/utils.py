@@ -462,7 +462,17 @@ def geometry_rings(geometry):
         rings = [_ring(np.asarray(geometry.exterior.coords)[:, :2])]
         rings.extend(_ring(np.asarray(r.coords)[:, :2]) for r in geometry.interiors)
         return rings
-    return []
+    kind = getattr(geometry, "geom_type", type(geometry).__name__)
+    if kind in ("Point", "MultiPoint"):
+        # no area: nothing to scan-convert.  AggregateRaster samples such features at the cell
+        # that contains them (the cell GDAL's point burn would label); rasterize_geoseries
+        # refuses them (see there)
+        return []
+    # GDAL burns lines with its own Bresenham variant (GDALdllImageLine); that rule is not
+    # part of this build, and dropping the feature silently would be wrong
+    raise NotImplementedError(
+        "geometries of type '{}' are not supported by the CUDA rasteriser "
+        "(polygons and multipolygons only)".format(kind))
 
 
 def point_in_rings(rings, x, y):
@@ -498,7 +508,12 @@ class PolygonSoup(object):
     def __init__(self, geometries):
         xy, ring_offsets, poly_offsets = [], [0], [0]
         n_vertices = 0
+        # features without area (points) hold no rings; consumers that cannot sample them
+        # (rasterize_geoseries) check this flag instead of dropping them silently
+        self.has_points = False
         for geometry in geometries:
+            if getattr(geometry, "geom_type", None) in ("Point", "MultiPoint"):
+                self.has_points = True
             for ring in geometry_rings(geometry):
                 xy.append(ring)
                 n_vertices += len(ring)
@@ -516,6 +531,7 @@ class PolygonSoup(object):
         """The soup of the polygons `ids` (in that order); index arithmetic only."""
         ids = np.asarray(ids, dtype=np.int64)
         sub = PolygonSoup([])
+        sub.has_points = self.has_points
         if len(ids) == 0:
             return sub
         ring_a, ring_n = self.poly_offsets[ids], self.poly_offsets[ids + 1] - self.poly_offsets[ids]
@@ -648,6 +664,9 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None,
         soup = PolygonSoup(geoseries.values)
     elif len(positions) != soup.n_polygons:
         soup = soup.subset(positions)
+    if soup.has_points:
+        raise NotImplementedError(
+            "point geometries cannot be burned by the CUDA rasteriser (polygons only)")
     burn = (
         np.ones(soup.n_polygons, dtype=dtype)
         if values is None

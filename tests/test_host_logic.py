@@ -110,3 +110,32 @@ def test_plan_keys_identify_fused_groups():
     assert fusion._plan_key(fusion.optimize(graph2, name2)[name2][1], leaves) != key
     assert fusion._freeze(np.arange(3)) == fusion._freeze(np.arange(3)) != fusion._freeze(np.arange(4))
     assert fusion._freeze(float("nan")) == fusion._freeze(float("nan"))
+
+
+def test_fused_group_with_an_ndarray_operand():
+    """BaseMath accepts ndarray operands; inside a fused group they become extra
+    leaves (the lowering used to raise KeyError)."""
+    from dask_geomodeling_b200.raster import _program
+
+    a, _ = workloads.cfg1_arrays(8)
+    src = workloads.source(a, workloads.F32_MAX)
+    ones = np.ones((1, 8, 8), "f4")
+    view = raster.Add(raster.Multiply(src, 2.0), ones)
+    graph, name = view.get_compute_graph(**workloads.request(8, 8))
+    fused = fusion.optimize(graph, name)
+    assert fused[name][0] in (fusion.fused_process, fusion.streamed_fused_process)
+    plan = fused[name][1]
+    with pytest.raises(_program.FusionLimit):
+        fusion.build_expression(plan)                    # no place to put the array
+    extra = []
+    expression = fusion.build_expression(plan, 1, extra)
+    assert len(extra) == 1 and extra[0] is ones
+    prog, _, results = _program.compile_expression(
+        [expression], [(np.dtype("f4"), workloads.F32_MAX), (ones.dtype, None)])
+    assert prog.n_inputs == 2 and results[0].dtype == np.float32
+    # bins of Classify stay literals (they are not raster operands)
+    view = raster.Classify(raster.Multiply(src, 2.0), np.array([10.0, 20.0]))
+    graph, name = view.get_compute_graph(**workloads.request(8, 8))
+    extra = []
+    fusion.build_expression(fusion.optimize(graph, name)[name][1], 1, extra)
+    assert extra == []

@@ -1,0 +1,573 @@
+"""The reference's own unit tests for the rows VERDICT r1 listed as untested on the CUDA
+path, replayed through the blocks' ``get_data`` (graph -> process -> C ABI -> kernels):
+
+* Rasterize / RasterizeWKT            reference tests/test_raster.py:1642-1815,
+                                      tests/test_raster_misc.py:257-297
+* utils.rasterize_geoseries branches  tests/test_utils.py:336-456
+* AggregateRaster(AboveThreshold)     tests/test_aggregate_raster.py:138-217, :357-394,
+                                      :443-534, :590-643
+* MemorySource window requests        tests/test_raster_sources.py:68-171
+
+Expected values are the ones the reference's tests assert.  Cases that need a coordinate
+transformation (EPSG:4326 / EPSG:3857 variants) are not replayed: this build has no PROJ.
+"""
+from datetime import datetime as Datetime
+from datetime import timedelta as Timedelta
+
+import numpy as np
+import pandas as pd
+import pytest
+from numpy.testing import assert_almost_equal, assert_array_equal
+
+from dask_geomodeling_b200 import raster, utils
+from dask_geomodeling_b200.geometry import AggregateRaster, AggregateRasterAboveThreshold
+from dask_geomodeling_b200.raster import MemorySource
+from dask_geomodeling_b200.utils import box
+
+from mocks import MockGeometry, MockRaster
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------
+# Rasterize (tests/test_raster.py:1642-1815)
+# ---------------------------------------------------------------------------------------
+
+POINT_REQUEST = dict(mode="vals", width=1, height=1, bbox=(0, 0, 0, 0), projection="EPSG:3857")
+VALS_REQUEST = dict(mode="vals", width=2, height=3, bbox=(0, 0, 2, 3), projection="EPSG:3857")
+SQUARES = [
+    ((0.0, 1.0), (0.0, 2.0), (1.0, 2.0), (1.0, 1.0)),       # 1 pixel inside
+    ((10.0, 2.0), (10.0, 3.0), (20.0, 3.0), (20.0, 2.0)),   # outside
+    ((1.0, 2.0), (1.0, 13.0), (12.0, 13.0), (12.0, 2.0)),   # partially inside
+]
+PROPERTIES = [{"id": x, "value": x / 3} for x in (51, 212, 512)]
+PIXEL = np.array(((0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)))
+
+
+@pytest.fixture
+def geometry_source():
+    return MockGeometry(SQUARES, PROPERTIES)
+
+
+def test_rasterize_vals_request(geometry_source):
+    data = raster.Rasterize(geometry_source, "id").get_data(**VALS_REQUEST)
+    values = data["values"][0, ::-1]   # invert the vertical axis: x, y correspond to j, i
+    assert values.dtype == np.int32
+    assert values[1, 0] == 51
+    assert values[2, 1] == 512
+    assert np.sum(values == data["no_data_value"]) == 4
+
+
+def test_rasterize_overlapping_last_on_top():
+    squares = [
+        ((0.0, 0.0), (2.0, 0.0), (2.0, 3.0), (0.0, 3.0)),   # full bbox
+        ((0.0, 1.0), (0.0, 2.0), (1.0, 2.0), (1.0, 1.0)),   # 1 pixel
+    ]
+    values = raster.Rasterize(MockGeometry(squares), "id").get_data(**VALS_REQUEST)["values"][0]
+    assert values[1, 0] == 1
+    assert np.sum(values == 0) == 5
+
+
+@pytest.mark.parametrize("offset", [0.0, 0.49, 0.51, 1.0])
+def test_rasterize_shifting_pixel(offset):
+    data = raster.Rasterize(MockGeometry([PIXEL + [offset, 0.0]]), "id").get_data(**VALS_REQUEST)
+    assert data["values"][0, 2, 0 if offset < 0.5 else 1] == 0
+    assert np.sum(data["values"] == 0) == 1
+    data = raster.Rasterize(MockGeometry([PIXEL + [0.0, offset]]), "id").get_data(**VALS_REQUEST)
+    assert data["values"][0, 2 if offset < 0.5 else 1, 0] == 0
+    assert np.sum(data["values"] == 0) == 1
+
+
+def test_rasterize_point_request():
+    data = raster.Rasterize(MockGeometry([]), "id").get_data(**POINT_REQUEST)
+    assert data["values"].tolist() == [[[data["no_data_value"]]]]
+    data = raster.Rasterize(MockGeometry([PIXEL, PIXEL]), "id").get_data(**POINT_REQUEST)
+    assert data["values"].tolist() == [[[1]]]
+    view = raster.Rasterize(MockGeometry([PIXEL, PIXEL], [{"id": x} for x in (51, 212)]), "id")
+    assert view.get_data(**POINT_REQUEST)["values"].tolist() == [[[212]]]
+
+
+def test_rasterize_meta_time(geometry_source):
+    view = raster.Rasterize(geometry_source, "id")
+    assert view.get_data(mode="time")["time"] == [Datetime(1970, 1, 1)]
+    assert view.get_data(mode="meta")["meta"] == [None]
+    assert not view.temporal
+
+
+def test_rasterize_limit(geometry_source):
+    data = raster.Rasterize(geometry_source, "id", limit=1).get_data(**VALS_REQUEST)
+    assert np.sum(data["values"] == data["no_data_value"]) == 5
+
+
+def test_rasterize_id_as_uint(geometry_source):
+    data = raster.Rasterize(geometry_source, column_name="id", dtype="uint8").get_data(**VALS_REQUEST)
+    values = data["values"][0, ::-1]
+    assert values.dtype == np.uint8
+    assert data["no_data_value"] == 255
+    assert values[1, 0] == np.uint8(51)
+    assert values[2, 1] == np.array(512).astype(np.uint8)
+    assert np.sum(values == data["no_data_value"]) == 4
+
+
+def test_rasterize_value(geometry_source):
+    data = raster.Rasterize(geometry_source, column_name="value", dtype="float").get_data(**VALS_REQUEST)
+    values = data["values"][0, ::-1]
+    assert values.dtype == np.float64
+    assert values[1, 0] == 51 / 3
+    assert values[2, 1] == 512 / 3
+    assert np.sum(values == data["no_data_value"]) == 4
+
+
+def test_rasterize_value_as_float16(geometry_source):
+    data = raster.Rasterize(geometry_source, column_name="value", dtype="float16").get_data(**VALS_REQUEST)
+    values = data["values"][0, ::-1]
+    assert values.dtype == np.float16
+    assert values[1, 0] == np.float16(51 / 3)
+    assert values[2, 1] == np.float16(512 / 3)
+    assert np.sum(values == data["no_data_value"]) == 4
+
+
+def test_rasterize_bool_and_missing_column(geometry_source):
+    data = raster.Rasterize(geometry_source).get_data(**VALS_REQUEST)
+    assert data["values"].dtype == bool and data["no_data_value"] is None
+    assert data["values"].sum() == 2
+    data = raster.Rasterize(geometry_source, "nonexistent").get_data(**VALS_REQUEST)
+    assert (data["values"] == data["no_data_value"]).all()
+
+
+def test_rasterize_feeds_a_fused_chain(geometry_source):
+    """Rasterize -> IsData / Clip: the burned raster flows into the element-wise evaluator."""
+    burned = raster.Rasterize(geometry_source, "id")
+    got = raster.IsData(burned).get_data(**VALS_REQUEST)["values"]
+    assert got.dtype == bool and got.sum() == 2
+    src = MemorySource(np.arange(6, dtype="f4").reshape(1, 3, 2), 99.0, "EPSG:3857", 1.0, (0, 3))
+    clipped = raster.Clip(src, burned).get_data(**VALS_REQUEST)
+    expected = np.full((1, 3, 2), 99.0, "f4")
+    expected[0, 0, 1], expected[0, 1, 0] = 1.0, 2.0
+    assert_array_equal(clipped["values"], expected)
+
+
+# ---------------------------------------------------------------------------------------
+# RasterizeWKT (tests/test_raster_misc.py:257-297), EPSG:28992 variant
+# ---------------------------------------------------------------------------------------
+
+WKT_VALS_REQUEST = dict(mode="vals", start=None, stop=None, width=4, height=6,
+                        bbox=(135000, 456000 - 3, 135000 + 2, 456000), projection="EPSG:28992")
+WKT_POINT_REQUEST = dict(mode="vals", start=None, stop=None, width=1, height=1,
+                         bbox=(135001, 455999, 135001, 455999), projection="EPSG:28992")
+
+
+def _box_wkt(x1, y1, x2, y2):
+    return "POLYGON (({2} {1}, {2} {3}, {0} {3}, {0} {1}, {2} {1}))".format(x1, y1, x2, y2)
+
+
+def test_rasterize_wkt_vals():
+    view = raster.RasterizeWKT(_box_wkt(135000.5, 455998, 135001.5, 455999.5), "EPSG:28992")
+    actual = view.get_data(**WKT_VALS_REQUEST)
+    assert actual["values"].dtype == bool and actual["no_data_value"] is None
+    assert actual["values"][0].astype(int).tolist() == [
+        [0, 0, 0, 0],
+        [0, 1, 1, 0],
+        [0, 1, 1, 0],
+        [0, 1, 1, 0],
+        [0, 0, 0, 0],
+        [0, 0, 0, 0],
+    ]
+
+
+def test_rasterize_wkt_vals_no_intersection():
+    view = raster.RasterizeWKT(_box_wkt(135004, 455995, 135004.5, 455996), "EPSG:28992")
+    assert not view.get_data(**WKT_VALS_REQUEST)["values"].any()
+
+
+@pytest.mark.parametrize("bbox,expected", [
+    [(135000.5, 455998, 135001.5, 455999.5), True],
+    [(135000.5, 455998, 135000.9, 455998.9), False],
+])
+def test_rasterize_wkt_point(bbox, expected):
+    view = raster.RasterizeWKT(_box_wkt(*bbox), "EPSG:28992")
+    assert view.get_data(**WKT_POINT_REQUEST)["values"].tolist() == [[[expected]]]
+
+
+# ---------------------------------------------------------------------------------------
+# utils.rasterize_geoseries (tests/test_utils.py:336-456)
+# ---------------------------------------------------------------------------------------
+
+BOX = dict(bbox=(0, 0, 10, 10), projection="EPSG:28992", width=10, height=10)
+POINT_IN = dict(bbox=(3, 3, 3, 3), projection="EPSG:28992", width=1, height=1)
+POINT_OUT = dict(bbox=(5, 5, 5, 5), projection="EPSG:28992", width=1, height=1)
+
+
+@pytest.fixture
+def geoseries():
+    return pd.Series([box(2, 2, 4, 4), box(6, 6, 8, 8)], dtype=object)
+
+
+def test_geoseries_bool(geoseries):
+    values = utils.rasterize_geoseries(geoseries, **BOX)["values"]
+    assert values.dtype == bool
+    assert values[0, 6:8, 2:4].all() and values[0, 2:4, 6:8].all()   # y axis points north
+    assert values.sum() == 2 * 2 * 2
+
+
+def test_geoseries_point(geoseries):
+    got = utils.rasterize_geoseries(geoseries, **POINT_IN)
+    assert got["values"].shape == (1, 1, 1) and got["values"].all()
+    got = utils.rasterize_geoseries(geoseries, **POINT_OUT)
+    assert got["values"].shape == (1, 1, 1) and not got["values"].any()
+
+
+def test_geoseries_none_geometry(geoseries):
+    geoseries.iloc[1] = None
+    assert utils.rasterize_geoseries(geoseries, **BOX)["values"].sum() == 2 * 2
+
+
+def test_geoseries_int(geoseries):
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1, 2]), **BOX)
+    values = got["values"]
+    assert values.dtype == np.int32
+    assert (values[0, 6:8, 2:4] == 1).all() and (values[0, 2:4, 6:8] == 2).all()
+    assert (values != got["no_data_value"]).sum() == 2 * 2 * 2
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1, 2]), **POINT_IN)
+    assert got["values"].shape == (1, 1, 1) and got["values"][0, 0, 0] == 1
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1, 2]), **POINT_OUT)
+    assert got["values"][0, 0, 0] == got["no_data_value"]
+
+
+def test_geoseries_float(geoseries):
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1.2, 2.4]), **BOX)
+    values = got["values"]
+    assert values.dtype == np.float64
+    assert (values[0, 6:8, 2:4] == 1.2).all() and (values[0, 2:4, 6:8] == 2.4).all()
+    assert (values != got["no_data_value"]).sum() == 2 * 2 * 2
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1.2, 2.4]), **POINT_IN)
+    assert got["values"][0, 0, 0] == 1.2
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1.2, 2.4]), **POINT_OUT)
+    assert got["values"][0, 0, 0] == got["no_data_value"]
+
+
+def test_geoseries_float_nan_inf(geoseries):
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([np.nan, np.inf]), **BOX)
+    assert got["values"].dtype == np.float64
+    assert (got["values"] != got["no_data_value"]).sum() == 0
+
+
+def test_geoseries_bool_values(geoseries):
+    values = utils.rasterize_geoseries(geoseries, values=pd.Series([True, False]), **BOX)["values"]
+    assert values.dtype == bool
+    assert values[0, 6:8, 2:4].all() and not values[0, 2:4, 6:8].any()
+    assert values.sum() == 2 * 2
+    values = utils.rasterize_geoseries(geoseries, values=pd.Series([False, False]), **BOX)["values"]
+    assert values.dtype == bool and values.sum() == 0
+
+
+def test_geoseries_categorical(geoseries):
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1, 2], dtype="category"), **BOX)
+    assert got["values"].dtype == np.int32
+    assert (got["values"][0, 2:4, 6:8] == 2).all()
+    got = utils.rasterize_geoseries(geoseries, values=pd.Series([1.2, 2.4], dtype="category"), **BOX)
+    assert got["values"].dtype == np.float64
+    assert (got["values"][0, 6:8, 2:4] == 1.2).all()
+
+
+def test_geoseries_rejects_lines_loudly():
+    class LineString(object):
+        geom_type = "LineString"
+        is_empty = False
+        coords = [(1, 1), (8, 8)]
+
+    with pytest.raises(NotImplementedError):
+        utils.rasterize_geoseries(pd.Series([LineString()], dtype=object), **BOX)
+
+
+# ---------------------------------------------------------------------------------------
+# AggregateRaster (tests/test_aggregate_raster.py)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.fixture
+def constant_raster():
+    return MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=1)
+
+
+@pytest.fixture
+def range_raster():
+    return MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=1,
+                      value=np.indices((10, 10))[0].astype(float))
+
+
+@pytest.fixture
+def square_source():
+    return MockGeometry(polygons=[((2.0, 2.0), (8.0, 2.0), (8.0, 8.0), (2.0, 8.0))], properties=[{"id": 1}])
+
+
+@pytest.fixture
+def geometry_request():
+    return dict(mode="intersects", projection="EPSG:3857", geometry=box(0, 0, 10, 10))
+
+
+@pytest.mark.parametrize("statistic,expected", [
+    ("sum", 162.0), ("count", 36.0), ("mean", 4.5), ("min", 2.0), ("max", 7.0), ("median", 4.5),
+    ("p75", 6.0),
+])
+def test_statistics(range_raster, square_source, geometry_request, statistic, expected):
+    geometry_request["start"] = Datetime(2018, 1, 1)
+    geometry_request["stop"] = Datetime(2018, 1, 1, 3)
+    view = AggregateRaster(source=square_source, raster=range_raster, statistic=statistic)
+    features = view.get_data(**geometry_request)["features"]
+    assert features.iloc[0]["agg"] == expected
+    assert features["agg"].dtype == np.float32
+
+
+@pytest.mark.parametrize("statistic,expected", [
+    ("sum", 0), ("count", 0), ("mean", np.nan), ("min", np.nan), ("max", np.nan), ("median", np.nan),
+    ("p75", np.nan),
+])
+def test_statistics_empty_and_partial_empty(square_source, geometry_request, statistic, expected):
+    nodata_raster = MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=1, value=255)
+    request = dict(geometry_request, start=Datetime(2018, 1, 1), stop=Datetime(2018, 1, 1, 3))
+    view = AggregateRaster(source=square_source, raster=nodata_raster, statistic=statistic)
+    assert_almost_equal(view.get_data(**request)["features"].iloc[0]["agg"], expected)
+
+    values = np.indices((10, 10), dtype=np.uint8)[0]
+    values[2:8, 2:8] = 255
+    partial = MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=1, value=values)
+    view = AggregateRaster(source=square_source, raster=partial, statistic=statistic)
+    assert_almost_equal(view.get_data(**geometry_request)["features"].iloc[0]["agg"], expected)
+
+
+def test_extensive_and_intensive_scaling(square_source, constant_raster, geometry_request):
+    # a coarser aggregation grid (auto_pixel_size): sums scale with the cell area, means do not
+    view1 = AggregateRaster(source=square_source, raster=constant_raster, statistic="sum")
+    view2 = AggregateRaster(square_source, constant_raster, statistic="sum", pixel_size=0.1,
+                            max_pixels=6 ** 2, auto_pixel_size=True)
+    agg1 = view1.get_data(**geometry_request)["features"].iloc[0]["agg"]
+    agg2 = view2.get_data(**geometry_request)["features"].iloc[0]["agg"]
+    assert agg1 == 36.0 and agg1 * (10 ** 2) == agg2
+    view1 = AggregateRaster(square_source, constant_raster, statistic="mean")
+    view2 = AggregateRaster(square_source, constant_raster, statistic="mean", pixel_size=0.1,
+                            max_pixels=6 ** 2, auto_pixel_size=True)
+    agg1 = view1.get_data(**geometry_request)["features"].iloc[0]["agg"]
+    assert agg1 == view2.get_data(**geometry_request)["features"].iloc[0]["agg"] == 1.0
+
+
+def test_auto_pixel_size_on_a_memory_source(geometry_request):
+    """auto_pixel_size makes the raster request coarser than the source (2 x 2 source cells per
+    aggregation cell): MemorySource answers with the nearest-neighbour gather."""
+    data = np.arange(100, dtype="f4").reshape(1, 10, 10)
+    src = MemorySource(data, -1.0, "EPSG:3857", 1.0, (0, 10))
+    source = MockGeometry([((2.0, 2.0), (8.0, 2.0), (8.0, 8.0), (2.0, 8.0))], [{"id": 1}])
+    view = AggregateRaster(source, src, statistic="sum", max_pixels=9, auto_pixel_size=True)
+    _, (_, request), _ = view.get_sources_and_requests(**geometry_request)
+    assert request["width"] == 3 and request["height"] == 3
+    got = view.get_data(**geometry_request)["features"].iloc[0]["agg"]
+    # centres of the 2 x 2 blocks fall on cell corners: GDAL's nearest neighbour takes the cell
+    # to the lower right of the corner (rows 3, 5, 7; columns 3, 5, 7), sums scale by 2 ** 2
+    expected = data[0][np.ix_([3, 5, 7], [3, 5, 7])].sum() * 4
+    assert got == np.float32(expected)
+
+
+def test_time_and_multi_frame_cells(square_source, geometry_request):
+    mock = MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=3)
+    view = AggregateRaster(source=square_source, raster=mock, statistic="mean")
+    request = dict(geometry_request)
+    request["start"], request["stop"] = mock.period
+    value = view.get_data(**request)["features"].iloc[0]["agg"][0]
+    assert len(value) == 3 and list(value) == [1.0, 1.0, 1.0]
+    request["stop"] = None
+    assert view.get_data(**request)["features"].iloc[0]["agg"] == 1.0
+    request["start"] = mock.period[0] + Timedelta(days=1)
+    request["stop"] = mock.period[1] + Timedelta(days=1)
+    assert np.isnan(view.get_data(**request)["features"].iloc[0]["agg"])
+
+
+def test_chained_aggregation(square_source, constant_raster, geometry_request):
+    first = AggregateRaster(source=square_source, raster=constant_raster, statistic="sum")
+    raster2 = MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=1, value=7)
+    chained = AggregateRaster(first, raster2, statistic="mean", column_name="agg2")
+    feature = chained.get_data(**geometry_request)["features"].iloc[0]
+    assert feature["agg"] == 36.0 and feature["agg2"] == 7.0
+
+
+def test_overlapping_geometries(constant_raster, geometry_request):
+    source = MockGeometry(
+        polygons=[((2.0, 2.0), (8.0, 2.0), (8.0, 8.0), (2.0, 8.0)),
+                  ((2.0, 2.0), (8.0, 2.0), (8.0, 5.0), (2.0, 5.0))],
+        properties=[{"id": 1}, {"id": 2}])
+    view = AggregateRaster(source=source, raster=constant_raster, statistic="sum")
+    assert view.get_data(**geometry_request)["features"]["agg"].values.tolist() == [36.0, 18.0]
+
+
+@pytest.mark.parametrize("agg", ["mean", "min", "max", "median", "p90.0"])
+def test_aggregate_percentile_one_empty(geometry_request, agg):
+    data = np.ones((1, 10, 10), dtype=np.uint8)
+    data[:, :5, :] = 255
+    src = MemorySource(data, 255, "EPSG:3857", pixel_size=1, pixel_origin=(0, 10))
+    source = MockGeometry(
+        polygons=[((2.0, 2.0), (4.0, 2.0), (4.0, 4.0), (2.0, 4.0)),
+                  ((6.0, 6.0), (8.0, 6.0), (8.0, 8.0), (6.0, 8.0))],
+        properties=[{"id": 1}, {"id": 2}])
+    result = AggregateRaster(source=source, raster=src, statistic=agg).get_data(**geometry_request)
+    assert result["features"]["agg"].values[0] == 1.0
+    assert np.isnan(result["features"]["agg"].values[1])
+
+
+def test_empty_dataset(constant_raster, geometry_request):
+    view = AggregateRaster(source=MockGeometry(polygons=[], properties=[]), raster=constant_raster,
+                           statistic="sum")
+    assert len(view.get_data(**geometry_request)["features"]) == 0
+
+
+@pytest.mark.parametrize("statistic,expected", [
+    ("sum", [16.0, 30.0, 0.0, 0.0]),
+    ("count", [2, 4, 0, 0]),
+    ("mean", [8.0, 7.5, np.nan, np.nan]),
+])
+def test_aggregate_above_threshold(range_raster, geometry_request, statistic, expected):
+    source = MockGeometry(
+        polygons=[
+            ((2.0, 2.0), (4.0, 2.0), (4.0, 4.0), (2.0, 4.0)),   # contains 7, 8
+            ((2.0, 2.0), (4.0, 2.0), (4.0, 4.0), (2.0, 4.0)),   # contains 7, 8
+            ((7.0, 7.0), (9.0, 7.0), (9.0, 9.0), (7.0, 9.0)),   # contains 2, 3
+            ((6.0, 6.0), (8.0, 6.0), (8.0, 8.0), (6.0, 8.0)),   # contains 3, 4
+        ],
+        properties=[{"id": 1, "threshold": 8.0}, {"id": 3, "threshold": 3.0},
+                    {"id": 2000000, "threshold": 4.0}, {"id": 9}])
+    request = dict(geometry_request, start=Datetime(2018, 1, 1), stop=Datetime(2018, 1, 1, 3))
+    view = AggregateRasterAboveThreshold(source=source, raster=range_raster, statistic=statistic,
+                                         threshold_name="threshold")
+    features = view.get_data(**request)["features"]
+    pd.testing.assert_series_equal(
+        features["agg"], pd.Series(expected, index=[1, 3, 2000000, 9], dtype=np.float32),
+        check_names=False)
+
+
+@pytest.fixture
+def raster_2x3():
+    return MemorySource(np.arange(6).reshape(2, 3).astype(float), 255, "EPSG:3857", pixel_size=2.0,
+                        pixel_origin=(0, 4))
+
+
+@pytest.mark.parametrize("statistic,expected", [
+    ("max", 3.0), ("min", 3.0), ("sum", 3.0), ("count", 1.0), ("mean", 3.0), ("p95", 3.0),
+])
+def test_small_geometry_statistics(geometry_request, statistic, expected, raster_2x3):
+    source = MockGeometry(polygons=[((2, 2), (1.9, 2), (2, 1.9))], properties=[{"id": 1}])
+    view = AggregateRaster(source=source, raster=raster_2x3, statistic=statistic)
+    assert_almost_equal(view.get_data(**geometry_request)["features"]["agg"].values, expected)
+
+
+@pytest.mark.parametrize("threshold,expected", [(2.0, 3.0), (3.0, 3.0), (4.0, np.nan)])
+def test_small_geometry_threshold(geometry_request, raster_2x3, threshold, expected):
+    source = MockGeometry(polygons=[((2, 2), (1.9, 2), (2, 1.9))],
+                          properties=[{"id": 1, "threshold": threshold}])
+    view = AggregateRasterAboveThreshold(source=source, raster=raster_2x3, statistic="max",
+                                         threshold_name="threshold")
+    assert_almost_equal(view.get_data(**geometry_request)["features"]["agg"].values, [expected])
+
+
+def test_small_geometry_temporal(geometry_request):
+    mock = MockRaster(origin=Datetime(2018, 1, 1), timedelta=Timedelta(hours=1), bands=3)
+    source = MockGeometry(polygons=[((2.0, 2.0), (2.1, 2.0), (2.1, 3.0), (2.0, 3.0))],
+                          properties=[{"id": 1}])
+    view = AggregateRaster(source=source, raster=mock, statistic="max")
+    request = dict(geometry_request)
+    request["start"], request["stop"] = mock.period
+    result = view.get_data(**request)
+    assert_almost_equal(result["features"]["agg"].loc[1][0], [1.0, 1.0, 1.0])
+
+
+def test_point_geometries_take_the_cell_under_them(geometry_request):
+    """A point feature is burned into the cell that contains it (GDAL point burn), which is what
+    the centroid sampling of geometries without cells returns."""
+    data = np.arange(100, dtype="f4").reshape(1, 10, 10)
+    src = MemorySource(data, -1.0, "EPSG:3857", 1.0, (0, 10))
+    source = MockGeometry([utils.Point(2.5, 7.5), utils.Point(9.2, 0.3)], [{"id": 1}, {"id": 2}])
+    got = AggregateRaster(source, src, statistic="max").get_data(**geometry_request)["features"]["agg"]
+    assert got.values.tolist() == [22.0, 99.0]
+
+
+# ---------------------------------------------------------------------------------------
+# MemorySource window requests (tests/test_raster_sources.py:68-171)
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.fixture
+def single_pixel():
+    return MemorySource(data=np.array([[[5]]], dtype=np.uint8), no_data_value=255,
+                        projection="EPSG:28992", pixel_size=5, pixel_origin=(136700, 455800))
+
+
+def _get(source, bbox, width, height):
+    return source.get_data(mode="vals", projection="EPSG:28992", bbox=bbox, width=width, height=height)
+
+
+def test_source_point_requests(single_pixel):
+    # data is defined at [136700, 136705) and (455795, 455800]
+    for dx, dy in ((0, 0), (0, -4.99), (4.99, 0), (4.99, -4.99)):
+        data = _get(single_pixel, (136700 + dx, 455800 + dy) * 2, 1, 1)
+        assert data["values"].shape == (1, 1, 1) and data["values"][0, 0, 0] == 5
+    for dx, dy in ((0, -5.0), (5.0, 0), (-5.0, 5.0), (-0.01, 0), (0, 0.01)):
+        data = _get(single_pixel, (136700 + dx, 455800 + dy) * 2, 1, 1)
+        assert data["values"].shape == (1, 1, 1) and data["values"][0, 0, 0] == data["no_data_value"]
+
+
+def test_source_bbox_requests(single_pixel):
+    data = _get(single_pixel, (136700, 455800 - 5, 136700 + 5, 455800), 1, 1)
+    assert data["values"].tolist() == [[[5]]]
+    for dx, dy in ((0, -5), (-5, 0), (0, 5), (5, 0)):
+        data = _get(single_pixel, (136700 + dx, 455800 - 5 + dy, 136705 + dx, 455800 + dy), 1, 1)
+        assert data["values"].tolist() == [[[data["no_data_value"]]]]
+    n = 255
+    data = _get(single_pixel, (136700, 455800 - 5, 136710, 455800), 2, 1)
+    assert data["values"].tolist() == [[[5, n]]]
+    data = _get(single_pixel, (136700, 455800 - 10, 136705, 455800), 1, 2)
+    assert data["values"].tolist() == [[[5], [n]]]          # y axis: no data on the low-y side
+    data = _get(single_pixel, (136700, 455800 - 5, 136710, 455800), 4, 2)
+    assert data["values"].tolist() == [[[5, 5, n, n], [5, 5, n, n]]]
+    data = _get(single_pixel, (136700, 455800 - 5, 136705, 455800), 5, 5)
+    assert data["values"].shape == (1, 5, 5) and (data["values"] == 5).all()
+
+
+def _nearest_neighbour(array, nodata, origin, cell, bbox, height, width):
+    """GDAL's nearest-neighbour warp for a same-CRS request, restated (reference call site
+    raster/sources.py:119-149; GWKNearestThread: source cell = floor(source pixel coordinate of
+    the target cell centre + 1e-10), outside the source -> no data)."""
+    x1, y1, x2, y2 = bbox
+    cols = np.floor(((x1 + (np.arange(width) + 0.5) * (x2 - x1) / width) - origin[0]) / cell + 1e-10).astype(int)
+    rows = np.floor((origin[1] - (y2 - (np.arange(height) + 0.5) * (y2 - y1) / height)) / cell + 1e-10).astype(int)
+    out = np.full((array.shape[0], height, width), nodata, dtype=array.dtype)
+    ok_r, ok_c = (rows >= 0) & (rows < array.shape[1]), (cols >= 0) & (cols < array.shape[2])
+    out[:, np.nonzero(ok_r)[0][:, None], np.nonzero(ok_c)[0][None, :]] = \
+        array[:, rows[ok_r][:, None], cols[ok_c][None, :]]
+    return out
+
+
+@pytest.mark.parametrize("dtype", ["u1", "i2", "f4", "f8"])
+@pytest.mark.parametrize("resident", [False, True])
+def test_source_non_aligned_and_zoomed_requests(dtype, resident):
+    """zoomed-in, zoomed-out, shifted and partly-outside requests on the same CRS."""
+    from dask_geomodeling_b200._compat import config as gm_config
+
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 200, (3, 37, 53)).astype(dtype)
+    nodata = 250
+    origin, cell = (1000.0, 2000.0), 2.5
+    src = MemorySource(data, nodata, "EPSG:28992", cell, origin, time_first=0, time_delta=3600000)
+    requests = [
+        ((1000.0, 2000.0 - 37 * cell, 1000.0 + 53 * cell, 2000.0), 37, 53),     # aligned, whole
+        ((1010.0, 1950.0, 1060.0, 1990.0), 16, 20),                               # aligned window
+        ((1003.1, 1921.7, 1117.3, 1998.2), 64, 96),                               # shifted + zoom in
+        ((1003.1, 1921.7, 1117.3, 1998.2), 7, 5),                                 # zoom out
+        ((980.3, 1890.2, 1170.9, 2030.6), 33, 41),                                # larger than source
+        ((1000.0, 1907.5, 1132.5, 2000.0), 74, 106),                              # exactly 2x zoom in
+        ((1000.0, 1910.0, 1130.0, 2000.0), 18, 26),                               # 2x zoom out (corners)
+    ]
+    start, stop = Datetime(1970, 1, 1), Datetime(1970, 1, 1, 2)
+    with gm_config.set({"geomodeling.device-cache-bytes": (1 << 20) if resident else 0}):
+        for bbox, height, width in requests:
+            got = src.get_data(mode="vals", projection="EPSG:28992", bbox=bbox, width=width,
+                               height=height, start=start, stop=stop)
+            expected = _nearest_neighbour(data, nodata, origin, cell, bbox, height, width)
+            assert got["values"].dtype == data.dtype and got["no_data_value"] == nodata
+            assert_array_equal(got["values"], expected)
