@@ -1236,31 +1236,7 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
   }
 }
 
-// ---- order statistics, the usual polygon -------------------------------------------------------
-// float32 rasters, polygons of <= ZW_MAXV vertices, <= ZS_MAXROWS rows of <= ZW_MAXC crossings,
-// <= ZS_MAXSPANS spans, no horizontal bottom edge on a scanline, and whose cells fit shared
-// memory; everything else is appended to the list in `work` for zonal_select_kernel.  One
-// block per polygon:
-//   1. a thread per row finds the row's spans (same arithmetic as the scanline code);
-//   2. a block scan gives every span its slot range in shared memory, padded to whole quads;
-//   3. warps copy spans with 16-byte loads, turning cells into sortable keys on the way (cells
-//      outside the span or without data become the all-ones sentinel), 4 rows in flight;
-//   4. 32 sampled keys bracket the wanted rank; ONE counting pass over the keys (cells below
-//      the bracket are counted, cells inside it fall into 2048 equal bins of the bracket), a
-//      scan of the bins, one pass that collects the handful of keys of the bin holding the
-//      rank, and a rank count among those.  When the bracket misses (skewed data), the 8-bit
-//      radix select runs over all keys instead.
-// The order of the keys in shared memory is irrelevant, so spans are stored as they come.
-constexpr int ZS_THREADS = 256;
-constexpr int ZS_MAXROWS = 512;
-constexpr int ZS_MAXSPANS = 512;
-constexpr int ZS_DIGIT = 10, ZS_BINS = 1 << ZS_DIGIT;
-constexpr int ZS_CAND = 256;
-constexpr int ZS_ROWS = 8;               // rows per warp and round of loads
-constexpr int ZS_MARGIN = 8;             // sample positions either side of the wanted rank (of 32)
-constexpr unsigned ZS_EMPTY = 0xffffffffu;
-
-// 32-bit sortable keys of the dtypes this kernel takes (float32 and integers up to 4 bytes)
+// 32-bit sortable keys of the dtypes the streaming select takes (float32 and integers up to 4 bytes)
 template <typename T> struct Key32 {
   static __device__ __forceinline__ unsigned key(T v) {
     return std::is_signed<T>::value ? ((unsigned)(int)v ^ 0x80000000u) : (unsigned)v;
@@ -1274,222 +1250,722 @@ template <> struct Key32<float> {
   static __device__ __forceinline__ float value(unsigned k) { return unorder_f32(k); }
 };
 
+// ---- order statistics, one WARP per polygon (streaming select) -----------------------------------
+// The usual polygon (<= ZW_MAXV vertices, <= ZW_BIG_ROWS rows, bounding box <= ZW_BIG_CELLS cells,
+// rasters of up to 4 bytes per cell) is selected by ONE warp that streams it from the raster -- no
+// block barrier, no shared key space, polygons fetched from an atomic counter like
+// zonal_reduce_warp_kernel:
+//   1. sample: every 16th row (lane = sample row, single-span rows only) is swept with scalar
+//      loads, two rows in flight: range of the sampled keys, then a 256-bin histogram of the range
+//      that is refined while the bins around the wanted rank still hold > 20 % of the sample.  The
+//      bins that hold the sample ranks q * n_s -+ (3 sigma + 2) give a BRACKET [lo, hi] of keys;
+//   2. main pass: the row walk of the reduce kernel (16-byte loads of whole aligned quads, edge cells
+//      by one lane each).  Per cell, compared as VALUES (same order as the keys): count it, count it
+//      as `below` when it is under the bracket, and when it lies in the bracket append it to the
+//      lane's own column of a scratch table in global memory (a few dozen cells per lane, L2
+//      resident) -- ten instructions per cell.  When the bracket spans < 256 distinct keys (byte
+//      rasters, classes, constant areas) the cells go to an exact histogram instead;
+//   3. the wanted ranks, now known from the exact count, are looked up among the bracket's keys:
+//      256-bin histogram of the bracket, the bin of the rank, its <= 32 keys ranked by the lanes
+//      (further levels while a bin holds more; at shift 0 a bin is one key).
+// Small polygons (bounding box <= WS_DIRECT cells) skip the sample: every cell is "in the bracket".
+// A polygon whose ranks fall outside the bracket (the sample misjudged the distribution) or whose
+// bracket overflows a lane's column joins the deferred list for zonal_select_kernel, like the
+// polygons this kernel does not take at all.  Results are bit-identical to the generic path: the
+// same two keys are found, only by another route.
+constexpr int WS_WARPS = 8;
+constexpr int WS_MIN_BLOCKS = 4;
+constexpr int WS_MAIN_BLOCKS = 3;        // the main kernel holds two batches of loads: 85 registers
+constexpr int WS_CAP = 128;              // cells per lane in the scratch table ([slot][lane] per warp)
+constexpr int WS_ROOM = 20;              // free slots a lane needs before a round of loads (<= 17 cells)
+constexpr int WS_BINS = 1024;             // histogram bins per warp (dynamic shared memory)
+constexpr int WS_BITS = 10;
+constexpr int WS_DIRECT = 1536;          // bounding-box cells up to which every cell is kept
+constexpr int WS_SAMPLE_STRIDE = 16;     // every 16th row is sampled
+enum { WS_SAMPLE_RANGE = 0, WS_SAMPLE_HIST = 1, WS_MAIN_STASH = 2, WS_MAIN_HIST = 3 };
+
+__device__ __forceinline__ void red_shared_inc(unsigned addr, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q red.shared.add.u32 [%0], 1;\n\t}"
+               :: "r"(addr), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void store_if(unsigned* at, unsigned word, bool p) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u32 [%0], %1;\n\t}"
+               :: "l"(at), "r"(word), "r"((unsigned)p) : "memory");
+}
+
+// bin of the warp's WS_BINS-entry table that holds the 0-based rank r, entries before it and
+// entries in it; -1 when r is not below the table's total.  Warp-wide call.
+__device__ __noinline__ int warp_find_bin(const int* hist, long long r, int* before, int* inside, int lane) {
+  constexpr int PERL = WS_BINS / 32;
+  const int4* mine4 = reinterpret_cast<const int4*>(hist) + (PERL / 4) * lane;
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < PERL / 4; ++j) { const int4 a = mine4[j]; sum += a.x + a.y + a.z + a.w; }
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int excl = incl - sum;
+  const bool mine = r >= excl && r < incl;
+  const unsigned m = __ballot_sync(0xffffffffu, mine);
+  if (m == 0) return -1;
+  int bin = -1, e = 0, c = 0;
+  if (mine) {
+    int left = (int)(r - excl);
+    e = excl;
+    for (int j = 0; j < PERL; ++j) {
+      const int h = hist[PERL * lane + j];
+      if (left < h) { bin = PERL * lane + j; c = h; break; }
+      left -= h; e += h;
+    }
+  }
+  const int src = __ffs(m) - 1;
+  *before = __shfl_sync(0xffffffffu, e, src);
+  *inside = __shfl_sync(0xffffffffu, c, src);
+  return __shfl_sync(0xffffffffu, bin, src);
+}
+
+// what a kept cell looks like in the scratch table: the raw bits of a float (the key is formed
+// when the table is read), the key of an integer
+template <typename T> struct StashWord {
+  static __device__ __forceinline__ unsigned word(T v) { return Key32<T>::key(v); }
+  static __device__ __forceinline__ unsigned key(unsigned w) { return w; }
+};
+template <> struct StashWord<float> {
+  static __device__ __forceinline__ unsigned word(float v) { return __float_as_uint(v); }
+  static __device__ __forceinline__ unsigned key(unsigned w) { return order_f32(__uint_as_float(w)); }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(ZS_THREADS, 3)
-zonal_select_fast_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
-                         int mis, int edge_scalar, int stat, double q, int capacity,
-                         float* __restrict__ out, long long* __restrict__ area, int* __restrict__ work) {
-  extern __shared__ __align__(16) unsigned char zs_smem[];
-  unsigned* keys = reinterpret_cast<unsigned*>(zs_smem);
-  __shared__ double s_px[ZW_MAXV], s_py[ZW_MAXV];
-  __shared__ int s_prev[ZW_MAXV];
-  __shared__ int s_y[ZS_MAXSPANS], s_x0[ZS_MAXSPANS], s_xe[ZS_MAXSPANS], s_base[ZS_MAXSPANS + 1];
-  __shared__ int s_hist[ZS_BINS];
-  __shared__ __align__(16) unsigned s_cand[ZS_CAND];
-  __shared__ int s_hist8[256];
-  __shared__ SelectScratch<unsigned> s_scratch;
-  __shared__ int s_wsum[ZS_THREADS / 32];
-  __shared__ int s_defer, s_count, s_ncand, s_blo, s_bhi, s_rlo, s_rhi, s_cells, s_nspans, s_below, s_inside;
-  __shared__ unsigned s_kmin, s_kmax, s_lowest, s_highest1;
-  // four cells per lane and load whatever the dtype: 16 bytes of 4-byte cells, 8 of int16, 4 of bytes
-  constexpr int VEC = 4;
+struct WarpSelect {
+  static constexpr int VEC = 4;
   typedef typename std::conditional<sizeof(T) == 4, uint4,
           typename std::conditional<sizeof(T) == 2, uint2, unsigned>::type>::type Quad;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* raster; int width; T nodata; bool no_nodata;
+  T vlo, vhi;               // the bracket as values: vlo <= v <= vhi
+  unsigned lo, span;        // ... and as keys: key - lo <= span
+  int shift;                // sample histogram: bin = (key - lo) >> shift
+  unsigned hist_at;         // shared-memory address of this warp's 256 bins
+  unsigned* column;         // this lane's column of the warp's scratch table (stride 32)
+  int n_active, below, cnt; // per lane
+  long long cells;
+  unsigned kmin, kmax;
+  float fmin_, fscale;      // float32 sample histogram: bin = (v - fmin_) * fscale (linear in the value)
+
+  // the cell of the main pass when the bracket's cells are kept: count it, count it as below,
+  // keep it -- nine instructions for float32 (predicated adds and store spelled out; the
+  // compiler's own selection needs fifteen).  `fill` = the cell may be a filler that carries the
+  // no-data value (lanes without a quad), which needs no test of its own.
+  __device__ __forceinline__ void keep(T v, bool ok) {
+    if constexpr (std::is_same<T, float>::value) {
+      unsigned* at = column + (unsigned)cnt * 32u;
+      asm volatile("{\n\t.reg .pred pa, pb, pi;\n\t"
+                   "setp.ne.u32 pa, %7, 0;\n\t"
+                   "setp.neu.and.f32 pa, %4, %5, pa;\n\t"   // active: a real cell that is not no data
+                   "setp.lt.and.f32 pb, %4, %6, pa;\n\t"    // below the bracket
+                   "setp.ge.and.f32 pi, %4, %6, pa;\n\t"
+                   "setp.le.and.f32 pi, %4, %8, pi;\n\t"    // in the bracket
+                   "@pa add.s32 %0, %0, 1;\n\t"
+                   "@pb add.s32 %1, %1, 1;\n\t"
+                   "@pi st.global.b32 [%3], %9;\n\t"
+                   "@pi add.s32 %2, %2, 1;\n\t}"
+                   : "+r"(n_active), "+r"(below), "+r"(cnt)
+                   : "l"(at), "f"(v), "f"(no_nodata ? __int_as_float(0x7fc00000) : nodata), "f"(vlo),
+                     "r"((unsigned)ok), "f"(vhi), "r"(__float_as_uint(v))
+                   : "memory");
+    } else {
+      const bool active = ok & (no_nodata | (v != nodata));
+      const bool in = active & (v >= vlo) & (v <= vhi);
+      n_active += active ? 1 : 0;
+      below += (active & (v < vlo)) ? 1 : 0;
+      store_if(column + (unsigned)cnt * 32u, StashWord<T>::word(v), in);
+      cnt += in ? 1 : 0;
+    }
+  }
+  // any mode, chosen at run time (the sample sweeps and the rows the table cannot describe)
+  __device__ __forceinline__ void take(int mode, T v, bool ok) {
+    if (mode == WS_MAIN_STASH) { keep(v, ok); return; }
+    const bool active = ok & (no_nodata | (v != nodata));
+    const unsigned key = Key32<T>::key(v), rel = key - lo;
+    if (mode == WS_SAMPLE_RANGE) {
+      n_active += active ? 1 : 0;
+      kmin = min(kmin, active ? key : 0xffffffffu);
+      kmax = max(kmax, active ? key : 0u);
+    } else {
+      if (mode == WS_MAIN_HIST) n_active += active ? 1 : 0;
+      below += (active & (key < lo)) ? 1 : 0;
+      red_shared_inc(hist_at + ((rel >> shift) << 2), active & (rel <= span));
+    }
+  }
+  // a lane's column is about to overflow: close the bracket (nothing is kept any more; the
+  // polygon is deferred when the pass is over because cnt stays above the capacity)
+  __device__ __forceinline__ void room() {
+    if (__any_sync(0xffffffffu, cnt > WS_CAP - WS_ROOM)) {
+      cnt = WS_CAP + 1; vlo = std::numeric_limits<T>::max(); vhi = std::numeric_limits<T>::lowest();
+    }
+  }
+  // one batch of ZW_ROWS single-span rows of the row table (see WarpReduce) in the main pass:
+  // whole aligned quads with one 16/8/4-byte load per lane and row, the edge cells (at most
+  // VEC - 1 either side of a row) by lanes 8 b + c of row b.  The quad a lane takes is rotated
+  // from row to row so that narrow polygons fill all columns evenly.  `issue` starts the loads,
+  // `consume` takes the cells: the kernel issues two batches before it consumes the first.
+  struct Batch { Quad qd[ZW_ROWS]; T edge; unsigned has; int longest; };
+  __device__ __forceinline__ void issue(int y0, const int* tab, Batch& B) const {
+    const int lane = threadIdx.x & 31;
+    const T filler = no_nodata ? T(0) : nodata;
+    Quad fillq;
+    {
+      T f[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) f[j] = filler;
+      memcpy(&fillq, f, sizeof(Quad));
+    }
+    B.has = 0u; B.longest = 0;
+#pragma unroll
+    for (int b = 0; b < ZW_ROWS; ++b) {
+      const int xh = tab[64 + b], xt = tab[96 + b];
+      const int x = xh + VEC * ((lane + 7 * (y0 + b)) & 31);
+      B.longest = max(B.longest, xt - xh);
+      B.qd[b] = fillq;
+      if (x < xt) {
+        B.has |= 1u << b;
+        B.qd[b] = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)(y0 + b) * width + x));
+      }
+    }
+    // edge cells: lane = 8 * row + c, c < 3 in front of the quads, 3 <= c < 6 behind them
+    const int eb = lane >> 3, ec = lane & 7;
+    const bool head = ec < VEC - 1;
+    const int ex = head ? tab[eb] + ec : tab[96 + eb] + ec - (VEC - 1);
+    B.edge = filler;
+    if (ec < 2 * (VEC - 1) && ex < (head ? min(tab[64 + eb], tab[32 + eb]) : tab[32 + eb])) {
+      B.has |= 1u << 8;
+      B.edge = __ldg(raster + (int64_t)(y0 + eb) * width + ex);
+    }
+  }
+  template <bool EXACT> __device__ __forceinline__ void consume(int y0, const int* tab, const Batch& B) {
+    const int lane = threadIdx.x & 31;
+    if (!EXACT) room();
+    // with a no-data value the fillers are inactive by themselves; without one they need `ok`
+#pragma unroll
+    for (int b = 0; b < ZW_ROWS; ++b) {
+      T e[VEC];
+      memcpy(e, &B.qd[b], sizeof(Quad));
+      const bool ok = ((B.has >> b) & 1u) | !no_nodata;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        if (EXACT) take(WS_MAIN_HIST, e[j], ok);
+        else keep(e[j], ok);
+      }
+    }
+    if (EXACT) take(WS_MAIN_HIST, B.edge, ((B.has >> 8) & 1u) | !no_nodata);
+    else keep(B.edge, ((B.has >> 8) & 1u) | !no_nodata);
+    if (B.longest > 32 * VEC) {   // rows of more than 32 quads: the rest
+      const T filler = no_nodata ? T(0) : nodata;
+      for (int k = 32 * VEC + VEC * lane; k - VEC * lane < B.longest; k += 32 * VEC) {
+        if (!EXACT) room();
+#pragma unroll 1
+        for (int b = 0; b < ZW_ROWS; ++b) {
+          const int x = tab[64 + b] + k;
+          const bool ok = x < tab[96 + b];
+          T e[VEC];
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) e[j] = filler;
+          if (ok) {
+            const Quad qv = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)(y0 + b) * width + x));
+            memcpy(e, &qv, sizeof(Quad));
+          }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) take(EXACT ? WS_MAIN_HIST : WS_MAIN_STASH, e[j], ok);
+        }
+      }
+    }
+  }
+};
+
+// cells x0..x1 of row y, lane per cell, four loads in flight; any mode.  Not inlined: the rows
+// the table cannot describe and the tails of very long sample rows are rare, and the kernel has
+// to stay small enough for the instruction cache (32 warps per SM in different phases).
+template <typename T>
+__device__ __noinline__ void select_span(WarpSelect<T>& w, int mode, int y, int x0, int x1) {
+  const T* row = w.raster + (int64_t)y * w.width;
+  const int lane = threadIdx.x & 31;
+  for (int x = x0 + lane; x - lane <= x1; x += 128) {
+    if (mode == WS_MAIN_STASH) w.room();
+    T v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = x + 32 * k <= x1 ? __ldg(row + x + 32 * k) : T(0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w.take(mode, v[k], x + 32 * k <= x1);
+  }
+}
+
+// sample sweep: rows y0 + r * stride of the table (x0 in tab[r], end in tab[32 + r]), two rows
+// and four cells per lane and row in flight.  RANGE: smallest / largest key and the number of
+// active cells; HIST: bins of (key - lo) >> shift and the number of keys below lo.
+template <typename T, int MODE>
+__device__ __noinline__ void select_sample(WarpSelect<T>& w, int n_rows, const int* tab, int y0, int stride) {
+  constexpr bool F = std::is_same<T, float>::value;   // float32: bins linear in the value, not the key
+  const int lane = threadIdx.x & 31;
+  const T nodata = w.nodata;
+  const bool no_nodata = w.no_nodata;
+  const unsigned lo = w.lo, span = w.span, hist_at = w.hist_at;
+  const int shift = w.shift;
+  const float f0 = w.fmin_, fs = w.fscale;
+  int count = 0;
+  unsigned kmin = 0xffffffffu, kmax = 0u;
+  float vmin = INFINITY, vmax = -INFINITY;
+  for (int r = 0; r < n_rows; r += 2) {
+    T v[2][4];
+    bool ok[2][4];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int rr = r + b < n_rows ? r + b : r;
+      const int x0 = tab[rr], xe = r + b < n_rows ? tab[32 + rr] : 0;
+      const T* row = w.raster + (int64_t)(y0 + rr * stride) * w.width + x0 + lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ok[b][k] = x0 + lane + 32 * k < xe;
+        v[b][k] = ok[b][k] ? __ldg(row + 32 * k) : T(0);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool active = ok[b][k] & (no_nodata | (v[b][k] != nodata));
+        if constexpr (F) {
+          const float x = (float)v[b][k];
+          if (MODE == WS_SAMPLE_RANGE) {
+            count += active ? 1 : 0;
+            vmin = fminf(vmin, active ? x : INFINITY);      // (NaN cells leave the range alone)
+            vmax = fmaxf(vmax, active ? x : -INFINITY);
+          } else {
+            const float rel = (x - f0) * fs;                  // NaN for NaN cells: neither below nor in a bin
+            count += (active & (rel < 0.0f)) ? 1 : 0;
+            const int bin = min((int)rel, WS_BINS - 1);
+            red_shared_inc(hist_at + ((unsigned)bin << 2), active & (rel >= 0.0f) & (rel < (float)WS_BINS + 0.5f));
+          }
+        } else {
+          const unsigned key = Key32<T>::key(v[b][k]);
+          if (MODE == WS_SAMPLE_RANGE) {
+            count += active ? 1 : 0;
+            kmin = min(kmin, active ? key : 0xffffffffu);
+            kmax = max(kmax, active ? key : 0u);
+          } else {
+            const unsigned rel = key - lo;
+            count += (active & (key < lo)) ? 1 : 0;
+            red_shared_inc(hist_at + ((rel >> shift) << 2), active & (rel <= span));
+          }
+        }
+      }
+  }
+  if (MODE == WS_SAMPLE_RANGE) {
+    w.n_active = count;
+    if constexpr (F) { w.kmin = __float_as_uint(vmin); w.kmax = __float_as_uint(vmax); }
+    else { w.kmin = kmin; w.kmax = kmax; }
+  } else {
+    w.below = count;
+  }
+  // (rows of more than 128 cells: their first 128 cells are the sample)
+}
+
+// visitor of the generic scanline for the rows the table cannot describe
+template <typename T>
+struct WarpSelectVisitor {
+  WarpSelect<T>& w;
+  int mode;
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    if ((threadIdx.x & 31) == 0) w.cells += x1 - x0 + 1;
+    select_span(w, mode, y, x0, x1);
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int* buf, int n) {
+    const T* row = w.raster + (int64_t)y * w.width;
+    int extra = 0;
+    for (int xb = x0; xb <= x1; xb += 32) {
+      if (mode == WS_MAIN_STASH) w.room();
+      const int x = xb + (threadIdx.x & 31);
+      const bool ok = x <= x1 && !in_pairs(x, buf, n);
+      w.take(mode, ok ? __ldg(row + x) : T(0), ok);
+      extra += ok ? 1 : 0;
+    }
+    w.cells += extra;
+  }
+};
+
+template <typename T>
+__device__ __noinline__ void select_complex_row(const PolyDev& P, int64_t r0, int64_t r1, int y, int* buf,
+                                                int* hbuf, WarpSelect<T>& w, int mode) {
+  WarpSelectVisitor<T> vis{w, mode};
+  generic_scanline(P, r0, r1, y, ZW_MAXV, buf, hbuf, vis);
+}
+
+// sorted crossings of row y with the polygon staged in (px, py, prev) into column `lane` of
+// `cross`; returns their number, or -1 for a row that needs the generic scanline (a horizontal
+// bottom edge on the scanline, more than ZW_MAXC crossings).  Same arithmetic as generic_scanline.
+__device__ __noinline__ int row_crossings(const double* px, const double* py, const int* prev, int nv,
+                                          int y, int (*cross)[32], int lane) {
+  const double dy = y + 0.5;
+  int cnt = 0;
+  bool complex_row = false;
+  for (int i = 0; i < nv; ++i) {
+    const int ind1 = prev[i];
+    double dy1 = py[ind1], dy2 = py[i];
+    if ((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy)) continue;
+    double dx1, dx2;
+    if (dy1 < dy2) {
+      dx1 = px[ind1]; dx2 = px[i];
+    } else if (dy1 > dy2) {
+      const double t = dy1; dy1 = dy2; dy2 = t;
+      dx2 = px[ind1]; dx1 = px[i];
+    } else {
+      if (px[ind1] > px[i]) complex_row = true;
+      continue;
+    }
+    if (dy < dy2 && dy >= dy1) {
+      const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
+      if (cnt < ZW_MAXC) cross[cnt][lane] = clamp_to_int(floor(intersect + 0.5));
+      ++cnt;
+    }
+  }
+  if (cnt > ZW_MAXC || complex_row) return -1;
+  for (int a = 1; a < cnt; ++a) {
+    const int v = cross[a][lane];
+    int j = a - 1;
+    while (j >= 0 && cross[j][lane] > v) { cross[j + 1][lane] = cross[j][lane]; --j; }
+    cross[j + 1][lane] = v;
+  }
+  return cnt;
+}
+
+// The select runs as THREE kernels, each a loop of warps over polygons (atomic counter) that
+// executes ONE phase: with all phases in a single kernel the 32 warps of an SM sat in different
+// parts of ~100 KB of code and 40-55 % of the issue slots were lost to instruction-cache misses
+// (ncu r02c); split, every kernel's hot loop fits the instruction cache.
+//   bracket kernel   sample -> state[p] = (lo, hi, what to do)
+//   main kernel      the pass over all cells -> counts + the bracket's cells in the polygon's table
+//                    (polygons with an exact histogram are finished here)
+//   final kernel     ranks among the table's cells -> out[p]
+// Polygons are processed in chunks so that the tables (WS_CAP x 32 words + 32 counts each) stay
+// bounded and L2-warm between the main and the final kernel.
+enum { WS_SKIP = 0, WS_TABLE = 1, WS_EXACT = 2 };
+struct SelectState { unsigned lo, hi; int what; int n_active; int below; int kept; };
+constexpr int WS_TABLE_WORDS = WS_CAP * 32 + 32;     // cells + per-lane counts
+
+// vertices of polygon p (and each vertex' predecessor on its ring) to the warp's shared memory;
+// returns the width of the bounding box clipped to the raster (+ 1)
+__device__ __forceinline__ double stage_polygon(const PolyDev& P, int64_t r0, int64_t r1, int64_t v0, int nv,
+                                                double* px, double* py, int* prev, int lane) {
+  double xmin = DBL_MAX, xmax = -DBL_MAX;
+  __syncwarp();
+  for (int i = lane; i < nv; i += 32) {
+    const double x = P.px[v0 + i];
+    px[i] = x; py[i] = P.py[v0 + i];
+    xmin = fmin(xmin, x); xmax = fmax(xmax, x);
+    int pr = i - 1;
+    for (int64_t r = r0; r < r1; ++r)
+      if ((int64_t)i + v0 == P.ring_offsets[r]) pr = (int)(P.ring_offsets[r + 1] - v0) - 1;
+    prev[i] = pr;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+  }
+  __syncwarp();
+  return fmax(fmin(xmax, (double)P.width) - fmax(xmin, 0.0), 0.0) + 1.0;
+}
+
+#define WS_SHARED_TABLES                                                              \
+  __shared__ double s_px[WS_WARPS][ZW_MAXV], s_py[WS_WARPS][ZW_MAXV];                 \
+  __shared__ int s_prev[WS_WARPS][ZW_MAXV];                                           \
+  __shared__ __align__(16) int s_cross[WS_WARPS][ZW_MAXC][32];                        \
+  extern __shared__ __align__(16) int ws_hist[];        /* WS_WARPS x WS_BINS */      \
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                         \
+  double* px = s_px[warp];                                                            \
+  double* py = s_py[warp];                                                            \
+  int* prev = s_prev[warp];                                                           \
+  int* hist = ws_hist + warp * WS_BINS;                                               \
+  int (*cross)[32] = s_cross[warp];                                                   \
+  const int* tab = &s_cross[warp][0][0];                                              \
+  auto zero_hist = [&]() {                                                            \
+    __syncwarp();                                                                     \
+    _Pragma("unroll")                                                                 \
+    for (int j = 0; j < WS_BINS / 32; ++j) hist[j * 32 + lane] = 0;                   \
+    __syncwarp();                                                                     \
+  };
+
+template <typename T>
+__global__ void __launch_bounds__(32 * WS_WARPS, WS_MIN_BLOCKS)
+zonal_select_bracket_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                            int stat, double q, int64_t p_begin, int64_t p_end, int* __restrict__ counter,
+                            SelectState* __restrict__ state, float* __restrict__ out,
+                            long long* __restrict__ area, int* __restrict__ work) {
+  // work[0]: length of the deferred list, work[2...]: the list
+  WS_SHARED_TABLES
   const int maxx = P.width - 1;
-  const float nanf_ = __int_as_float(0x7fc00000);
-  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
+  WarpSelect<T> w;
+  w.raster = raster; w.width = P.width; w.nodata = nodata; w.no_nodata = !has_nodata;
+  w.hist_at = (unsigned)__cvta_generic_to_shared(hist);
+  w.column = nullptr;
+  const double qf = stat == GM_STAT_MEDIAN ? 0.5 : q / 100.0;
+  for (;;) {
+    int64_t p = 0;
+    if (lane == 0) p = p_begin + atomicAdd(counter, 1);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= p_end) break;
     const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
     const int miny = P.miny[p], maxy = P.maxy[p];
     int64_t v0 = 0, v1 = 0;
     if (r1 > r0) { v0 = P.ring_offsets[r0]; v1 = P.ring_offsets[r1]; }
     const int nv = (int)min((int64_t)(ZW_MAXV + 1), v1 - v0);
-    const int rows = maxy - miny + 1;
-    // polygons without rows here (another stripe, outside the raster) and polygons for the
-    // generic kernel leave before any shared memory is touched: no barrier for them
-    if (rows <= 0 || nv == 0) {
-      if (tid == 0) { out[p] = nanf_; area[p] = 0; }
+    const int nrows = maxy - miny + 1;
+    if (nrows <= 0 || nv == 0) {     // no rows here (another stripe, outside the raster)
+      if (lane == 0) { out[p] = __int_as_float(0x7fc00000); area[p] = 0; state[p].what = WS_SKIP; }
       continue;
     }
-    if (nv > ZW_MAXV || nv < 2 || rows > ZS_MAXROWS) {
-      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
+    bool defer = nv > ZW_MAXV || nv < 2 || nrows > ZW_BIG_ROWS;
+    double boxw = 0.0;
+    if (!defer) {
+      boxw = stage_polygon(P, r0, r1, v0, nv, px, py, prev, lane);
+      defer = boxw * (double)nrows > (double)ZW_BIG_CELLS;
+    }
+    if (defer) {
+      if (lane == 0) { work[2 + atomicAdd(work, 1)] = (int)p; state[p].what = WS_SKIP; }
       continue;
     }
-    __syncthreads();   // the previous polygon is done with shared memory
-    if (tid == 0) {
-      s_defer = 0; s_count = 0; s_ncand = 0; s_cells = 0; s_nspans = 0; s_below = 0; s_inside = 0;
-      s_kmin = ZS_EMPTY; s_kmax = 0u; s_lowest = ZS_EMPTY; s_highest1 = 0u;
-    }
-    for (int i = tid; i < nv; i += ZS_THREADS) {
-      s_px[i] = P.px[v0 + i];
-      s_py[i] = P.py[v0 + i];
-      int pr = i - 1;
-      for (int64_t r = r0; r < r1; ++r)
-        if ((int64_t)i + v0 == P.ring_offsets[r]) pr = (int)(P.ring_offsets[r + 1] - v0) - 1;
-      s_prev[i] = pr;
-    }
-    __syncthreads();
-    // 1. one thread per row: sorted crossings in registers, one table entry per span
-    int my_cells = 0;
-    for (int r = tid; r < rows; r += ZS_THREADS) {
-      const int y = miny + r;
-      const double dy = y + 0.5;
-      int cnt = 0, c[ZW_MAXC];
-#pragma unroll
-      for (int j = 0; j < ZW_MAXC; ++j) c[j] = INT_MAX;
-      bool bad = edge_scalar && (y == 0 || y == P.height - 1);
-      for (int i = 0; i < nv; ++i) {
-        const int ind1 = s_prev[i];
-        double dy1 = s_py[ind1], dy2 = s_py[i];
-        if ((dy1 < dy && dy2 < dy) || (dy1 > dy && dy2 > dy)) continue;
-        double dx1, dx2;
-        if (dy1 < dy2) {
-          dx1 = s_px[ind1]; dx2 = s_px[i];
-        } else if (dy1 > dy2) {
-          const double t = dy1; dy1 = dy2; dy2 = t;
-          dx2 = s_px[ind1]; dx1 = s_px[i];
-        } else {
-          if (s_px[ind1] > s_px[i]) bad = true;  // bottom horizontal edge on the scanline
+    unsigned lo = 0u, hi = 0xffffffffu;
+    if (sizeof(T) == 1) {
+      hi = 255u;                       // byte rasters: an exact histogram of all keys, no sample
+    } else if (boxw * (double)nrows > (double)WS_DIRECT) {
+      const int stride = max(WS_SAMPLE_STRIDE, (nrows + 31) / 32);
+      const int n_sr = (nrows + stride - 1) / stride;          // <= 32 sample rows, one per lane
+      int sx0 = 0, sxe = 0;
+      if (lane < n_sr) {
+        const int y = miny + lane * stride;
+        const int c = row_crossings(px, py, prev, nv, y, cross, lane);
+        if (c == 2) {
+          const int xa = cross[0][lane], xb = cross[1][lane];
+          if (xa <= maxx && xb > 0) { sx0 = xa < 0 ? 0 : xa; sxe = xb > P.width ? P.width : xb; }
+        }
+      }
+      __syncwarp();
+      cross[0][lane] = sx0; cross[1][lane] = sxe;
+      __syncwarp();
+      // pass 0: range of the sampled keys; passes 1..: histograms of the bracket so far, until the
+      // bins around the wanted ranks hold little more than the ranks' own margin
+      int n_s = 0;
+      long long ra = 0, rb = 0;
+      bool open_lo = true, open_hi = true, usable = false;
+      unsigned blo = 0u, bhi = 0xffffffffu;
+      float vlo_s = 0.0f, vhi_s = 0.0f;      // float32: the bracket as values
+      int sh = 0;
+      for (int pass = 0; pass < 5; ++pass) {
+        if (pass == 0) {
+          select_sample<T, WS_SAMPLE_RANGE>(w, n_sr, tab, miny, stride);
+          n_s = __reduce_add_sync(0xffffffffu, w.n_active);
+          if constexpr (std::is_same<T, float>::value) {
+            vlo_s = __uint_as_float(w.kmin); vhi_s = __uint_as_float(w.kmax);
+            for (int o = 16; o > 0; o >>= 1) {
+              vlo_s = fminf(vlo_s, __shfl_xor_sync(0xffffffffu, vlo_s, o));
+              vhi_s = fmaxf(vhi_s, __shfl_xor_sync(0xffffffffu, vhi_s, o));
+            }
+          } else {
+            blo = __reduce_min_sync(0xffffffffu, w.kmin);
+            bhi = __reduce_max_sync(0xffffffffu, w.kmax);
+          }
+          if (n_s < 32) break;
+          if (std::is_same<T, float>::value && !(vhi_s - vlo_s < INFINITY)) break;   // range not finite
+          usable = true;
+          const double fs = qf * (double)(n_s - 1);
+          const double margin = 3.0 * sqrt(qf * (1.0 - qf) * (double)n_s) + 2.0;
+          ra = (long long)floor(fs - margin); rb = (long long)ceil(fs + margin);
+          open_lo = ra <= 0; open_hi = rb >= n_s - 1;
+          ra = max(ra, 0LL); rb = min(rb, (long long)n_s - 1);
           continue;
         }
-        if (dy < dy2 && dy >= dy1) {
-          const double intersect = (dy - dy1) * (dx2 - dx1) / (dy2 - dy1) + dx1;
-          int xi = clamp_to_int(floor(intersect + 0.5));
-#pragma unroll
-          for (int j = 0; j < ZW_MAXC; ++j) {   // sorted insert: the largest value falls out
-            const int lo = min(c[j], xi);
-            xi = max(c[j], xi);
-            c[j] = lo;
-          }
-          ++cnt;
+        zero_hist();
+        float width = 0.0f;
+        if constexpr (std::is_same<T, float>::value) {
+          width = vhi_s - vlo_s;
+          if (!(width > 0.0f)) break;                       // one value: the bracket is that value
+          w.fmin_ = vlo_s; w.fscale = (float)WS_BINS / width;
+        } else {
+          const unsigned range = bhi - blo;
+          sh = max(32 - __clz(range) - WS_BITS, 0);
+          w.lo = blo; w.span = range; w.shift = sh;
+        }
+        select_sample<T, WS_SAMPLE_HIST>(w, n_sr, tab, miny, stride);
+        const int below_s = __reduce_add_sync(0xffffffffu, w.below);
+        __syncwarp();
+        int ea = 0, ca = 0, eb = 0, cb = 0;
+        const int ba = warp_find_bin(hist, ra - below_s, &ea, &ca, lane);
+        const int bb = warp_find_bin(hist, rb - below_s, &eb, &cb, lane);
+        if (ba < 0 || bb < 0) break;   // cannot happen (the ranks lie in the bracket); keep the bracket
+        const long long wanted = rb - ra + 1, got = (long long)(eb + cb - ea);
+        if constexpr (std::is_same<T, float>::value) {
+          // one bin of slack either side covers the rounding of the bin arithmetic
+          const float step = width / (float)WS_BINS;
+          const float nlo = fmaxf(vlo_s, vlo_s + step * (float)(ba - 1));
+          const float nhi = fminf(vhi_s, vlo_s + step * (float)(bb + 2));
+          const bool narrower = nhi - nlo < 0.5f * width;
+          vlo_s = nlo; vhi_s = nhi;
+          if (!narrower || 3 * (got - wanted) <= wanted) break;
+        } else {
+          const unsigned long long top = (unsigned long long)blo + ((unsigned long long)(bb + 1) << sh) - 1ULL;
+          const unsigned nhi = top < (unsigned long long)bhi ? (unsigned)top : bhi;
+          blo = blo + ((unsigned)ba << sh);
+          bhi = nhi;
+          if (sh == 0 || 3 * (got - wanted) <= wanted) break;
         }
       }
-      if (cnt > ZW_MAXC || (cnt & 1)) bad = true;
-      if (!bad) {
-#pragma unroll
-        for (int i = 0; i + 1 < ZW_MAXC; i += 2) {
-          if (i + 1 < cnt && c[i] <= maxx && c[i + 1] > 0) {
-            const int x0 = c[i] < 0 ? 0 : c[i];
-            const int xe = c[i + 1] > P.width ? P.width : c[i + 1];
-            if (x0 < xe) {
-              const int at = atomicAdd(&s_nspans, 1);
-              if (at < ZS_MAXSPANS) {
-                const int64_t off = (int64_t)y * P.width + mis;
-                // slots: the 4-key groups of the span's quads that overlap the span
-                const int a0 = x0 - (int)((off + x0) & (VEC - 1));
-                s_y[at] = y; s_x0[at] = x0; s_xe[at] = xe;
-                s_base[at] = ((xe - a0 + 3) & ~3) - ((x0 - a0) & ~3);
-                my_cells += xe - x0;
-              } else {
-                bad = true;
-              }
+      if constexpr (std::is_same<T, float>::value) {
+        blo = order_f32(vlo_s); bhi = order_f32(vhi_s);
+      }
+      if (usable) {
+        lo = open_lo ? 0u : blo;
+        hi = open_hi ? 0xffffffffu : bhi;
+      }
+      __syncwarp();
+    }
+    // few distinct keys in the bracket: an exact histogram instead of the table
+    if (lane == 0) {
+      state[p].lo = lo; state[p].hi = hi;
+      state[p].what = hi - lo < (unsigned)WS_BINS ? WS_EXACT : WS_TABLE;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * WS_WARPS, WS_MAIN_BLOCKS)
+zonal_select_main_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int has_nodata,
+                         int mis, int edge_scalar, int stat, double q, int64_t p_begin, int64_t p_end,
+                         int* __restrict__ counter, SelectState* __restrict__ state,
+                         unsigned* __restrict__ tables, float* __restrict__ out,
+                         long long* __restrict__ area, int* __restrict__ work) {
+  WS_SHARED_TABLES
+  __shared__ int s_buf[WS_WARPS][ZW_MAXV + 2 * PG_MAX_HSPANS];
+  int* buf = s_buf[warp];
+  int* hbuf = buf + ZW_MAXV;
+  const int maxx = P.width - 1;
+  WarpSelect<T> w;
+  w.raster = raster; w.width = P.width; w.nodata = nodata; w.no_nodata = !has_nodata;
+  w.hist_at = (unsigned)__cvta_generic_to_shared(hist);
+  for (;;) {
+    int64_t p = 0;
+    if (lane == 0) p = p_begin + atomicAdd(counter, 1);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= p_end) break;
+    const int what = state[p].what;
+    if (what == WS_SKIP) continue;
+    const unsigned lo = state[p].lo, hi = state[p].hi;
+    const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
+    const int miny = P.miny[p], maxy = P.maxy[p];
+    const int64_t v0 = P.ring_offsets[r0];
+    const int nv = (int)(P.ring_offsets[r1] - v0);
+    stage_polygon(P, r0, r1, v0, nv, px, py, prev, lane);
+    const bool exact = what == WS_EXACT;
+    const int main_mode = exact ? WS_MAIN_HIST : WS_MAIN_STASH;
+    unsigned* table = tables + (size_t)(p - p_begin) * WS_TABLE_WORDS;
+    w.column = table + lane;
+    w.lo = lo; w.span = hi - lo; w.shift = 0;
+    w.vlo = Key32<T>::value(lo); w.vhi = Key32<T>::value(hi);
+    if (std::is_same<T, float>::value) {
+      // keys beyond +-infinity are NaNs: as values they compare false with everything, so an open
+      // end of the bracket is the infinity (NaN cells then count as "above", where they sort)
+      if (lo < 0x007fffffu) w.vlo = (T)(-INFINITY);
+      if (hi > 0xff800000u) w.vhi = (T)(INFINITY);
+    }
+    w.n_active = 0; w.below = 0; w.cnt = 0; w.cells = 0;
+    if (exact) zero_hist();
+    for (int base = miny; base <= maxy; base += 32) {
+      const int y = base + lane;
+      int cnt = 0;
+      if (y <= maxy) cnt = row_crossings(px, py, prev, nv, y, cross, lane);
+      const bool complex_row = cnt < 0;
+      const bool edge = edge_scalar && (y == 0 || y == P.height - 1);
+      const bool scalar_row = !complex_row && cnt >= 2 && (cnt > 2 || edge);
+      int fx0 = 0, fxe = 0, xh = 0, xt = 0;
+      if (!complex_row && !scalar_row && cnt == 2) {
+        constexpr int VEC = WarpSelect<T>::VEC;
+        const int xa = cross[0][lane], xb = cross[1][lane];
+        if (xa <= maxx && xb > 0 && (xa < 0 ? 0 : xa) < (xb > P.width ? P.width : xb)) {
+          fx0 = xa < 0 ? 0 : xa; fxe = xb > P.width ? P.width : xb;
+          w.cells += fxe - fx0;
+          const int64_t off = (int64_t)y * P.width + mis;
+          xh = fx0 + (int)((VEC - ((off + fx0) & (VEC - 1))) & (VEC - 1));
+          xt = fxe - (int)((off + fxe) & (VEC - 1));
+          if (xt < xh) xt = xh;
+        }
+      }
+      __syncwarp();
+      const unsigned complex_mask = __ballot_sync(0xffffffffu, complex_row);
+      unsigned scalar_mask = __ballot_sync(0xffffffffu, scalar_row);
+      const unsigned single_mask = __ballot_sync(0xffffffffu, fx0 < fxe);
+      while (scalar_mask) {            // the scalar rows first: they still need their raw crossings
+        const int r = __ffs(scalar_mask) - 1;
+        scalar_mask &= scalar_mask - 1;
+        const int c = __shfl_sync(0xffffffffu, cnt, r);
+        for (int i = 0; i + 1 < c; i += 2) {
+          const int xa = cross[i][r], xb = cross[i + 1][r];
+          if (xa <= maxx && xb > 0) {
+            const int x0 = xa < 0 ? 0 : xa, x1 = xb - 1 > maxx ? maxx : xb - 1;
+            if (x0 <= x1) {
+              if (lane == 0) w.cells += x1 - x0 + 1;
+              select_span(w, main_mode, base + r, x0, x1);
             }
           }
         }
       }
-      if (bad) s_defer = 1;
-    }
-    if (my_cells) atomicAdd(&s_cells, my_cells);
-    __syncthreads();
-    if (s_defer) {
-      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
-      continue;
-    }
-    const int spans = s_nspans;
-    // 2. exclusive scan of the slot counts (ZS_MAXSPANS / ZS_THREADS spans per thread)
-    {
-      constexpr int PERT = ZS_MAXSPANS / ZS_THREADS;
-      int v[PERT], sum = 0;
+      __syncwarp();
+      cross[0][lane] = fx0; cross[1][lane] = fxe; cross[2][lane] = xh; cross[3][lane] = xt;
+      __syncwarp();
+      constexpr unsigned BM = (1u << ZW_ROWS) - 1u;
+      if (sizeof(T) != 1 && exact) {
+        // (rare: few distinct keys in a raster of wider cells) span by span with scalar loads
+        for (int r = 0; r < 32; ++r)
+          if (tab[r] < tab[32 + r]) select_span(w, WS_MAIN_HIST, base + r, tab[r], tab[32 + r] - 1);
+      } else {
+        // two batches of rows in flight: the loads of the second hide behind the cells of the first
+        unsigned todo = 0u;
 #pragma unroll
-      for (int j = 0; j < PERT; ++j) { v[j] = PERT * tid + j < spans ? s_base[PERT * tid + j] : 0; sum += v[j]; }
-      int incl = sum;
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (lane == 31) s_wsum[warp] = incl;
-      __syncthreads();
-      int before = 0;
-      for (int w = 0; w < warp; ++w) before += s_wsum[w];
-      int run = before + incl - sum;
-#pragma unroll
-      for (int j = 0; j < PERT; ++j) { if (PERT * tid + j < spans) s_base[PERT * tid + j] = run; run += v[j]; }
-      if (tid == ZS_THREADS - 1) s_base[ZS_MAXSPANS] = run;   // total
-      __syncthreads();
-    }
-    const int total = s_base[ZS_MAXSPANS];
-    if (total > capacity) {
-      if (tid == 0) work[2 + atomicAdd(work, 1)] = (int)p;
-      continue;
-    }
-    if (tid == 0) area[p] = s_cells;
-    if (total == 0) {
-      if (tid == 0) out[p] = nanf_;
-      continue;
-    }
-    // 3. spans -> keys, ZS_ROWS spans per warp and round
-    int my_count = 0;
-    unsigned my_min = ZS_EMPTY, my_max1 = 0u;
-    for (int rb = ZS_ROWS * warp; rb < spans; rb += ZS_ROWS * (ZS_THREADS / 32)) {
-      int widest = 0;
-      int a0[ZS_ROWS], ae[ZS_ROWS];
-#pragma unroll
-      for (int b = 0; b < ZS_ROWS; ++b) {
-        const int r = rb + b;
-        a0[b] = 0; ae[b] = 0;
-        if (r < spans) {
-          const int64_t off = (int64_t)s_y[r] * P.width + mis;
-          a0[b] = s_x0[r] - (int)((off + s_x0[r]) & (VEC - 1));
-          ae[b] = s_xe[r] + (int)((VEC - ((off + s_xe[r]) & (VEC - 1))) & (VEC - 1));
-        }
-        widest = max(widest, ae[b] - a0[b]);
-      }
-      for (int k = VEC * lane; k - VEC * lane < widest; k += 32 * VEC) {
-        Quad qv[ZS_ROWS];
-#pragma unroll
-        for (int b = 0; b < ZS_ROWS; ++b) {
-          qv[b] = Quad();
-          if (a0[b] + k < ae[b])
-            qv[b] = __ldg(reinterpret_cast<const Quad*>(raster + (int64_t)s_y[rb + b] * P.width + (a0[b] + k)));
-        }
-#pragma unroll
-        for (int b = 0; b < ZS_ROWS; ++b) {
-          if (a0[b] + k < ae[b]) {
-            const int r = rb + b;
-            const int x0 = s_x0[r], xe = s_xe[r];
-            T e[VEC];
-            memcpy(e, &qv[b], sizeof(Quad));
-            unsigned kk[VEC];
-            const unsigned len = (unsigned)(xe - x0), rel = (unsigned)(a0[b] + k - x0);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-              const bool active = rel + j < len && !(has_nodata && e[j] == nodata);
-              const unsigned key = Key32<T>::key(e[j]);   // (the float NaN 0x7fffffff alone maps to the sentinel)
-              my_count += active ? 1 : 0;
-              kk[j] = active ? key : ZS_EMPTY;
-              my_min = min(my_min, kk[j]);             // the sentinel is neutral for the minimum
-              my_max1 = max(my_max1, kk[j] + 1u);      // ... and wraps to 0 here: largest key + 1
-            }
-            const int g0 = (x0 - a0[b]) & ~3, g1 = (xe - a0[b] + 3) & ~3;   // 4-key groups that overlap the span
-#pragma unroll
-            for (int j = 0; j < VEC; j += 4)
-              if (VEC == 4 || (k + j >= g0 && k + j < g1))
-                *reinterpret_cast<uint4*>(keys + s_base[r] + (k + j - g0)) = make_uint4(kk[j], kk[j + 1], kk[j + 2], kk[j + 3]);
-          }
+        for (int k = 0; k < 32 / ZW_ROWS; ++k) todo |= ((single_mask >> (k * ZW_ROWS)) & BM) ? 1u << k : 0u;
+#pragma unroll 1
+        while (todo) {
+          const int rb = ZW_ROWS * (__ffs(todo) - 1);
+          todo &= todo - 1;
+          const int rb2 = todo ? ZW_ROWS * (__ffs(todo) - 1) : -1;
+          todo &= todo - 1;
+          typename WarpSelect<T>::Batch A, B;
+          w.issue(base + rb, tab + rb, A);
+          if (rb2 >= 0) w.issue(base + rb2, tab + rb2, B);
+          w.template consume<sizeof(T) == 1>(base + rb, tab + rb, A);
+          if (rb2 >= 0) w.template consume<sizeof(T) == 1>(base + rb2, tab + rb2, B);
         }
       }
+      unsigned cm = complex_mask;
+      while (cm) {
+        const int r = __ffs(cm) - 1;
+        cm &= cm - 1;
+        select_complex_row(P, r0, r1, base + r, buf, hbuf, w, main_mode);
+      }
+      __syncwarp();
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      my_count += __shfl_xor_sync(0xffffffffu, my_count, o);
-      my_min = min(my_min, __shfl_xor_sync(0xffffffffu, my_min, o));
-      my_max1 = max(my_max1, __shfl_xor_sync(0xffffffffu, my_max1, o));
-    }
-    if (lane == 0) { atomicAdd(&s_count, my_count); atomicMin(&s_lowest, my_min); atomicMax(&s_highest1, my_max1); }
-    for (int i = tid; i < ZS_BINS; i += ZS_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    const int n = s_count;
+    const bool overflow = __any_sync(0xffffffffu, w.cnt > WS_CAP);
+    const int n = __reduce_add_sync(0xffffffffu, w.n_active);
+    const int below = __reduce_add_sync(0xffffffffu, w.below);
+    const int kept = __reduce_add_sync(0xffffffffu, w.cnt);
+    long long cells = w.cells;
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if (lane == 0) area[p] = cells;
     if (n == 0) {
-      if (tid == 0) out[p] = nanf_;
+      if (lane == 0) { out[p] = __int_as_float(0x7fc00000); state[p].what = WS_SKIP; }
+      continue;
+    }
+    if (!exact) {
+      // the final kernel takes it from here
+      table[WS_CAP * 32 + lane] = (unsigned)w.cnt;
+      if (lane == 0) { state[p].n_active = n; state[p].below = below; state[p].kept = overflow ? -1 : kept; }
       continue;
     }
     long long rank_lo, rank_hi;
@@ -1502,139 +1978,141 @@ zonal_select_fast_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
       rank_hi = (long long)ceil(frac);
       part = frac - floor(frac);
     }
-    // 4. A bracket [bk_lo, bk_hi] of keys around the wanted ranks from 32 evenly spaced
-    // samples (the sentinels sort behind every key, so ranks among all `total` slots are
-    // ranks among the active cells): sample positions +- ZS_MARGIN around the rank's share.
-    if (warp == 0) {
-      const unsigned mine = keys[(int)(((long long)lane * total) / 32)];
-      int rank = 0;
-      for (int j = 0; j < 32; ++j) {
-        const unsigned o = __shfl_sync(0xffffffffu, mine, j);
-        rank += (o < mine) || (o == mine && j < lane);
-      }
-      const int lo_at = (int)((rank_lo * 32) / total) - ZS_MARGIN;
-      const int hi_at = (int)((rank_hi * 32) / total) + 1 + ZS_MARGIN;
-      if (lo_at < 0 && lane == 0) s_kmin = s_lowest;            // the smallest / largest key
-      if (hi_at > 31 && lane == 0) s_kmax = s_highest1 - 1u;
-      if (rank == lo_at) s_kmin = mine;
-      if (rank == hi_at) s_kmax = mine;
-    }
-    __syncthreads();
-    unsigned bk_lo = s_kmin, bk_hi = min(s_kmax, ZS_EMPTY - 1u);
-    if (bk_lo > bk_hi) { bk_lo = 0u; bk_hi = ZS_EMPTY - 1u; }   // sentinels in the sample: no bracket
-    // the digit: ZS_DIGIT bits of (key - bk_lo), scaled so that the bracket fills the bins
-    const int shift = max(32 - __clz(bk_hi - bk_lo) - ZS_DIGIT, 0);
-    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
-    int below = 0, inside = 0;
-    const unsigned width = bk_hi - bk_lo;
-    const unsigned hist_at = (unsigned)__cvta_generic_to_shared(s_hist);
-    for (int i = tid; i < total / 4; i += ZS_THREADS) {
-      const uint4 v = k4[i];
-      const unsigned vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned rel = vv[j] - bk_lo;
-        below += vv[j] < bk_lo ? 1 : 0;
-        inside += rel <= width ? 1 : 0;
-        // if (rel <= width) ++s_hist[rel >> shift], as one predicated shared-memory reduction
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], 1;\n\t}"
-                     :: "r"(rel), "r"(width), "r"(hist_at + ((rel >> shift) << 2)) : "memory");
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      below += __shfl_xor_sync(0xffffffffu, below, o);
-      inside += __shfl_xor_sync(0xffffffffu, inside, o);
-    }
-    if (lane == 0) { atomicAdd(&s_below, below); atomicAdd(&s_inside, inside); }
-    __syncthreads();
-    unsigned klo, khi;
-    const long long in_lo = rank_lo - s_below, in_hi = rank_hi - s_below;
-    if (in_lo < 0 || in_hi >= s_inside) {
-      // the samples misjudged the distribution (rare): select over everything
-      block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
-    } else {
-      {
-        constexpr int PERT = ZS_BINS / ZS_THREADS;
-        int local[PERT], sum = 0;
-#pragma unroll
-        for (int j = 0; j < PERT; ++j) { local[j] = s_hist[tid * PERT + j]; sum += local[j]; }
-        int incl = sum;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        int before = 0;
-        for (int w = 0; w < warp; ++w) before += s_wsum[w];
-        const int excl = before + incl - sum;
-        if (in_lo >= excl && in_lo < excl + sum) {
-          int r = (int)in_lo - excl;
-#pragma unroll
-          for (int j = 0; j < PERT; ++j) {
-            if (r >= 0 && r < local[j]) { s_blo = tid * PERT + j; s_rlo = r; }
-            r -= local[j];
-          }
-        }
-        if (in_hi >= excl && in_hi < excl + sum) {
-          int r = (int)in_hi - excl;
-#pragma unroll
-          for (int j = 0; j < PERT; ++j) {
-            if (r >= 0 && r < local[j]) { s_bhi = tid * PERT + j; s_rhi = r; }
-            r -= local[j];
-          }
-        }
-        __syncthreads();
-      }
-      const int b_lo = s_blo, b_hi = s_bhi;
-      const int m = s_hist[b_lo];
-      if (shift == 0) {
-        klo = bk_lo + (unsigned)b_lo;          // one key per bin
-        khi = bk_lo + (unsigned)b_hi;
+    const long long in_lo = rank_lo - below, in_hi = rank_hi - below;
+    __syncwarp();
+    int e0, c0, e1, c1;
+    const int b_lo = in_lo >= 0 ? warp_find_bin(hist, in_lo, &e0, &c0, lane) : -1;
+    const int b_hi = in_hi >= 0 ? warp_find_bin(hist, in_hi, &e1, &c1, lane) : -1;
+    if (lane == 0) {
+      state[p].what = WS_SKIP;
+      if (b_lo >= 0 && b_hi >= 0) {
+        const T vlo = Key32<T>::value(lo + (unsigned)b_lo), vhi = Key32<T>::value(lo + (unsigned)b_hi);
+        out[p] = stat == GM_STAT_MEDIAN ? median_of<T>(vlo, vhi) : percentile_of<T>(vlo, vhi, part);
       } else {
-        // the keys of bin b_lo and, when the upper rank falls into a later bin, of that bin
-        // (a handful): its smallest key is the upper neighbour
-        const bool together = b_hi == b_lo;
-        const int m_all = m + (together ? 0 : s_hist[b_hi]);
-        if (m_all > ZS_CAND) {
-          block_select2<unsigned>(keys, total, rank_lo, rank_hi, &klo, &khi, s_hist8, &s_scratch);
-        } else {
-          for (int i = tid; i < total / 4; i += ZS_THREADS) {
-            const uint4 v = k4[i];
-            const unsigned vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const unsigned rel = vv[j] - bk_lo, d = rel >> shift;
-              if (rel <= width && (d == (unsigned)b_lo || d == (unsigned)b_hi)) s_cand[atomicAdd(&s_ncand, 1)] = vv[j];
-            }
-          }
-          __syncthreads();
-          // bin b_hi's keys sort behind bin b_lo's: ranks in the union
-          const int want_lo = s_rlo, want_hi = together ? s_rhi : m;
-          if (m_all <= 32) {
-            // one candidate per lane, ranked against the others
-            if (warp == 0) {
-              const unsigned mine = lane < m_all ? s_cand[lane] : ZS_EMPTY;
-              int rank = 0;
-              for (int j = 0; j < m_all; ++j) {
-                const unsigned o = __shfl_sync(0xffffffffu, mine, j);
-                rank += (o < mine) || (o == mine && j < lane);
-              }
-              if (lane < m_all && rank == want_lo) s_scratch.min_key = mine;
-              if (lane < m_all && rank == want_hi) s_kmax = mine;
-            }
-            __syncthreads();
-            klo = s_scratch.min_key;
-            khi = s_kmax;
-          } else {
-            block_select2<unsigned>(s_cand, m_all, (long long)want_lo, (long long)want_hi, &klo, &khi, s_hist8, &s_scratch);
-          }
-        }
+        work[2 + atomicAdd(work, 1)] = (int)p;     // the ranks fell outside the bracket
       }
     }
-    if (tid == 0) {
-      const T lo = Key32<T>::value(klo), hi = Key32<T>::value(khi);
-      out[p] = stat == GM_STAT_MEDIAN ? median_of<T>(lo, hi) : percentile_of<T>(lo, hi, part);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32 * WS_WARPS, WS_MIN_BLOCKS)
+zonal_select_final_kernel(int stat, double q, int64_t p_begin, int64_t p_end, int* __restrict__ counter,
+                          const SelectState* __restrict__ state, const unsigned* __restrict__ tables,
+                          float* __restrict__ out, int* __restrict__ work) {
+  extern __shared__ __align__(16) int ws_hist[];        // WS_WARPS x WS_BINS
+  __shared__ unsigned s_cand[WS_WARPS][32];
+  __shared__ int s_ncand[WS_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* hist = ws_hist + warp * WS_BINS;
+  const unsigned hist_at = (unsigned)__cvta_generic_to_shared(hist);
+  auto zero_hist = [&]() {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < WS_BINS / 32; ++j) hist[j * 32 + lane] = 0;
+    __syncwarp();
+  };
+  for (;;) {
+    int64_t p = 0;
+    if (lane == 0) p = p_begin + atomicAdd(counter, 1);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= p_end) break;
+    if (state[p].what != WS_TABLE) continue;
+    const int n = state[p].n_active, below = state[p].below, kept = state[p].kept;
+    const unsigned lo = state[p].lo, hi = state[p].hi;
+    const unsigned* column = tables + (size_t)(p - p_begin) * WS_TABLE_WORDS + lane;
+    long long rank_lo, rank_hi;
+    double part = 0.0;
+    if (stat == GM_STAT_MEDIAN) {
+      rank_lo = (n - 1) / 2; rank_hi = n / 2;
+    } else {
+      const double frac = (double)(n - 1) * (q / 100.0);
+      rank_lo = (long long)floor(frac);
+      rank_hi = (long long)ceil(frac);
+      part = frac - floor(frac);
+    }
+    long long in_lo = rank_lo - below, in_hi = rank_hi - below;
+    unsigned klo = 0u, khi = 0u;
+    bool found = false;
+    if (kept >= 0 && in_lo >= 0 && in_hi < kept) {
+      const int mine = (int)column[WS_CAP * 32];
+      const int most = __reduce_max_sync(0xffffffffu, mine);
+      // every lane walks `most` slots (its own beyond `mine` are skipped by predicate), eight
+      // loads in flight; `sweep(f)` calls f(key, real) for each of the lane's kept cells
+      auto sweep = [&](auto&& f) {
+        for (int s = 0; s < most; s += 8) {
+          unsigned wd[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) wd[j] = s + j < mine ? __ldcg(column + (s + j) * 32) : 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f(StashWord<T>::key(wd[j]), s + j < mine);
+        }
+      };
+      unsigned from = lo, range = hi - lo;
+      for (;;) {
+        const int sh = max(32 - __clz(range) - WS_BITS, 0);
+        zero_hist();
+        sweep([&](unsigned k, bool ok) {
+          const unsigned rel = k - from;
+          red_shared_inc(hist_at + ((rel >> sh) << 2), ok & (rel <= range));
+        });
+        __syncwarp();
+        int e_lo = 0, c_lo = 0, e_hi = 0, c_hi = 0;
+        const int b_lo = warp_find_bin(hist, in_lo, &e_lo, &c_lo, lane);
+        const int b_hi = warp_find_bin(hist, in_hi, &e_hi, &c_hi, lane);
+        if (b_lo < 0 || b_hi < 0) break;                 // (cannot happen: the ranks lie in the table)
+        if (b_lo != b_hi) {
+          // neighbouring ranks in different bins: the largest key of the one, the smallest of the other
+          unsigned a = 0u, b = 0xffffffffu;
+          sweep([&](unsigned k, bool ok) {
+            const unsigned rel = k - from;
+            const int d = (int)(rel >> sh);
+            const bool in = ok & (rel <= range);
+            a = max(a, (in & (d == b_lo)) ? k : 0u);
+            b = min(b, (in & (d == b_hi)) ? k : 0xffffffffu);
+          });
+          klo = __reduce_max_sync(0xffffffffu, a);
+          khi = __reduce_min_sync(0xffffffffu, b);
+          found = true;
+          break;
+        }
+        if (sh == 0) { klo = khi = from + (unsigned)b_lo; found = true; break; }
+        if (c_lo <= 32) {
+          // the bin's keys, one per lane, ranked against each other
+          if (lane == 0) s_ncand[warp] = 0;
+          __syncwarp();
+          sweep([&](unsigned k, bool ok) {
+            const unsigned rel = k - from;
+            if (ok && rel <= range && (int)(rel >> sh) == b_lo) s_cand[warp][atomicAdd(&s_ncand[warp], 1) & 31] = k;
+          });
+          __syncwarp();
+          const unsigned key = lane < c_lo ? s_cand[warp][lane] : 0xffffffffu;
+          int rank = 0;
+          for (int j = 0; j < c_lo; ++j) {
+            const unsigned o = __shfl_sync(0xffffffffu, key, j);
+            rank += (o < key) || (o == key && j < lane);
+          }
+          const unsigned m_lo = __ballot_sync(0xffffffffu, lane < c_lo && rank == (int)(in_lo - e_lo));
+          const unsigned m_hi = __ballot_sync(0xffffffffu, lane < c_lo && rank == (int)(in_hi - e_lo));
+          if (m_lo && m_hi) {
+            klo = __shfl_sync(0xffffffffu, key, __ffs(m_lo) - 1);
+            khi = __shfl_sync(0xffffffffu, key, __ffs(m_hi) - 1);
+            found = true;
+          }
+          break;
+        }
+        from += (unsigned)b_lo << sh;
+        range = (1u << sh) - 1u;
+        in_lo -= e_lo; in_hi -= e_lo;
+      }
+    }
+    if (lane == 0) {
+      if (found) {
+        const T vlo = Key32<T>::value(klo), vhi = Key32<T>::value(khi);
+        out[p] = stat == GM_STAT_MEDIAN ? median_of<T>(vlo, vhi) : percentile_of<T>(vlo, vhi, part);
+      } else {   // ranks outside the bracket, or more bracket cells than a column holds
+        work[2 + atomicAdd(work, 1)] = (int)p;
+      }
     }
   }
 }
@@ -1906,41 +2384,77 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   void* dlist = nullptr;
   int n_listed = 0;
   std::vector<int> listed;
+  bool area_done = false;
   if (order_stat) {
     GM_TRY(cudaMallocAsync(&dlist, sizeof(int) * (size_t)(np_ + 2), s));
     scratch_list = dlist;
-    // float32 and integers up to 4 bytes; the all-ones key is the kernel's "no cell" mark, so a
-    // 4-byte integer raster qualifies only when the value with that key (the dtype maximum) is
-    // its no-data value
-    bool fast = sizeof(T) <= 4 && !thresholds && out;
-    if (std::is_integral<T>::value && sizeof(T) == 4)
-      fast = fast && has_nodata && nd == std::numeric_limits<T>::max();
-    if (fast) {
+    // the streaming select takes float32 and integers up to 4 bytes (32-bit sortable keys)
+    const bool streaming = sizeof(T) <= 4 && !thresholds && out;
+    constexpr int svec = 4;   // the kernels' cells per load
+    const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (svec - 1));
+    const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
+                            (((int64_t)u.dev.height * u.dev.width + mis) % svec) != 0;
+    if (streaming) {
+      // one warp per polygon, three kernels (bracket, main pass, final ranks) per chunk of
+      // polygons; the bracket's cells of a chunk wait in per-polygon tables between the last two
       GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
       GM_TRY(cudaMemsetAsync(dlist, 0, 2 * sizeof(int), s));
-      constexpr int svec = 4;   // the kernel's cells per load
-      const int mis = (int)(((uintptr_t)raster.dev / sizeof(T)) & (svec - 1));
-      const int edge_scalar = ((uintptr_t)raster.dev % sizeof(T)) != 0 || mis != 0 ||
-                              (((int64_t)u.dev.height * u.dev.width + mis) % svec) != 0;
-      int dev = 0, smem_max = 0;
-      GM_TRY(cudaGetDevice(&dev));
-      GM_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      // three blocks per SM: a third of the 227 KB minus the static tables (~15 k cells per polygon)
-      const int dyn = (smem_max - 3 * 18 * 1024) / 3 / 16 * 16;
+      const int64_t chunk = np_ < 32768 ? np_ : 32768;
+      const int64_t n_chunks = (np_ + chunk - 1) / chunk;
+      void *dstate = nullptr, *dcounters = nullptr;
+      GM_TRY(cudaMallocAsync(&dstate, sizeof(SelectState) * np_, s));
+      GM_TRY(cudaMallocAsync(&dcounters, sizeof(int) * 3 * n_chunks, s));
+      GM_TRY(cudaMemsetAsync(dcounters, 0, sizeof(int) * 3 * n_chunks, s));
+      GM_TRY(cudaMallocAsync(&dbig, sizeof(unsigned) * (size_t)chunk * WS_TABLE_WORDS, s));
       if constexpr (sizeof(T) <= 4) {
-        GM_TRY(cudaFuncSetAttribute(zonal_select_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-        zonal_select_fast_kernel<T><<<poly_grid(np_), ZS_THREADS, dyn, s>>>(
-            u.dev, (const T*)raster.dev, nd, has_nodata, mis, edge_scalar, stat, q, dyn / 4,
-            (float*)dout, (long long*)darea, (int*)dlist);
+        constexpr int ws_smem = WS_WARPS * WS_BINS * (int)sizeof(int);
+        GM_TRY(cudaFuncSetAttribute(zonal_select_bracket_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+        GM_TRY(cudaFuncSetAttribute(zonal_select_main_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+        GM_TRY(cudaFuncSetAttribute(zonal_select_final_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+        for (int64_t c = 0; c < n_chunks; ++c) {
+          const int64_t p0 = c * chunk, p1 = p0 + chunk < np_ ? p0 + chunk : np_;
+          int64_t wblocks = (p1 - p0 + WS_WARPS - 1) / WS_WARPS;
+          if (wblocks > (int64_t)sm_count() * WS_MIN_BLOCKS) wblocks = (int64_t)sm_count() * WS_MIN_BLOCKS;
+          int* counters = (int*)dcounters + 3 * c;
+          zonal_select_bracket_kernel<T><<<(unsigned)wblocks, 32 * WS_WARPS, ws_smem, s>>>(
+              u.dev, (const T*)raster.dev, nd, has_nodata, stat, q, p0, p1, counters, (SelectState*)dstate,
+              (float*)dout, (long long*)darea, (int*)dlist);
+          int64_t mblocks = (p1 - p0 + WS_WARPS - 1) / WS_WARPS;
+          if (mblocks > (int64_t)sm_count() * WS_MAIN_BLOCKS) mblocks = (int64_t)sm_count() * WS_MAIN_BLOCKS;
+          zonal_select_main_kernel<T><<<(unsigned)mblocks, 32 * WS_WARPS, ws_smem, s>>>(
+              u.dev, (const T*)raster.dev, nd, has_nodata, mis, edge_scalar, stat, q, p0, p1, counters + 1,
+              (SelectState*)dstate, (unsigned*)dbig, (float*)dout, (long long*)darea, (int*)dlist);
+          zonal_select_final_kernel<T><<<(unsigned)wblocks, 32 * WS_WARPS, ws_smem, s>>>(
+              stat, q, p0, p1, counters + 2, (const SelectState*)dstate, (const unsigned*)dbig, (float*)dout,
+              (int*)dlist);
+          count_launch(3);
+        }
       }
       GM_TRY(cudaGetLastError());
+      // the covered cells of the deferred polygons (the kernel reads the list's length on the
+      // device), then ONE synchronisation for the list and all the counts
+      zonal_area_kernel<<<poly_grid(np_ < 1024 ? np_ : 1024), PG_THREADS, smem_scan, s>>>(
+          u.dev, (long long*)darea, (const int*)dlist);
+      GM_TRY(cudaGetLastError());
       count_launch();
-      GM_TRY(cudaMemcpyAsync(&n_listed, dlist, sizeof(int), cudaMemcpyDeviceToHost, s));
+      const int64_t head = np_ < 4096 ? np_ : 4096;
+      std::vector<int> front(head + 2);
+      GM_TRY(cudaMemcpyAsync(front.data(), dlist, sizeof(int) * (head + 2), cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaMemcpyAsync(area, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
       GM_TRY(cudaStreamSynchronize(s));
-      listed.resize(n_listed);
+      area_done = true;
+      cudaFreeAsync(dbig, s);
+      cudaFreeAsync(dstate, s);
+      cudaFreeAsync(dcounters, s);
+      dbig = nullptr;
+      n_listed = front[0];
+      listed.assign(front.begin() + 2, front.begin() + 2 + (n_listed < head ? n_listed : head));
       if (getenv("GM_DEBUG_ZONAL")) fprintf(stderr, "gm_zonal_stats: %d of %lld polygons deferred to the generic select\n", n_listed, (long long)np_);
-      if (n_listed > 0)
+      if (n_listed > head) {
+        listed.resize(n_listed);
         GM_TRY(cudaMemcpyAsync(listed.data(), (const int*)dlist + 2, sizeof(int) * n_listed, cudaMemcpyDeviceToHost, s));
+        GM_TRY(cudaStreamSynchronize(s));
+      }
     } else {
       n_listed = (int)np_;
       listed.resize(np_);
@@ -1950,14 +2464,16 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       GM_TRY(cudaMemcpyAsync(dlist, host.data(), sizeof(int) * (np_ + 2), cudaMemcpyHostToDevice, s));
       GM_TRY(cudaStreamSynchronize(s));
     }
-    if (n_listed > 0) {
-      // pixel centres inside the listed polygons (no raster access): `covered` and buffer sizes
-      zonal_area_kernel<<<poly_grid(n_listed), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea, (const int*)dlist);
-      GM_TRY(cudaGetLastError());
-      count_launch();
+    if (!area_done) {
+      if (n_listed > 0) {
+        // pixel centres inside the listed polygons (no raster access): `covered` and buffer sizes
+        zonal_area_kernel<<<poly_grid(n_listed), PG_THREADS, smem_scan, s>>>(u.dev, (long long*)darea, (const int*)dlist);
+        GM_TRY(cudaGetLastError());
+        count_launch();
+      }
+      GM_TRY(cudaMemcpyAsync(area, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaStreamSynchronize(s));
     }
-    GM_TRY(cudaMemcpyAsync(area, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
-    GM_TRY(cudaStreamSynchronize(s));
   }
 
   if (!order_stat || partial) {

@@ -347,7 +347,7 @@ def zonal_striped(geometries, local, no_data_value, bbox, height, rows, statisti
 
 
 def _zonal_order_by_exchange(soup, local, no_data_value, stripe_bbox, has_rows, statistic, percentile,
-                             threshold_values, group):
+                             threshold_values, group, with_covered=False):
     """Median / percentile of polygons that reach beyond a neighbouring stripe: every rank
     extracts the active values of its rows (gm_zonal_values), the segments are routed to the
     polygons' owner ranks ``p % world`` and selected there (gm_segment_order_stat)."""
@@ -382,7 +382,17 @@ def _zonal_order_by_exchange(soup, local, no_data_value, stripe_bbox, has_rows, 
         values = np.zeros(0, dtype=local.dtype)
     owned, offsets, merged = exchange_segments(counts, values, group)
     mine = segment_order_statistic(merged, offsets, statistic, percentile)
-    return _gather_owned(mine, owned, n, group)
+    result = _gather_owned(mine, owned, n, group)
+    if not with_covered:
+        return result
+    import torch
+
+    dist = _dist()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    total = torch.from_numpy(covered).to(dev)
+    if _world(group)[1] > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return result, total.cpu().numpy()
 
 
 def _polygon_rows(soup, bbox, height):
@@ -495,6 +505,26 @@ def _order_stat_call(soup, payload, no_data_value, bbox, threshold_values, stati
     return out, covered
 
 
+def _rank_soups(soup, bbox, height, world, rank):
+    """This rank's share of the order statistics, cached on the soup: the polygons it owns that
+    lie inside its stripe and the ones that cross into the next stripe, each as ids + a soup of
+    just those polygons (kept resident in HBM when a device is in use), so that a call visits
+    ~N / world polygons instead of all N."""
+    key = (tuple(bbox), int(height), int(world), int(rank))
+    cache = getattr(soup, "_rank_soups", None)
+    if cache is None:
+        cache = soup._rank_soups = {}
+    hit = cache.get(key)
+    if hit is None:
+        owner, near, far, crosses, _, _ = _stripe_ownership(soup, bbox, height, world)
+        top, bottom = _polygon_rows(soup, bbox, height)
+        outside = (bottom < 0) | (top > height - 1)
+        inside_ids = np.nonzero((owner == rank) & ~crosses & ~outside)[0]
+        near_ids = np.nonzero((owner == rank) & near)[0]
+        hit = cache[key] = (inside_ids, soup.subset(inside_ids), near_ids, soup.subset(near_ids))
+    return hit
+
+
 def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statistic, percentile,
                          threshold_values, group):
     """Median / percentile over a raster sharded in row stripes.
@@ -503,9 +533,12 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
     inside one stripe is selected there by the single-GPU kernel; one that crosses into the
     next stripe is selected by its owner on a boundary strip = the owner's last rows + the
     rows it needs from its southern neighbour (one ncclSend/ncclRecv of a few hundred rows).
-    Only polygons that reach beyond the neighbouring stripe go through the value exchange
-    (`_zonal_order_by_exchange`).  The owners' results are all-gathered."""
+    Each rank only visits the polygons it owns (`_rank_soups`).  The owners' results and
+    covered-cell counts travel in ONE all-gather.  Only polygons that reach beyond the
+    neighbouring stripe go through the value exchange (`_zonal_order_by_exchange`)."""
     import torch
+
+    from . import _native
 
     rank, world = _world(group)
     dist = _dist()
@@ -514,17 +547,22 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
     x1, y1, x2, y2 = bbox
     dy = (y2 - y1) / height
     owner, near, far, crosses, halo, keep = _stripe_ownership(soup, bbox, height, world)
+    inside_ids, inside_soup, near_ids, near_soup = _rank_soups(soup, bbox, height, world, rank)
+    on_device = _native.is_device(local) or hasattr(local, "data_ptr")
+    if on_device:
+        inside_soup.to_device()
+        near_soup.to_device()
     tensor = _as_tensor(local) if r1 > r0 else None
     stripe_bbox = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
-    out = np.full(n, np.nan, dtype=np.float32)
-    covered = np.zeros(n, dtype=np.int64)
-    if r1 > r0:
-        got, cov = _order_stat_call(soup, local, no_data_value, stripe_bbox, threshold_values, statistic, percentile)
-        mine = (owner == rank) & ~crosses
-        out[mine] = got[mine]
-        covered[:] = cov
-    # boundary rows: my first rows go north, the southern neighbour's first rows come here
-    # (NCCL moves device memory, gloo host memory; the strip is assembled next to the stripe)
+    # row 0: the statistic of the polygons this rank owns (others stay 0), row 1: their covered cells
+    mine = np.zeros((2, n), dtype=np.float64)
+    owned = np.zeros(n, dtype=bool)
+
+    def thresholds_of(ids):
+        return None if threshold_values is None else np.asarray(threshold_values)[ids]
+
+    # boundary rows first (asynchronous under NCCL): my first rows go north, the southern
+    # neighbour's first rows come here; the select of the inner polygons runs meanwhile
     link = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     ops, recv = [], None
     if rank > 0 and halo[rank - 1] > 0:
@@ -533,34 +571,44 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
     if rank < world - 1 and halo[rank] > 0:
         recv = torch.empty((1, int(halo[rank]), tensor.shape[2]), dtype=tensor.dtype, device=link)
         ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
-    if ops:
-        for work in dist.batch_isend_irecv(ops):
-            work.wait()
-    if recv is not None:
+    pending = dist.batch_isend_irecv(ops) if ops else []
+    if r1 > r0 and len(inside_ids):
+        got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
+                                    statistic, percentile)
+        mine[0, inside_ids], mine[1, inside_ids] = got, cov
+        owned[inside_ids] = True
+    for work in pending:
+        work.wait()
+    if recv is not None and len(near_ids):
         k = int(keep[rank])
         strip = torch.cat([tensor[:, r1 - r0 - k:], recv.to(tensor.device)], dim=1).contiguous()
         strip_bbox = (x1, y2 - (r1 + int(halo[rank])) * dy, x2, y2 - (r1 - k) * dy)
         if strip.is_cuda:
             torch.cuda.current_stream().synchronize()   # the strip is complete before the library reads it
-        got, _ = _order_stat_call(soup, _as_payload(strip), no_data_value, strip_bbox, threshold_values,
-                                  statistic, percentile)
-        mine = (owner == rank) & near
-        out[mine] = got[mine]
-    # owners publish their results; covered cells add up over the stripes
+        got, cov = _order_stat_call(near_soup, _as_payload(strip), no_data_value, strip_bbox,
+                                    thresholds_of(near_ids), statistic, percentile)
+        mine[0, near_ids], mine[1, near_ids] = got, cov
+        owned[near_ids] = True
+    # owners publish their results and covered-cell counts: one all-gather of a (2, N) block
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    gathered = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(world)]
-    dist.all_gather(gathered, torch.from_numpy(out).to(dev), group=group)
-    gathered = torch.stack(gathered).cpu().numpy()
-    result = gathered[owner, np.arange(n)]
-    cov = torch.from_numpy(covered).to(dev)
-    dist.all_reduce(cov, op=dist.ReduceOp.SUM, group=group)
-    covered = cov.cpu().numpy()
+    block = torch.from_numpy(mine).to(dev)
+    gathered = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group) if dev == "cuda" else \
+        dist.all_gather(list(gathered.unbind(0)), block, group=group)
+    gathered = gathered.cpu().numpy()
+    at = np.arange(n)
+    result = gathered[owner, 0, at].astype(np.float32)
+    covered = gathered[owner, 1, at].astype(np.int64)
+    top, bottom = _polygon_rows(soup, bbox, height)
+    nowhere = (bottom < 0) | (top > height - 1)          # outside the raster: nobody selected them
+    result[nowhere] = np.nan
+    covered[nowhere] = 0
     if far.any():   # same on every rank: the collectives inside line up
         ids = np.nonzero(far)[0]
         sub = soup.subset(ids)
-        sub_thresholds = None if threshold_values is None else np.asarray(threshold_values)[ids]
-        result[ids] = _zonal_order_by_exchange(sub, local, no_data_value, stripe_bbox, r1 > r0, statistic,
-                                               percentile, sub_thresholds, group)
+        result[ids], covered[ids] = _zonal_order_by_exchange(
+            sub, local, no_data_value, stripe_bbox, r1 > r0, statistic, percentile, thresholds_of(ids), group,
+            with_covered=True)
     return result, np.nonzero(covered == 0)[0].tolist()
 
 

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--temporal-size", type=int, default=4096, help="8192 = cfg5 (98 GB of float32 at 365 frames)")
     ap.add_argument("--temporal-stats", default="sum,max,mean,median")
     ap.add_argument("--temporal-dtype", default="f4", choices=["f4", "i2"])
+    ap.add_argument("--zonal-size", type=int, default=0, help="raster edge of the zonal leg (40000 = cfg4)")
+    ap.add_argument("--zonal-grid", type=int, default=0, help="polygons per side (316 = cfg4)")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
 
@@ -137,10 +139,16 @@ def main():
 
     # ---- zonal statistics (cfg4 scaled: 16k x 16k, 128 x 128 polygons) ---------------------------
     if not only or any(o.startswith(("zonal", "rasterize")) for o in only):
-        r = torch.rand(1, n, n, device="cuda") * 100
-        r[torch.rand(1, n, n, device="cuda") < 0.02] = nodata
+        if args.zonal_size:
+            n = args.zonal_size
+        r = torch.empty(1, n, n, device="cuda")
+        rows = max(1, (1 << 27) // n)
+        for a in range(0, n, rows):   # chunked: bounded temporaries next to a 6.4 GB raster
+            block = r[0, a:a + rows]
+            block.uniform_(0, 100)
+            block[torch.rand(block.shape, device="cuda") < 0.02] = nodata
         rd = wrap(r)
-        g = int(128 * args.scale)
+        g = args.zonal_grid or int(128 * args.scale)
         polys = workloads.cfg4_polygons(n, g)   # the generator bench.py and the parity tests use
         bbox = (0, 0, n, n)
         soup = utils.PolygonSoup(polys).to_device()   # CSR build (6 us / polygon) + upload kept out of the timing
