@@ -1,22 +1,37 @@
 """Benchmark of the per-tile raster compute path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--legs chain,zonal,...]
 
-Workload at every N: BASELINE.json configs[1] -- Reclassify + Clip + Step +
-IsData on a 16384 x 16384 int16 / float32 MemorySource pair -- one such raster
-pair per GPU (weak scaling, no data-path collective: pixels are independent).
-A step is one pass of the fused chain over the whole raster pair.
+Headline workload at every N: BASELINE.json configs[1] -- Reclassify + Clip + Step + IsData on a
+16384 x 16384 int16 / float32 MemorySource pair -- one such raster pair per GPU (weak scaling, no
+data-path collective: pixels are independent).  A step is one pass of the fused chain.
 
   value     Gpixel/s with the inputs resident in HBM (CUDA events around K launches)
-  e2e       the same metric through ``view.get_data(**request)`` with host NumPy
-            inputs: pinned H2D of both rasters and D2H of the result in every step
-  roofline  algorithmic bytes (2 + 4 in, 1 out = 7 B/px) / measured kernel time
-            against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle port of the same chain (NumPy, all host threads)
-            on a bounded row-stripe sample of the same inputs
+  e2e       the same metric through ``view.get_data(**request)`` with host NumPy inputs: pinned
+            H2D of both rasters and D2H of the result in every step
+  roofline  algorithmic bytes (2 + 4 in, 1 out = 7 B/px) / measured kernel time against
+            MEASURED_PEAKS.json hbm_gbs; ``traffic`` = DRAM bytes per launch from the ncu capture
+            listed in profiles/r02_dram_traffic.json (null when there is none for this size)
+  cpu_baseline  the reference's CPU path for the same chain on the box's host cores (the real
+            reference ``process`` functions when the reference checkout exists, else the oracle
+            port), whole 16384 x 16384 request in 2048 x 2048 tiles on a thread pool
 
-``--impl reference`` times that CPU port as the reference arm (the reference is
-pure NumPy/SciPy; its own package cannot be imported without GDAL).
+The other configurations of BASELINE.json are ``striped`` legs of the same JSON line -- ONE
+workload sharded in row stripes over the N ranks (strong scaling; at N = 1 the single-GPU path):
+
+  stencils  configs[2]: Smooth(5) / MovingMax(11) / HillShade on ONE 32768 x 32768 DEM, halo
+            exchange (ncclSend/Recv) + kernel per step
+  zonal     configs[3]: AggregateRaster mean / max / p90 of ~100 k polygons over ONE
+            40000 x 40000 raster: stripe partials + all-reduce, order statistics by stripe owners
+  temporal  configs[4]: TemporalAggregate sum / max over ONE 365 x 8192 x 8192 stack sharded by
+            rows (no collective); at N = 1 also Cumulative, std and median on the first 64 frames
+
+Each striped entry carries its own ``roofline`` (algorithmic bytes / time against N x the measured
+HBM peak) and, at N > 1, ``single_gpu_ms`` (the same operation on the whole workload, measured on
+rank 0 in the same run) and the speed-up over it.
+
+``--impl reference`` times the CPU arm alone and prints the same JSON line with
+``"impl": "reference"``.
 """
 import argparse
 import json
@@ -34,6 +49,7 @@ sys.path.insert(0, ROOT)
 METRIC = "fused raster chain throughput (Reclassify+Clip+Step+IsData)"
 UNIT = "Gpixel/s"
 BYTES_PER_PIXEL = 7  # int16 + float32 in, bool out
+ALL_LEGS = "chain,stencils,zonal,temporal"
 
 
 def parse_args():
@@ -42,94 +58,63 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=16384, help="raster edge in pixels")
-    ap.add_argument("--cpu-sample-rows", type=int, default=2048)
+    ap.add_argument("--size", type=int, default=16384, help="raster edge of the chain (cfg2)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--legs", default=ALL_LEGS, help="comma list of chain,stencils,zonal,temporal")
+    ap.add_argument("--dem-size", type=int, default=32768, help="raster edge of the stencil leg (cfg3)")
     ap.add_argument("--zonal-size", type=int, default=40000, help="raster edge of the zonal leg (cfg4)")
     ap.add_argument("--zonal-grid", type=int, default=316, help="polygons per side of the zonal leg")
-    ap.add_argument("--zonal-steps", type=int, default=10)
-    ap.add_argument("--no-zonal", action="store_true", help="skip the AggregateRaster (cfg4) leg")
+    ap.add_argument("--temporal-frames", type=int, default=365)
+    ap.add_argument("--temporal-size", type=int, default=8192)
+    ap.add_argument("--leg-steps", type=int, default=10, help="timed calls per striped operation")
+    ap.add_argument("--no-zonal", action="store_true", help="(kept for old command lines) skip the zonal leg")
+    ap.add_argument("--no-single", action="store_true", help="skip the single-GPU reference runs at N > 1")
     ap.add_argument("--profile", action="store_true",
-                    help="kernel-resident loop only (for ncu): no e2e, no CPU baseline")
-    return ap.parse_args()
+                    help="kernel-resident chain loop only (for ncu): no e2e, no CPU baseline, no other legs")
+    args = ap.parse_args()
+    args.legs = [x for x in args.legs.split(",") if x]
+    if args.no_zonal and "zonal" in args.legs:
+        args.legs.remove("zonal")
+    if args.profile:
+        args.legs = ["chain"]
+    return args
 
 
 # ----------------------------------------------------------------------------
-# CPU baseline (oracle port, threaded over row tiles)
+# CPU arm (reference process functions or their oracle port, threaded over tiles)
 # ----------------------------------------------------------------------------
-
-
-def cpu_chain_throughput(ints, floats, rows, repeats, threads):
-    """Gpixel/s of the oracle chain on the first ``rows`` rows, tiled over threads."""
-    from concurrent.futures import ThreadPoolExecutor
-
-    from dask_geomodeling_b200.workloads import CFG2_PAIRS
-    from oracle import workloads as ow
-
-    rows = min(rows, ints.shape[1])
-    tile = max(rows // (threads * 2), 64)
-    bounds = [(r, min(r + tile, rows)) for r in range(0, rows, tile)]
-
-    def work(b):
-        r0, r1 = b
-        (isdata, _), _ = ow.cfg2(ints[:, r0:r1], floats[:, r0:r1], CFG2_PAIRS)
-        return int(isdata.sum())
-
-    best = None
-    with ThreadPoolExecutor(threads) as pool:
-        list(pool.map(work, bounds[: threads]))  # warm-up
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            list(pool.map(work, bounds))
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    pixels = rows * ints.shape[2]
-    return pixels / best / 1e9, pixels, best
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from dask_geomodeling_b200 import workloads
+    from oracle import reference_chain
+
     size = args.size
-    threads = os.cpu_count() or 1
-    rows = min(args.cpu_sample_rows, size)
-    # only the sampled stripe is generated: same generator, same seed, first rows
-    ints, floats = _stripe(size, rows)
-    times = []
-    for step in range(args.warmup + args.steps):
-        gpx, pixels, dt = cpu_chain_throughput(ints, floats, rows, 1, threads)
-        if step >= args.warmup:
-            times.append(dt)
+    ints, floats = workloads.cfg2_arrays(size, seed=43)
+    times, kind, threads, checksum = reference_chain.time_chain(
+        ints, floats, workloads.CFG2_PAIRS, steps=args.steps, warmup=args.warmup)
     ms = 1e3 * sum(times) / len(times)
-    value = pixels / (ms / 1e3) / 1e9
-    sample = "first {} rows x {} cols of the {}x{} workload per step".format(rows, size, size, size)
+    value = size * size / (ms / 1e3) / 1e9
+    sample = "whole {0}x{0} request per step, {1} tiles of 2048 x 2048 on {2} threads".format(
+        size, len(reference_chain.tiles(size, size)), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16/float32->bool", "data": "synthetic",
-        "config": {"workload": "cfg2 Reclassify+Clip+Step+IsData {}x{} int16/float32".format(size, size),
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": "cfg2 Reclassify+Clip+Step+IsData {0}x{0} int16/float32".format(size),
+                   "same_config": True, "checksum_true_pixels": checksum},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    if not args.no_zonal:
-        # the zonal leg of the metric on the CPU: the reference's aggregate_polygons restated
-        gpx, seconds = cpu_zonal_throughput()
-        line["zonal"] = {"mean": {"value": gpx, "unit": UNIT}, "cores": 1, "kind": "port",
-                         "sample": "mean of 1024 polygons over 4096 x 4096 float32 (cfg4 scaled), {:.1f} s".format(seconds)}
+    if "zonal" in args.legs:
+        gpx, seconds, zthreads, zkind = reference_chain.time_zonal()
+        line["zonal"] = {"mean": {"value": gpx, "unit": UNIT}, "cores": zthreads, "kind": zkind,
+                         "sample": "mean of 1024 polygons over 4096 x 4096 float32 (cfg4 scaled), "
+                                   "{:.1f} s".format(seconds)}
     print(json.dumps(line))
-
-
-def _stripe(size, rows):
-    from dask_geomodeling_b200 import workloads
-
-    rng = np.random.default_rng(43)
-    shape = (1, rows, size)
-    ints = workloads._with_nodata(rng, rng.integers(0, 50, shape, dtype=np.int16), 32767, 0.05)
-    floats = workloads._with_nodata(rng, rng.uniform(0, 100, shape).astype(np.float32),
-                                    workloads.F32_MAX, 0.05)
-    return ints, floats
 
 
 # ----------------------------------------------------------------------------
@@ -140,7 +125,7 @@ def _stripe(size, rows):
 class NvmlSampler(object):
     """SM clock and throttle reasons sampled through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.0005):
         import pynvml
 
         self.nvml = pynvml
@@ -154,10 +139,8 @@ class NvmlSampler(object):
 
     def _loop(self):
         n = self.nvml
-        flags = {
-            "hw_slowdown": n.nvmlClocksEventReasonHwSlowdown if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-            "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
-        }
+        flags = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "sw_power_cap": 0x4}
         while self.running:
             try:
                 self.sm.append(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
@@ -183,14 +166,7 @@ class NvmlSampler(object):
                 "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
 
 
-def make_sampler(index):
-    try:
-        return NvmlSampler(index)
-    except Exception:
-        return ClockSampler(index)
-
-
-class ClockSampler(object):
+class SmiSampler(object):
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -201,7 +177,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -235,135 +211,405 @@ class ClockSampler(object):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def cpu_zonal_throughput(size=4096, grid=32, statistic="mean", q=None):
-    """The reference's aggregate_polygons (geometry/aggregate.py:113-203) as the oracle restates
-    it: bucketize the polygons into sets of disjoint boxes, burn one label raster per bucket
-    (GDAL fill rule, oracle/polyfill.c) and reduce with scipy.ndimage labelled statistics.
-    One thread, like the reference's process function.  Returns (Gpixel/s, seconds)."""
-    from dask_geomodeling_b200 import workloads
-    from dask_geomodeling_b200.geometry.aggregate import bucketize
-    from oracle import polyfill
-    from oracle import raster as R
-
-    rng = np.random.default_rng(11)
-    frame = rng.uniform(0, 100, (size, size)).astype(np.float32)
-    frame[rng.random((size, size)) < 0.02] = workloads.F32_MAX
-    rings = workloads.cfg4_rings(size, grid)
-    bbox = (0, 0, size, size)
-    t0 = time.perf_counter()
-    boxes = [(r[:, 0].min(), r[:, 1].min(), r[:, 0].max(), r[:, 1].max()) for r in rings]
-    label_sets = []
-    for ids in bucketize(boxes):
-        labels = polyfill.burn_index([[rings[i]] for i in ids], bbox, size, size)
-        labelled = labels != np.iinfo(np.int32).max
-        labels[labelled] = np.asarray(ids, dtype=np.int32)[labels[labelled]]
-        label_sets.append((labels, ids))
-    R.zonal_from_labels(frame, workloads.F32_MAX, label_sets, len(rings), statistic, q)
-    seconds = time.perf_counter() - t0
-    return size * size / seconds / 1e9, seconds
+def make_sampler(index):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return SmiSampler(index)
 
 
 # ----------------------------------------------------------------------------
-# zonal statistics leg (BASELINE.json configs[3])
+# helpers of the GPU arm
 # ----------------------------------------------------------------------------
 
 
-def run_zonal(args, torch, dist, stream, rank, world, peak, host_raster):
-    """AggregateRaster mean / max / p90 of ~100 k polygons over a 40000 x 40000 float32 raster
-    resident in HBM, one raster + polygon set per GPU (weak scaling; a striped single raster
-    would add one all-reduce of N-vectors).  Timed per call of
-    ``aggregate_polygons`` -- the function AggregateRaster.process hands the raster to --
-    including the download of the per-polygon results; pixels/s = H * W / time."""
-    from dask_geomodeling_b200 import _native, utils, workloads
-    from dask_geomodeling_b200.core import fusion
-    from dask_geomodeling_b200.geometry import aggregate
+def bind_to_gpu_numa_node(local_rank, ranks_on_box):
+    """Pin this rank to the host cores of its GPU's NUMA node (and thereby, by first touch, its
+    host rasters and pinned staging to that node's memory): with every rank on node 0 the
+    end-to-end leg at 8 GPUs was bound by one socket's memory and PCIe root.  The
+    node's cores are divided among the ranks that share it.  Best effort: returns what was done."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import pynvml
 
-    n, g = args.zonal_size, args.zonal_grid
-    raster = torch.empty((1, n, n), dtype=torch.float32, device="cuda")
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(7 + rank)
-    rows = max(1, (1 << 27) // n)
-    for r0 in range(0, n, rows):   # chunked: bounded temporaries next to the 6.4 GB raster
-        block = raster[0, r0:r0 + rows]
-        block.uniform_(0, 100, generator=gen)
-        block[torch.rand(block.shape, device="cuda", generator=gen) < 0.02] = workloads.F32_MAX
-    rd = _native.DeviceArray((1, n, n), "f4", ptr=raster.data_ptr(), owner=raster)
-    soup = utils.PolygonSoup(workloads.cfg4_polygons(n, g, seed=7 + rank)).to_device()
-    bbox = (0, 0, n, n)
-    out = {"workload": "cfg4 AggregateRaster {0}x{0} float32, {1} polygons per GPU".format(n, soup.n_polygons),
-           "unit": "Gpixel/s", "bytes_per_pixel": 4, "steps": args.zonal_steps,
-           "timed": "aggregate_polygons call on the HBM-resident raster incl. result download"}
-    with _native.use_stream(stream.cuda_stream), fusion.device_resident():
-        for label, stat, q in (("mean", "mean", None), ("max", "max", None), ("p90", "percentile", 90.0)):
-            def call():
-                return aggregate.aggregate_polygons(soup, rd, workloads.F32_MAX, bbox,
-                                                    workloads.PROJECTION, None, stat, q)
-            for _ in range(3):
-                res, _ = call()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/{}/numa_node".format(bus)).read())
+        allowed = sorted(os.sched_getaffinity(0))
+        info["allowed_cpus"] = len(allowed)
+        if node < 0:
+            return info
+        cpus = []
+        for part in open("/sys/devices/system/node/node{}/cpulist".format(node)).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = [c for c in cpus if c in set(allowed)]
+        info["numa_node"] = node
+        if not cpus:
+            return info
+        # ranks on the same node (GPU order = rank order on one box) share its cores evenly
+        same = [r for r in range(ranks_on_box) if _gpu_node(pynvml, r) == node]
+        if local_rank in same and len(cpus) >= len(same):
+            k = same.index(local_rank)
+            per = len(cpus) // len(same)
+            cpus = cpus[k * per:(k + 1) * per]
+        os.sched_setaffinity(0, cpus)
+        info["cpus"] = "{}-{} ({})".format(cpus[0], cpus[-1], len(cpus))
+    except Exception as e:  # no NVML / sysfs: leave the affinity alone
+        info["error"] = str(e)[:80]
+    return info
+
+
+def _gpu_node(pynvml, index):
+    try:
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        return int(open("/sys/bus/pci/devices/{}/numa_node".format(bus)).read())
+    except Exception:
+        return -1
+
+
+class Context(object):
+    """What every leg needs: torch, the process group, the stream all kernels, collectives and
+    CUDA events share, the roofline denominators."""
+
+    def __init__(self, args, torch, dist, rank, local_rank, world):
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            self.peak, self.peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
+        else:
+            self.peak, self.peak_kind = 6650.0, "fallback"
+        self.traffic = {}
+        path = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+        if os.path.exists(path):
+            self.traffic = json.load(open(path))
+        # a group of rank 0 alone: the single-GPU reference runs of the striped legs
+        self.solo = dist.new_group([0]) if world > 1 else None
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def time_calls(self, fn, iters, warm=3, everyone=True):
+        """ms per call of fn(): CUDA events on the launching stream, max over ranks."""
+        from dask_geomodeling_b200 import _native
+
+        torch = self.torch
+        with _native.use_stream(self.stream.cuda_stream):
+            for _ in range(warm):
+                out = fn()
+            if everyone:
+                self.barrier()
+            else:
+                torch.cuda.synchronize()
             before = _native.launch_count()
             start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            start.record(stream)
-            for _ in range(args.zonal_steps):
-                res, _ = call()
-            stop.record(stream)
+            start.record(self.stream)
+            for _ in range(iters):
+                out = fn()
+            stop.record(self.stream)
             torch.cuda.synchronize()
-            t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0]) / args.zonal_steps
-            gpx = world * n * n / ms / 1e6
-            out[label] = {"value": gpx, "ms_per_call": ms, "gpu_launches_per_call":
-                          (_native.launch_count() - before) / args.zonal_steps,
-                          "frac_of_hbm_peak": 4 * n * n / ms / 1e6 / peak,
-                          "checksum": float(np.nansum(res[0].astype(np.float64)))}
-    del raster, rd
+            launches = (_native.launch_count() - before) / float(iters)
+        t = torch.tensor([start.elapsed_time(stop) / iters], dtype=torch.float64, device="cuda")
+        if everyone and self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), launches, out
+
+    def roofline(self, nbytes, ms, kernel, n_gpus=None, traffic_key=None):
+        n_gpus = n_gpus or self.world
+        achieved = nbytes / ms / 1e6
+        entry = self.traffic.get(traffic_key or kernel, {})
+        return {"bound": "hbm", "achieved": achieved, "peak": self.peak * n_gpus, "unit": "GB/s",
+                "frac": achieved / (self.peak * n_gpus), "traffic": entry.get("dram_bytes_per_launch"),
+                "traffic_source": entry.get("source"), "peak_kind": self.peak_kind, "kernel": kernel,
+                "algorithmic_bytes": nbytes}
+
+
+def wrap(t):
+    """torch CUDA tensor -> DeviceArray sharing its memory."""
+    from dask_geomodeling_b200 import _native
+
+    return _native.DeviceArray(tuple(t.shape), str(t.dtype).replace("torch.", ""), ptr=t.data_ptr(), owner=t)
+
+
+def striped_entry(ctx, name, fn_striped, fn_single, pixels, nbytes, kernel, iters, traffic_key=None):
+    """Time one operation on the sharded workload (all ranks) and, at N > 1, on the whole
+    workload on rank 0 alone; returns the JSON object of the entry."""
+    ms, launches, _ = ctx.time_calls(fn_striped, iters)
+    entry = {"ms": ms, "gpx_s": pixels / ms / 1e6, "gpu_launches_per_call": launches,
+             "roofline": ctx.roofline(nbytes, ms, kernel, traffic_key=traffic_key)}
+    if ctx.world > 1 and not ctx.args.no_single:      # (every rank takes this branch: broadcast below)
+        single = ctx.torch.zeros(1, dtype=ctx.torch.float64, device="cuda")
+        if ctx.rank == 0 and fn_single is not None:
+            single[0], _, _ = ctx.time_calls(fn_single, max(3, iters // 2), everyone=False)
+        ctx.dist.broadcast(single, 0)
+        entry["single_gpu_ms"] = float(single[0])
+        entry["speedup_vs_1gpu"] = float(single[0]) / ms
+    return entry
+
+
+# ----------------------------------------------------------------------------
+# configs[2]: stencils on ONE DEM in row stripes
+# ----------------------------------------------------------------------------
+
+
+def make_dem(torch, r0, r1, n, seed, nodata):
+    """Rows [r0, r1) of the synthetic DEM: smooth terrain + noise, 1 % no data."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    out = torch.empty((1, r1 - r0, n), dtype=torch.float32, device="cuda")
+    x = torch.arange(n, device="cuda", dtype=torch.float32)[None, :]
+    rows = max(1, (1 << 26) // n)
+    for a in range(r0, r1, rows):     # chunked: bounded temporaries next to a 4 GB raster
+        b = min(a + rows, r1)
+        y = torch.arange(a, b, device="cuda", dtype=torch.float32)[:, None]
+        z = 50 * torch.sin(x / 17.0) + 30 * torch.cos(y / 11.0) + 0.05 * x + 100
+        z += torch.randn(b - a, n, device="cuda", generator=gen)
+        z[torch.rand(b - a, n, device="cuda", generator=gen) < 0.01] = nodata
+        out[0, a - r0:b - r0] = z
+    return out
+
+
+def run_stencils(ctx):
+    from dask_geomodeling_b200 import parallel, raster, workloads
+
+    torch, args = ctx.torch, ctx.args
+    n = args.dem_size
+    nodata = workloads.F32_MAX
+    lw = parallel.smooth_halo(5.0)
+    ops = [
+        ("smooth", "Smooth(size=5.0), exact mode", lw, 5, raster.Smooth.process,
+         (dict(smooth_mode="exact", fill=0, size=[5.0, 5.0], margin=(lw, 5)),), 8, "smooth_fast_kernel"),
+        ("movingmax", "MovingMax(size=11)", 5, 5, raster.MovingMax.process, (11,), 8, "moving_max_quad_kernel"),
+        ("hillshade", "HillShade(altitude=45, azimuth=315)", 1, 1, raster.HillShade.process,
+         (dict(resolution=(1.0, 1.0), altitude=45.0, azimuth=315.0, fill=0),), 5, "hillshade_quad_kernel"),
+    ]
+    out = {"workload": "cfg3 ONE {0}x{0} float32 DEM in {1} row stripe(s), halo exchange + kernel per step".format(
+        n, ctx.world), "unit": UNIT, "steps": args.leg_steps}
+    r0, r1 = parallel.stripe_rows(n, ctx.world)[ctx.rank]
+    dem = make_dem(torch, r0, r1, n, 100 + ctx.rank, nodata)
+    whole = None
+    if ctx.world > 1 and ctx.rank == 0 and not args.no_single:
+        whole = make_dem(torch, 0, n, n, 99, nodata)
+    px = n * n
+    for name, label, halo_rows, halo_cols, process, extra, bpp, kernel in ops:
+        stored = parallel.pad_columns(parallel.exchange_halo(dem, halo_rows, nodata), halo_cols, nodata)
+        stored_whole = None
+        if whole is not None:
+            stored_whole = parallel.pad_columns(
+                parallel.exchange_halo(whole, halo_rows, nodata, group=ctx.solo), halo_cols, nodata)
+        entry = striped_entry(
+            ctx, name,
+            lambda: parallel.stencil_haloed(process, stored, nodata, halo_rows, halo_cols, *extra),
+            None if stored_whole is None else (lambda: parallel.stencil_haloed(
+                process, stored_whole, nodata, halo_rows, halo_cols, *extra, group=ctx.solo)),
+            px, px * bpp, kernel, args.leg_steps)
+        entry["op"] = label
+        entry["halo_rows"] = halo_rows
+        entry["bytes_per_pixel"] = bpp
+        out[name] = entry
+        del stored, stored_whole
+    del dem, whole
+    torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------
+# configs[3]: zonal statistics of ONE raster in row stripes
+# ----------------------------------------------------------------------------
+
+
+def make_uniform(torch, shape, seed, nodata, fraction):
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    out = torch.empty(shape, dtype=torch.float32, device="cuda")
+    flat = out.view(-1, shape[-1])
+    rows = max(1, (1 << 27) // shape[-1])
+    for a in range(0, flat.shape[0], rows):
+        block = flat[a:a + rows]
+        block.uniform_(0, 100, generator=gen)
+        block[torch.rand(block.shape, device="cuda", generator=gen) < fraction] = nodata
+    return out
+
+
+def run_zonal(ctx, host_raster):
+    from dask_geomodeling_b200 import _native, parallel, utils, workloads
+    from dask_geomodeling_b200.core import fusion
+
+    torch, args = ctx.torch, ctx.args
+    n, g = args.zonal_size, args.zonal_grid
+    nodata = workloads.F32_MAX
+    rings = workloads.cfg4_rings(n, g, seed=7)          # the same polygons on every rank
+    areas = workloads.ring_areas(rings)
+    soup = utils.PolygonSoup([utils.Polygon(r) for r in rings]).to_device()
+    bbox = (0, 0, n, n)
+    r0, r1 = parallel.stripe_rows(n, ctx.world)[ctx.rank]
+    stripe = make_uniform(torch, (1, r1 - r0, n), 200 + ctx.rank, nodata, 0.02)
+    whole = None
+    if ctx.world > 1 and ctx.rank == 0 and not args.no_single:
+        whole = make_uniform(torch, (1, n, n), 199, nodata, 0.02)
+    out = {"workload": "cfg4 AggregateRaster over ONE {0}x{0} float32 raster in {1} row stripe(s), {2} polygons".format(
+        n, ctx.world, soup.n_polygons), "unit": UNIT, "bytes_per_pixel": 4, "steps": args.leg_steps,
+        "polygons": {"count": soup.n_polygons, "mean_area_px": float(areas.mean()),
+                     "area_fraction_of_raster": float(areas.sum() / (float(n) * n)),
+                     "vertices": "6-12 per polygon, jittered cell boundaries, 5 % overlapping their neighbours",
+                     "definition": "SURVEY.md section 8(d); dask_geomodeling_b200/workloads.py cfg4_rings"},
+        "timed": "zonal_striped call: stripe kernels + collectives + download of the per-polygon results"}
+    px = n * n
+    kernels = {"mean": "zonal_reduce_warp_kernel<float, SUM>", "max": "zonal_reduce_warp_kernel<float, MAX>",
+               "p90": "zonal_select_bracket/main/final_kernel<float>"}
+    checks = {}
+    with fusion.device_resident():
+        for label, stat, q in (("mean", "mean", None), ("max", "max", None), ("p90", "percentile", 90.0)):
+            def striped(stat=stat, q=q):
+                return parallel.zonal_striped(soup, stripe, nodata, bbox, n, (r0, r1), stat, q)
+
+            single = None
+            if whole is not None:
+                def single(stat=stat, q=q):
+                    return parallel.zonal_striped(soup, whole, nodata, bbox, n, (0, n), stat, q, group=ctx.solo)
+            entry = striped_entry(ctx, label, striped, single, px, px * 4, kernels[label], args.leg_steps,
+                                  traffic_key="zonal_" + label)
+            with _native.use_stream(ctx.stream.cuda_stream):
+                res, no_cells = striped()
+            entry["checksum"] = float(np.nansum(np.asarray(res, dtype=np.float64)))
+            entry["polygons_without_cells"] = len(no_cells)
+            out[label] = entry
+            checks[label] = res
+    # size-independent property on the full result: min <= p90 <= max is implied by mean <= max etc.
+    ok = np.asarray(checks["mean"]) <= np.asarray(checks["max"])
+    out["property_mean_le_max"] = bool(np.all(ok | np.isnan(checks["mean"])))
+    del stripe, whole
     torch.cuda.empty_cache()
 
-    # end to end through the Block API: host raster (the cfg2 float32 raster, 1 GiB) in a
-    # MemorySource, polygons in a MemoryGeometrySource, AggregateRaster.get_data per request --
-    # raster upload over PCIe, zonal kernels and the result frame inside the timed region
-    from dask_geomodeling_b200 import geometry, raster as raster_blocks
+    if ctx.world == 1 and host_raster is not None:
+        out["e2e"] = zonal_e2e(ctx, host_raster)
+        from oracle import reference_chain
+
+        gpx, seconds, threads, kind = reference_chain.time_zonal()
+        out["cpu_baseline"] = {"value": gpx, "unit": UNIT, "cores": threads, "kind": kind,
+                               "sample": "mean of 1024 polygons over 4096 x 4096 float32 (cfg4 scaled): "
+                                         "bucketize + GDAL-rule labels + scipy labelled mean, {:.1f} s".format(seconds)}
+    return out
+
+
+def zonal_e2e(ctx, host_raster):
+    """AggregateRaster.get_data on a host MemorySource (the cfg2 float32 raster) and a
+    MemoryGeometrySource: raster upload over PCIe, zonal kernels and the result frame inside the
+    timed region."""
+    from dask_geomodeling_b200 import _native, geometry, raster as raster_blocks, utils, workloads
     from dask_geomodeling_b200._compat import config as gm_config
 
     size = host_raster.shape[-1]
     grid = max(1, size // 128)
     src = raster_blocks.MemorySource(host_raster, workloads.F32_MAX, workloads.PROJECTION, pixel_size=1.0,
                                      pixel_origin=(0, size))
-    source = geometry.MemoryGeometrySource(workloads.cfg4_polygons(size, grid, seed=7 + rank), None,
-                                           workloads.PROJECTION)
+    source = geometry.MemoryGeometrySource(workloads.cfg4_polygons(size, grid, seed=7), None, workloads.PROJECTION)
     request = dict(mode="intersects", projection=workloads.PROJECTION, geometry=utils.box(0, 0, size, size))
-    e2e = {"workload": "AggregateRaster.get_data, host raster {0}x{0} float32 + {1} polygons per GPU".format(
-        size, grid * grid), "unit": "Gpixel/s", "h2d_bytes_per_step": int(host_raster.nbytes), "steps": 3}
+    e2e = {"workload": "AggregateRaster.get_data, host raster {0}x{0} float32 + {1} polygons".format(size, grid * grid),
+           "unit": UNIT, "h2d_bytes_per_step": int(host_raster.nbytes), "steps": 3}
     with gm_config.set({"geomodeling.raster-limit": 4 * size * size}):
         for label in ("mean", "p90"):
             view = geometry.AggregateRaster(source=source, raster=src, statistic=label)
             for _ in range(2):
                 frame = view.get_data(**request)["features"]
             _native.synchronize()
-            if world > 1:
-                dist.barrier()
             t0 = time.perf_counter()
             for _ in range(3):
                 frame = view.get_data(**request)["features"]
             _native.synchronize()
-            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            seconds = float(t[0]) / 3
-            e2e[label] = {"value": world * size * size / seconds / 1e9, "ms_per_request": seconds * 1e3,
-                          "d2h_bytes_per_step": 4 * len(frame), "checksum": float(np.nansum(frame["agg"].values.astype(np.float64)))}
-    out["e2e"] = e2e
-    if world == 1:
-        gpx, seconds = cpu_zonal_throughput()
-        out["cpu_baseline"] = {"value": gpx, "unit": "Gpixel/s", "cores": 1, "kind": "port",
-                               "sample": "mean of 1024 polygons over 4096 x 4096 float32 (cfg4 scaled), "
-                                         "bucketize + GDAL-rule labels + scipy labelled mean, {:.1f} s".format(seconds)}
+            seconds = (time.perf_counter() - t0) / 3
+            e2e[label] = {"value": size * size / seconds / 1e9, "ms_per_request": seconds * 1e3,
+                          "d2h_bytes_per_step": 4 * len(frame),
+                          "checksum": float(np.nansum(frame["agg"].values.astype(np.float64)))}
+    return e2e
+
+
+# ----------------------------------------------------------------------------
+# configs[4]: temporal aggregation of ONE stack sharded by rows
+# ----------------------------------------------------------------------------
+
+
+def run_temporal(ctx):
+    from datetime import datetime, timedelta
+
+    from dask_geomodeling_b200 import parallel, raster, workloads
+    from dask_geomodeling_b200.core import fusion
+
+    torch, args = ctx.torch, ctx.args
+    T, m = args.temporal_frames, args.temporal_size
+    nodata = workloads.F32_MAX
+    r0, r1 = parallel.stripe_rows(m, ctx.world)[ctx.rank]
+    times = [datetime(2000, 1, 1) + timedelta(days=i) for i in range(T)]
+
+    def kwargs_for(stat, dtype="f4"):
+        return dict(mode="vals", start=times[-1], stop=None, frequency=None, timezone=None, closed=None,
+                    label=None, dtype=dtype, statistic=stat)
+
+    out = {"workload": "cfg5 TemporalAggregate over ONE {0} x {1} x {1} float32 stack, rows sharded over {2} rank(s), "
+                       "no collective".format(T, m, ctx.world), "unit": "Gpixel-frames/s", "steps": max(3, args.leg_steps // 2)}
+    stack = make_uniform(torch, (T, r1 - r0, m), 300 + ctx.rank, nodata, 0.03)
+    sd = wrap(stack)
+    whole = None
+    if ctx.world > 1 and ctx.rank == 0 and not args.no_single:
+        whole = wrap(make_uniform(torch, (T, m, m), 299, nodata, 0.03))
+    px = T * m * m
+    nbytes = T * m * m * 4 + m * m * 4
+    iters = max(3, args.leg_steps // 2)
+    resident = fusion.device_resident()
+    resident.__enter__()           # results stay in HBM, as between the blocks of a view
+    for stat in ("sum", "max"):
+        kw = kwargs_for(stat)
+        entry = striped_entry(
+            ctx, stat,
+            lambda kw=kw: raster.TemporalAggregate.process(kw, {"time": times}, {"values": sd, "no_data_value": nodata}),
+            None if whole is None else (lambda kw=kw: raster.TemporalAggregate.process(
+                kw, {"time": times}, {"values": whole, "no_data_value": nodata})),
+            px, nbytes, "temporal_stream_kernel<float, {}>".format(stat), iters, traffic_key="temporal_" + stat)
+        entry["bytes"] = "T * itemsize in + itemsize out per pixel"
+        out[stat] = entry
+    if ctx.world == 1:
+        # the rest of the temporal rows on the first 64 frames (outputs of Cumulative are T frames)
+        t64 = min(64, T)
+        sub = wrap(stack[:t64])
+        sub_times = times[:t64]
+        px64 = t64 * (r1 - r0) * m
+        for stat, kernel in (("mean", "temporal_stream_kernel<float, mean>"), ("std", "temporal_moments_stream_kernel"),
+                             ("median", "temporal_sort_reg_kernel")):
+            kw = dict(kwargs_for(stat), start=sub_times[-1])
+            ms, launches, _ = ctx.time_calls(lambda kw=kw: raster.TemporalAggregate.process(
+                kw, {"time": sub_times}, {"values": sub, "no_data_value": nodata}), iters)
+            nb = (2 if stat == "std" else 1) * px64 * 4 + (r1 - r0) * m * 4     # std reads the frames twice
+            out["{}_{}frames".format(stat, t64)] = {
+                "ms": ms, "gpx_s": px64 / ms / 1e6, "gpu_launches_per_call": launches,
+                "roofline": ctx.roofline(nb, ms, kernel, traffic_key="temporal_" + stat)}
+        kw = dict(mode="vals", start=sub_times[0], stop=sub_times[-1], frequency=None, timezone=None,
+                  closed="right", label="right", dtype="<f4", statistic="sum")
+        ms, launches, _ = ctx.time_calls(lambda: raster.Cumulative.process(
+            kw, {"time": sub_times}, {"values": sub, "no_data_value": nodata}), iters)
+        out["cumulative_sum_{}frames".format(t64)] = {
+            "ms": ms, "gpx_s": px64 / ms / 1e6, "gpu_launches_per_call": launches,
+            "roofline": ctx.roofline(2 * px64 * 4, ms, "temporal_cumulative_stream_kernel", traffic_key="cumulative_sum"),
+            "bytes": "2 * T * itemsize per pixel (every frame read once, every running sum written once)"}
+        del sub
+    resident.__exit__(None, None, None)
+    del stack, sd, whole
+    torch.cuda.empty_cache()
     return out
 
 
@@ -385,15 +631,19 @@ def run_b200(args):
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     os.environ.setdefault("GM_DEVICE", str(local_rank))
+    binding = bind_to_gpu_numa_node(local_rank, world) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from dask_geomodeling_b200 import _native, workloads
+    from dask_geomodeling_b200._compat import config as gm_config
     from dask_geomodeling_b200.core import fusion
     from dask_geomodeling_b200.raster import _program
 
+    ctx = Context(args, torch, dist, rank, local_rank, world)
+    stream = ctx.stream
     size = args.size
     pixels = size * size
     ints, floats = workloads.cfg2_arrays(size, seed=43 + rank)
@@ -423,42 +673,31 @@ def run_b200(args):
         del result
 
     # ---- kernel-resident measurement: compile once, launch K times -------------
-    from dask_geomodeling_b200._compat import config as gm_config
-
     graph, name = view.get_compute_graph(**request)
     with gm_config.set({"geomodeling.stream": False}):  # resident launch, not the chunk pipeline
         fused = fusion.optimize(graph, name)
     task = fused[name]
     assert task[0] is fusion.fused_process, "the chain did not fuse into one task"
     plan, leaf_keys = task[1], task[2:]
-    # a dedicated (non-default) stream: the kernels, the CUDA events that time them
-    # and torch's allocator all use this one stream handle
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
+    warmup = max(args.warmup, 3)
     with _native.use_stream(stream.cuda_stream), fusion.device_resident():
         leaf_payloads = [fused[k][0](*fused[k][1:]) for k in leaf_keys]  # H2D, once
         inputs = [p["values"] for p in leaf_payloads]
         leaf_types = [(p["values"].dtype, p["no_data_value"]) for p in leaf_payloads]
         compiled = _program.CompiledProgram([fusion.build_expression(plan)], leaf_types)
         out = _native.DeviceArray((1, size, size), compiled.results[0].dtype)
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             compiled.launch(inputs, [out])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ctx.barrier()
         sampler = make_sampler(local_rank) if rank == 0 else None
+        time.sleep(0.005)          # the sampler thread is running before the first timed launch
         launches_before = _native.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
         for _ in range(args.steps):
             compiled.launch(inputs, [out])
         stop.record(stream)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ctx.barrier()
         launches = _native.launch_count() - launches_before
         elapsed_ms = start.elapsed_time(stop)
         clocks = sampler.stop() if sampler else None
@@ -466,61 +705,63 @@ def run_b200(args):
         del inputs, leaf_payloads, out
     assert e2e_checksum is None or e2e_checksum == checksum, "e2e result differs from the resident result"
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_kind = json.load(open(peaks_path))["hbm_gbs"], "measured"
-    else:
-        peak, peak_kind = 6650.0, "fallback"
-    zonal = None
-    if not args.profile and not args.no_zonal:
-        zonal = run_zonal(args, torch, dist, stream, rank, world, peak, floats)
-
     t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms, e2e_s = float(t[0]), float(t[1])
 
+    striped = {}
+    if "stencils" in args.legs:
+        striped["stencils"] = run_stencils(ctx)
+    if "zonal" in args.legs:
+        striped["zonal"] = run_zonal(ctx, floats)
+    if "temporal" in args.legs:
+        striped["temporal"] = run_temporal(ctx)
+
     if rank == 0:
         ms_per_step = elapsed_ms / args.steps
         value = world * pixels / (ms_per_step / 1e3) / 1e9
         e2e_value = world * pixels * args.e2e_steps / e2e_s / 1e9
-        achieved = BYTES_PER_PIXEL * pixels / (ms_per_step / 1e3) / 1e9
+        roof = ctx.roofline(BYTES_PER_PIXEL * pixels, ms_per_step, "gm_fused (NVRTC-specialised evaluator, "
+                            "V=4 px x U=4 groups per thread)", n_gpus=1, traffic_key="gm_fused_cfg2_{}".format(size))
+        roof["bytes_per_pixel"] = BYTES_PER_PIXEL
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16/float32->bool",
             "data": "synthetic",
             "config": {
                 "workload": "cfg2 Reclassify+Clip+Step+IsData {0}x{0} int16/float32 per GPU".format(size),
                 "l2": "inputs {:.2f} GiB per step >> 126 MB L2, no flush needed".format(h2d / 2 ** 30),
-                "parallelism": "row stripes, one raster pair per GPU, no collective",
+                "parallelism": "one raster pair per GPU, no collective (weak); the striped legs shard ONE workload (strong)",
                 "checksum_true_pixels": checksum,
             },
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size
-                         # (ncu --set full, profiles/r01b_eval_specialised_ncu_details.txt)
-                         "traffic": 1.86e9 if size == 16384 else None, "peak_kind": peak_kind,
-                         "bytes_per_pixel": BYTES_PER_PIXEL, "kernel": "gm_fused (NVRTC-specialised evaluator, V=4 px x U=4 groups per thread)"},
+            "roofline": roof,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                    "per_rank_link_gb_s": (h2d + d2h) * args.e2e_steps / e2e_s / 1e9,
+                    "rank0_host_binding": binding},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if zonal is not None:
-            line["zonal"] = zonal
+        if striped:
+            line["striped"] = striped
         if world == 1 and not args.profile:
-            threads = os.cpu_count() or 1
-            rows = min(args.cpu_sample_rows, size)
-            gpx, cpu_pixels, best = cpu_chain_throughput(ints, floats, rows, 3, threads)
+            from oracle import reference_chain
+
+            times, kind, threads, cpu_checksum = reference_chain.time_chain(
+                ints, floats, workloads.CFG2_PAIRS, steps=3, warmup=1)
+            best = min(times)
+            assert cpu_checksum == checksum, "CPU arm and GPU arm disagree on the result"
             line["cpu_baseline"] = {
-                "value": gpx, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": "first {} rows x {} cols of the same inputs, best of 3 ({:.2f} s)".format(
-                    rows, size, best),
+                "value": pixels / best / 1e9, "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": "the whole {0}x{0} request, 2048 x 2048 tiles on a thread pool, best of 3 "
+                          "({1:.2f} s); result equal to the GPU arm's".format(size, best),
             }
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

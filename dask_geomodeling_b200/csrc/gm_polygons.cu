@@ -2652,7 +2652,8 @@ __global__ void zonal_unpack_kernel(const double* __restrict__ sums, const doubl
 
 template <typename T>
 static int run_zonal_partials_device(PolyUpload& u, const Staged& raster, const void* nodata, int has_nodata,
-                                     const float* thresholds, double* sums, double* extremes, cudaStream_t s) {
+                                     const float* thresholds, double* sums, double* extremes, int stat,
+                                     cudaStream_t s) {
   const int64_t np_ = u.dev.n_polygons;
   if (np_ == 0) return 0;
   T nd = T(0);
@@ -2677,12 +2678,21 @@ static int run_zonal_partials_device(PolyUpload& u, const Staged& raster, const 
                           (((int64_t)u.dev.height * u.dev.width + mis) % vec) != 0;
   int64_t wblocks = (np_ + ZW_WARPS - 1) / ZW_WARPS;
   if (wblocks > (int64_t)sm_count() * ZW_MIN_BLOCKS) wblocks = (int64_t)sm_count() * ZW_MIN_BLOCKS;
-  zonal_reduce_warp_kernel<T, ZW_ALL><<<(unsigned)wblocks, 32 * ZW_WARPS, 0, s>>>(
-      u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, mis, edge_scalar,
-      (GmZonalPartial*)dpartial, (long long*)darea, (int*)dwork);
+  // only what the statistic needs (a stripe call for the mean runs the sum-only kernel)
+  const int need = stat == GM_STAT_MIN ? ZW_MIN : stat == GM_STAT_MAX ? ZW_MAX
+                 : (stat == GM_STAT_SUM || stat == GM_STAT_MEAN || stat == GM_STAT_COUNT) ? ZW_SUM : ZW_ALL;
+#define GM_ZW(NEED)                                                                              \
+  zonal_reduce_warp_kernel<T, NEED><<<(unsigned)wblocks, 32 * ZW_WARPS, 0, s>>>(                  \
+      u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, mis, edge_scalar,          \
+      (GmZonalPartial*)dpartial, (long long*)darea, (int*)dwork)
+  if (need == ZW_SUM) GM_ZW(ZW_SUM);
+  else if (need == ZW_MIN) GM_ZW(ZW_MIN);
+  else if (need == ZW_MAX) GM_ZW(ZW_MAX);
+  else GM_ZW(ZW_ALL);
+#undef GM_ZW
   GM_TRY(cudaGetLastError());
   count_launch();
-  zonal_reduce_kernel<T><<<poly_grid(np_), PG_THREADS, smem_scan, s>>>(
+  zonal_reduce_kernel<T><<<poly_grid(np_ < 1024 ? np_ : 1024), PG_THREADS, smem_scan, s>>>(
       u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, (GmZonalPartial*)dpartial,
       (long long*)darea, (const int*)dwork);
   GM_TRY(cudaGetLastError());
@@ -2856,7 +2866,7 @@ extern "C" int gm_zonal_stats(const GmArray* raster, const void* nodata, int has
 extern "C" int gm_zonal_partials_device(const GmArray* raster, const void* nodata, int has_nodata,
                                         const GmPolygons* polys, const double geo[6],
                                         const float* thresholds, int64_t row_begin, int64_t row_end,
-                                        double* sums, double* extremes, void* stream) {
+                                        double* sums, double* extremes, int stat, void* stream) {
   if (ensure_init()) return 1;
   if (!raster || !polys || !sums || !extremes) return fail("gm_zonal_partials_device: null argument");
   if (raster->shape[0] != 1) return fail("gm_zonal_partials_device: one frame per call");
@@ -2870,7 +2880,7 @@ extern "C" int gm_zonal_partials_device(const GmArray* raster, const void* nodat
   if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s);
   if (!rc) {
     GM_RASTER_DISPATCH(raster->dtype,
-                       run_zonal_partials_device<T>(u, in, nodata, has_nodata, thresholds, sums, extremes, s),
+                       run_zonal_partials_device<T>(u, in, nodata, has_nodata, thresholds, sums, extremes, stat, s),
                        "gm_zonal_partials_device")
   }
   if (!rc) rc = check_overflow(u, s);

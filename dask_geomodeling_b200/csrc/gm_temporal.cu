@@ -411,6 +411,137 @@ temporal_cumulative_kernel(const S* __restrict__ src, D* __restrict__ dst, S nod
   }
 }
 
+// Cumulative sum / count, streaming: a thread owns 16 / sizeof(S) consecutive pixels, every frame
+// is read once with 16-byte loads (eight frames in flight) and every running total is written once
+// with 16-byte streaming stores.  Same arithmetic as temporal_cumulative_kernel (sequential in t in
+// the working dtype).  Algorithmic bytes: T * (itemsize in + itemsize out) per pixel.
+template <typename S, typename W, typename D>
+__global__ void __launch_bounds__(256)
+temporal_cumulative_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                                  int stat, const int* __restrict__ bin_offsets,
+                                  const int* __restrict__ frame_index, const int* __restrict__ out_frame,
+                                  int n_bins, int64_t plane) {
+  constexpr int VEC = 16 / (int)sizeof(S);
+  constexpr int UNROLL = 8;
+  typedef PixelVec<S, VEC> V;
+  const int64_t grp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (grp >= plane / VEC) return;
+  const int64_t pix = grp * VEC;
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
+    W acc[VEC];
+    int cnt[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i] = (W)0; cnt[i] = 0; }
+    auto step = [&](const V& x, int f) {
+      D outv[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const S v = x.v[i];
+        const W w = (W)v;
+        const bool valid = !(has_nodata && v == nodata) && (w == w);
+        acc[i] = valid ? acc[i] + w : acc[i];
+        cnt[i] += valid ? 1 : 0;
+        if (stat == GM_STAT_COUNT) {
+          outv[i] = (D)cnt[i];
+        } else {
+          const bool finite = (acc[i] == acc[i]) && (fabs((double)acc[i]) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+          outv[i] = finite ? cast_out<W, D>(acc[i]) : (D)0;
+        }
+      }
+      const int o = out_frame[f];
+      if (o >= 0) {
+        D* at = dst + (int64_t)o * plane + pix;
+        if constexpr ((VEC * sizeof(D)) % 16 == 0) {
+          uint4 raw[VEC * sizeof(D) / 16];
+          memcpy(raw, outv, sizeof(raw));
+#pragma unroll
+          for (int k = 0; k < (int)(VEC * sizeof(D) / 16); ++k) __stcs(reinterpret_cast<uint4*>(at) + k, raw[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) at[i] = outv[i];
+        }
+      }
+    };
+    int f = f0;
+    for (; f + UNROLL <= f1; f += UNROLL) {
+      V x[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        x[u] = load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f + u] * plane + pix));
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) step(x[u], f + u);
+    }
+    for (; f < f1; ++f)
+      step(load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f] * plane + pix)), f);
+  }
+}
+
+// std / var, streaming: np.nanvar's two passes over t (mean, then the squared deviations from it),
+// each with 16-byte loads and four frames in flight; same arithmetic, in the same order, as the
+// generic kernel.  Algorithmic bytes: 2 * T * itemsize in + itemsize out per pixel.
+template <typename S, typename W, typename D>
+__global__ void __launch_bounds__(256)
+temporal_moments_stream_kernel(const S* __restrict__ src, D* __restrict__ dst, S nodata, int has_nodata,
+                               int stat, const int* __restrict__ bin_offsets,
+                               const int* __restrict__ frame_index, int n_bins, int64_t plane) {
+  constexpr int VEC = 16 / (int)sizeof(S);
+  constexpr int UNROLL = 4;
+  typedef PixelVec<S, VEC> V;
+  const int64_t grp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (grp >= plane / VEC) return;
+  const int64_t pix = grp * VEC;
+  const D fill = DMax<D>::value();
+  for (int g = 0; g < n_bins; ++g) {
+    const int f0 = bin_offsets[g], f1 = bin_offsets[g + 1];
+    W acc[VEC], avg[VEC], ss[VEC];
+    int cnt[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { acc[i] = (W)0; ss[i] = (W)0; cnt[i] = 0; }
+    for (int pass = 0; pass < 2; ++pass) {
+      auto take = [&](const V& x) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const S v = x.v[i];
+          const W w = (W)v;
+          const bool valid = !(has_nodata && v == nodata) && (w == w);
+          if (pass == 0) {
+            acc[i] = valid ? acc[i] + w : acc[i];
+            cnt[i] += valid ? 1 : 0;
+          } else {
+            const W d = w - avg[i];
+            ss[i] = valid ? ss[i] + d * d : ss[i];
+          }
+        }
+      };
+      int f = f0;
+      for (; f + UNROLL <= f1; f += UNROLL) {
+        V x[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          x[u] = load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f + u] * plane + pix));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) take(x[u]);
+      }
+      for (; f < f1; ++f)
+        take(load_pixels(reinterpret_cast<const V*>(src + (int64_t)frame_index[f] * plane + pix)));
+      if (pass == 0) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) avg[i] = (W)((double)acc[i] / (double)(int64_t)cnt[i]);
+      }
+    }
+    D* o = dst + (int64_t)g * plane + pix;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const W var = cnt[i] > 0 ? (W)((double)ss[i] / (double)(int64_t)cnt[i]) : nan_<W>();
+      W result = var;
+      if (stat == GM_STAT_STD) result = sizeof(W) == 4 ? (W)sqrtf((float)var) : (W)sqrt((double)var);
+      const bool finite = (result == result) && (fabs((double)result) <= (sizeof(W) == 4 ? (double)FLT_MAX : DBL_MAX));
+      o[i] = (f1 > f0 && finite) ? cast_out<W, D>(result) : fill;
+    }
+  }
+}
+
 struct TemporalArgs {
   const void* nodata; int has_nodata; int stat; double q;
   const int* bins; const int* frames; const int* out_frame; int n_bins; int64_t plane;
@@ -442,6 +573,13 @@ static int launch_aggregate(const Staged& in, Staged& out, const TemporalArgs& a
       default: GM_STREAM(GM_STAT_MEAN); break;
     }
 #undef GM_STREAM
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
+  if ((a.stat == GM_STAT_STD || a.stat == GM_STAT_VAR) && a.plane % VEC == 0 && ((uintptr_t)in.dev % 16) == 0) {
+    const unsigned nb = (unsigned)((a.plane / VEC + 255) / 256);
+    temporal_moments_stream_kernel<S, W, D><<<nb, 256, 0, s>>>(
+        (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.bins, a.frames, a.n_bins, a.plane);
     GM_LAUNCH_CHECK();
     return 0;
   }
@@ -485,6 +623,15 @@ template <typename S, typename W, typename D>
 static int launch_cumulative(const Staged& in, Staged& out, const TemporalArgs& a, cudaStream_t s) {
   S nd = S(0);
   if (a.has_nodata) memcpy(&nd, a.nodata, sizeof(S));
+  constexpr int VEC = 16 / (int)sizeof(S);
+  if (a.plane % VEC == 0 && ((uintptr_t)in.dev % 16) == 0 && ((uintptr_t)out.dev % 16) == 0) {
+    const unsigned nb = (unsigned)((a.plane / VEC + 255) / 256);
+    temporal_cumulative_stream_kernel<S, W, D><<<nb, 256, 0, s>>>(
+        (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.bins, a.frames, a.out_frame,
+        a.n_bins, a.plane);
+    GM_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t blocks = (a.plane + 255) / 256;
   temporal_cumulative_kernel<S, W, D><<<(unsigned)blocks, 256, 0, s>>>(
       (const S*)in.dev, (D*)out.dev, nd, a.has_nodata, a.stat, a.bins, a.frames, a.out_frame,

@@ -31,6 +31,14 @@ __all__ = [
 ]
 
 
+TRACE = None     # tools/zonal_striped_breakdown.py sets a callable(name) to time the phases
+
+
+def _trace(name):
+    if TRACE is not None:
+        TRACE(name)
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -572,11 +580,13 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
         recv = torch.empty((1, int(halo[rank]), tensor.shape[2]), dtype=tensor.dtype, device=link)
         ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
     pending = dist.batch_isend_irecv(ops) if ops else []
+    _trace("boundary rows posted")
     if r1 > r0 and len(inside_ids):
         got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
                                     statistic, percentile)
         mine[0, inside_ids], mine[1, inside_ids] = got, cov
         owned[inside_ids] = True
+    _trace("select inside the stripe")
     for work in pending:
         work.wait()
     if recv is not None and len(near_ids):
@@ -589,19 +599,36 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
                                     thresholds_of(near_ids), statistic, percentile)
         mine[0, near_ids], mine[1, near_ids] = got, cov
         owned[near_ids] = True
+    _trace("select on the boundary strip")
     # owners publish their results and covered-cell counts: one all-gather of a (2, N) block
+    # (page-locked staging buffers and the owner -> slot index are kept with the soup)
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    block = torch.from_numpy(mine).to(dev)
+    key = (tuple(bbox), int(height), int(world), dev)
+    buffers = getattr(soup, "_gather_buffers", None)
+    if buffers is None or buffers[0] != key:
+        top, bottom = _polygon_rows(soup, bbox, height)
+        pick = owner.astype(np.int64) * (2 * n) + np.arange(n)
+        stage_in = torch.empty((2, n), dtype=torch.float64)
+        stage_out = torch.empty((world, 2, n), dtype=torch.float64)
+        if dev == "cuda":
+            stage_in, stage_out = stage_in.pin_memory(), stage_out.pin_memory()
+        buffers = soup._gather_buffers = (key, stage_in, stage_out, pick, (bottom < 0) | (top > height - 1))
+    _, stage_in, stage_out, pick, nowhere = buffers
+    stage_in.numpy()[...] = mine
+    block = stage_in.to(dev, non_blocking=True)
     gathered = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered, block, group=group) if dev == "cuda" else \
+    if dev == "cuda":
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        stage_out.copy_(gathered, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        flat = stage_out.numpy().reshape(-1)
+    else:
         dist.all_gather(list(gathered.unbind(0)), block, group=group)
-    gathered = gathered.cpu().numpy()
-    at = np.arange(n)
-    result = gathered[owner, 0, at].astype(np.float32)
-    covered = gathered[owner, 1, at].astype(np.int64)
-    top, bottom = _polygon_rows(soup, bbox, height)
-    nowhere = (bottom < 0) | (top > height - 1)          # outside the raster: nobody selected them
-    result[nowhere] = np.nan
+        flat = gathered.numpy().reshape(-1)
+    _trace("all-gather + download")
+    result = flat[pick].astype(np.float32)
+    covered = flat[pick + n].astype(np.int64)
+    result[nowhere] = np.nan          # outside the raster: nobody selected them
     covered[nowhere] = 0
     if far.any():   # same on every rank: the collectives inside line up
         ids = np.nonzero(far)[0]
@@ -614,8 +641,11 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
 
 def _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, threshold_values, group, has_rows):
     """count / sum / mean / min / max of a striped raster with everything but the final N
-    results in HBM: stripe partials (gm_zonal_partials_device), one SUM and one MIN
-    all-reduce over NVLink, statistic + download (gm_zonal_finalize_device)."""
+    results in HBM: stripe partials (gm_zonal_partials_device; only what the statistic needs),
+    one SUM all-reduce (plus one MIN all-reduce for min / max) over NVLink, statistic + download
+    (gm_zonal_finalize_device).  A 40000 x 40000 stripe pass takes a fraction of a millisecond, so
+    everything that does not change between calls -- descriptors, partial vectors, page-locked
+    result buffers -- is kept with the soup."""
     import ctypes
 
     import torch
@@ -630,36 +660,52 @@ def _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, th
     stream = _native.current_stream()
     torch_stream = torch.cuda.current_stream().cuda_stream
     same_stream = stream is not None and int(stream) == int(torch_stream)
-    big = float(np.finfo(np.float64).max)
-    sums = torch.zeros(3 * n, dtype=torch.float64, device="cuda")
-    extremes = torch.full((2 * n,), big, dtype=torch.float64, device="cuda")
+    shape = tuple(local.shape) if has_rows else None
+    key = (tuple(stripe_bbox), shape, str(local.dtype) if has_rows else None, repr(no_data_value), n)
+    kept = getattr(soup, "_stripe_call", None)
+    if kept is None or kept["key"] != key:
+        kept = {"key": key,
+                "sums": torch.empty(3 * n, dtype=torch.float64, device="cuda"),
+                "extremes": torch.empty(2 * n, dtype=torch.float64, device="cuda"),
+                "out": _native.pinned_empty((n,), np.float32),
+                "covered": _native.pinned_empty((n,), np.int64)}
+        if has_rows:
+            s = sentinel(local.dtype, no_data_value)
+            kept["geo"] = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, shape[1], shape[2]))
+            kept["nodata"] = _native.scalar_ptr(0 if s is None else s, local.dtype)
+            kept["has_nodata"] = int(s is not None)
+            kept["polys"] = soup.as_struct()
+        soup._stripe_call = kept
+    sums, extremes = kept["sums"], kept["extremes"]
+    sums.zero_()
+    if statistic in ("min", "max"):
+        extremes.fill_(float(np.finfo(np.float64).max))
     if has_rows:
-        _, h, w = local.shape
-        geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, h, w))
-        s = sentinel(local.dtype, no_data_value)
-        holder, nodata_ptr = _native.scalar_ptr(0 if s is None else s, local.dtype)
         thresholds = None
         if threshold_values is not None:
             thresholds = np.ascontiguousarray(threshold_values, dtype=np.float32)
-        polys = soup.as_struct()
         desc = _frame_descriptor(local, 0)
         if not same_stream:
             torch.cuda.current_stream().synchronize()   # the tensors above are ready
         _native.check(lib.gm_zonal_partials_device(
-            ctypes.byref(desc), nodata_ptr, int(s is not None), ctypes.byref(polys), geo,
-            None if thresholds is None else thresholds.ctypes.data, 0, h,
-            sums.data_ptr(), extremes.data_ptr(), stream))
+            ctypes.byref(desc), kept["nodata"][1], kept["has_nodata"], ctypes.byref(kept["polys"]), kept["geo"],
+            None if thresholds is None else thresholds.ctypes.data, 0, shape[1],
+            sums.data_ptr(), extremes.data_ptr(), _STAT_CODES[statistic], stream))
         if not same_stream:
             _native.synchronize()
+    _trace("stripe partials")
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(extremes, op=dist.ReduceOp.MIN, group=group)
+    if statistic in ("min", "max"):       # the extremes only travel when they are asked for
+        dist.all_reduce(extremes, op=dist.ReduceOp.MIN, group=group)
+    _trace("all-reduce")
     if not same_stream:
         torch.cuda.current_stream().synchronize()
-    out = _native.pinned_empty((n,), np.float32)
-    covered = _native.pinned_empty((n,), np.int64)
+    # (the result buffers are reused by the next call on this soup: copy what must outlive it)
+    out, covered = kept["out"], kept["covered"]
     _native.check(lib.gm_zonal_finalize_device(sums.data_ptr(), extremes.data_ptr(), n, _STAT_CODES[statistic],
                                                out.ctypes.data, covered.ctypes.data, stream))
-    return out, np.nonzero(covered == 0)[0].tolist()
+    _trace("finalise + download")
+    return out.copy(), np.nonzero(covered == 0)[0].tolist()
 
 
 # ---------------------------------------------------------------------------

@@ -285,11 +285,13 @@ int  gm_segment_order_stat(const void* values, int32_t dtype, const int64_t* off
  * sums[3N] = (count, covered cells, sum) as float64 for a SUM, extremes[2N] = (min, -max) for a
  * MIN -- and after the collectives the statistic of scipy.ndimage sum/mean/minimum/maximum
  * (geometry/aggregate.py:311-316) is formed from them.  `sums` / `extremes` are DEVICE
- * pointers (e.g. torch tensors); `out` / `covered` are host buffers.                        */
+ * pointers (e.g. torch tensors); `out` / `covered` are host buffers.  `stat` (GmStat, or -1 for
+ * everything) lets the stripe pass compute only what the statistic needs: the sums for
+ * sum / mean / count, one extreme for min / max.                                             */
 int  gm_zonal_partials_device(const GmArray* raster, const void* nodata, int has_nodata,
                               const GmPolygons* polys, const double geo[6],
                               const float* thresholds, int64_t row_begin, int64_t row_end,
-                              double* sums, double* extremes, void* stream);
+                              double* sums, double* extremes, int stat, void* stream);
 int  gm_zonal_finalize_device(const double* sums, const double* extremes, int64_t n_polygons,
                               int stat, float* out, int64_t* covered, void* stream);
 

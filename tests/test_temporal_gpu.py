@@ -27,10 +27,16 @@ def times(n):
     return [datetime(2000, 1, 1) + timedelta(hours=i) for i in range(n)]
 
 
+# (19, 45): 855 cells, no whole 16-byte pixel groups -> the one-pixel-per-thread kernels;
+# (16, 48): 768 cells -> the streaming kernels (16-byte loads, several pixels per thread)
+SHAPES = [(19, 45), (16, 48)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("dtype", ["f4", "u1", "i2", "i4", "f8"])
 @pytest.mark.parametrize("statistic", ["sum", "count", "min", "max", "mean", "median", "std", "var", "p90", "p25"])
-def test_aggregate_all_frames(dtype, statistic):
-    values, nodata = stack(dtype)
+def test_aggregate_all_frames(dtype, statistic, shape):
+    values, nodata = stack(dtype, shape=shape)
     name, q = (statistic, None) if not statistic.startswith("p") else ("percentile", float(statistic[1:]))
     expected, expected_nodata = R.temporal_aggregate(values, nodata, name, [range(len(values))], q)
     kwargs = dict(mode="vals", start=times(11)[-1], stop=None, frequency=None, timezone=None,
@@ -59,11 +65,12 @@ def test_aggregate_resampled(dtype, statistic):
     np.testing.assert_array_equal(got["values"], expected)
 
 
-@pytest.mark.parametrize("dtype", ["f4", "u1", "i4"])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dtype", ["f4", "u1", "i4", "f8"])
 @pytest.mark.parametrize("statistic", ["sum", "count"])
 @pytest.mark.parametrize("frequency", [None, "4h"])
-def test_cumulative(dtype, statistic, frequency):
-    values, nodata = stack(dtype, frames=10)
+def test_cumulative(dtype, statistic, frequency, shape):
+    values, nodata = stack(dtype, frames=10, shape=shape)
     ts = times(10)
     if frequency is None:
         bins = [list(range(10))]
