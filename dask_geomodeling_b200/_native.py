@@ -146,6 +146,8 @@ SYMBOLS = {
     "gm_hillshade": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _d, _d, _d, _d, _d, _vp]),
     "gm_moving_max": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _i, _vp]),
     "gm_dilate": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _vp]),
+    "gm_set_smooth_mode": (_i, [_i]),
+    "gm_get_smooth_mode": (_i, []),
     "gm_smooth": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _d, _vp, _i, _vp, _i, _i, _i, _i,
                        _d, _d, _d, _d, _vp]),
     "gm_temporal_aggregate": (_i, [_P(GmArray), _P(GmArray), _vp, _i, _i, _d, _vp, _vp, _i, _vp]),
@@ -432,6 +434,27 @@ def segment_order_statistic(values, offsets, statistic, percentile=None):
         values.ctypes.data if values.size else None, dtype_code(values.dtype), offsets.ctypes.data, n,
         _ORDER_STATS[statistic], float(percentile or 0.0), out.ctypes.data, current_stream()))
     return out
+
+
+SMOOTH_MODES = {"exact": 0, "fma": 1, "float32": 2}
+
+
+class smooth_arithmetic:
+    """Context manager: arithmetic of Smooth's tap sums ('exact' = SciPy bit for bit, 'fma' =
+    float64 with fused multiply-add (default), 'float32' = float32 accumulation); see
+    gm_set_smooth_mode in include/geokernels.h."""
+
+    def __init__(self, mode):
+        self.mode = SMOOTH_MODES[mode]
+
+    def __enter__(self):
+        self.previous = lib().gm_get_smooth_mode()
+        check(lib().gm_set_smooth_mode(self.mode))
+        return self
+
+    def __exit__(self, *exc):
+        lib().gm_set_smooth_mode(self.previous)
+        return False
 
 
 _pipeline_streams = []

@@ -9,8 +9,80 @@
 #include <limits>
 #include <algorithm>
 #include <type_traits>
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through the runtime)
 
 namespace gm {
+
+
+// ---- TMA tile staging ------------------------------------------------------------------------
+// Stencil tiles with their halo are fetched by ONE cp.async.bulk.tensor (2-D tile mode) into
+// shared memory and awaited on an mbarrier, instead of ~13 predicated loads per thread: the copy
+// engine walks the rows, the threads only patch "no data" cells afterwards.  A tensor map needs
+// a 16-byte aligned base and row pitch, so the TMA path is taken when the source window has
+// such a pitch (the blocks ask their store for a window padded to it, see raster/spatial.py)
+// and for tiles that lie wholly inside the window; everything else keeps the load path.
+typedef CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiled tensor_map_encoder() {
+  static TensorMapEncodeTiled fn = []() -> TensorMapEncodeTiled {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<TensorMapEncodeTiled>(p);
+  }();
+  return fn;
+}
+
+// 2-D map over a (rows, cols) array of 4-byte cells with a row pitch of `pitch_cols` cells, box =
+// (box_rows, box_cols).  Returns false when the array does not qualify (alignment) or the
+// driver refuses; the caller then uses the load path.
+static bool make_tile_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t pitch_cols,
+                          int box_rows, int box_cols, bool is_float) {
+  if (getenv("GM_NO_TMA")) return false;
+  TensorMapEncodeTiled encode = tensor_map_encoder();
+  if (!encode || ((uintptr_t)base % 16) != 0 || (pitch_cols * 4) % 16 != 0 || (box_cols * 4) % 16 != 0 ||
+      box_cols > 256 || box_rows > 256 || rows <= 0 || cols <= 0)
+    return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t elem[2] = {1, 1};
+  return encode(map, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_INT32, 2,
+                const_cast<void*>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void st_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ST_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra ST_WAIT_DONE;\n"
+      "bra ST_WAIT_LOOP;\n"
+      "ST_WAIT_DONE:\n"
+      "}\n" ::"r"(st_smem_u32(bar)), "r"(parity) : "memory");
+}
+// tile (x, y) of the map -> shared memory, completion counted on `bar`
+__device__ __forceinline__ void st_tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(st_smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(st_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void st_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T> static T read_scalar(const void* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 static dim3 grid3(int W, int H, int bands, int bx, int by) {
@@ -507,28 +579,59 @@ __device__ __forceinline__ void disc_quads(const T* chord_px, int plane_stride, 
 template <typename T, int SIZE>
 __global__ void __launch_bounds__(256)
 moving_max_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
-                       int bands, int H, int W, int dst_aligned) {
+                       int bands, int H, int W, int SW, int dst_aligned, int use_tma,
+                       const __grid_constant__ CUtensorMap tile_map) {
   static_assert(sizeof(T) == 4, "quads of four 4-byte cells");
-  extern __shared__ __align__(16) unsigned char mm_smem[];
+  extern __shared__ __align__(128) unsigned char mm_smem[];
+  __shared__ __align__(8) uint64_t tile_bar;
   constexpr int R = Disc<SIZE>::R;
   constexpr int NQ = (4 + 2 * R + 3) / 4;                // quads per segment window
   constexpr int TW = MM2_TX - 4 + 4 * NQ;                // tile row stride: every window in bounds
   constexpr int TH = MM2_TY + 2 * R;
   constexpr int PLANE = TH * MM2_TX;
   constexpr int SEGS = MM2_TX / 4;
-  T* tile = reinterpret_cast<T*>(mm_smem);               // TH x TW
+  // (the bulk tensor copy wants a 128-byte aligned destination: 128 spare bytes are allocated)
+  T* tile = reinterpret_cast<T*>(mm_smem + ((128u - (st_smem_u32(mm_smem) & 127u)) & 127u));   // TH x TW
   T* chord = tile + TH * TW;                             // n_planes x TH x MM2_TX
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int SW = W + 2 * R, SH = H + 2 * R;
+  const int SH = H + 2 * R;                 // SW >= W + 2 R: the window may carry pitch padding
   const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
   const int x0 = blockIdx.x * MM2_TX, y0 = blockIdx.y * MM2_TY;
   const T lowest = Lowest<T>::value();
+  uint32_t tile_phase = 0;
+  if (use_tma) {
+    if (threadIdx.x == 0) st_mbar_init(&tile_bar, 1);
+    __syncthreads();
+  }
   for (int b = blockIdx.z; b < bands; b += gridDim.z) {
     const T* plane = src + (int64_t)b * in_plane;
+    if (use_tma) st_fence_async();          // patches of the previous tile before the next bulk copy
     __syncthreads();
     // phase 1: the tile with its halo; tiles that lie inside the array (all but the last
     // row / column of tiles) skip every bound test
-    if (x0 + TW <= SW && y0 + TH <= SH) {
+    if (use_tma && x0 + TW <= SW && y0 + TH <= SH) {
+      // one bulk tensor copy for the whole TH x TW tile (bands are stacked along y in the map)
+      if (threadIdx.x == 0) {
+        st_mbar_expect_tx(&tile_bar, (uint32_t)(TH * TW * sizeof(T)));
+        st_tma_load_2d(tile, &tile_map, x0, b * SH + y0, &tile_bar);
+      }
+      st_mbar_wait(&tile_bar, tile_phase);
+      tile_phase ^= 1u;
+      if (has_nodata) {     // "no data" -> lowest, in place, a quad at a time
+        constexpr int QUADS = TH * TW / 4;
+        for (int i = threadIdx.x; i < QUADS; i += 256) {
+          Quad<T> q = lds_quad<T>(tile + 4 * i);
+          bool hit = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool nd = q.v[j] == nodata;
+            q.v[j] = nd ? lowest : q.v[j];
+            hit |= nd;
+          }
+          if (hit) sts_quad<T>(tile + 4 * i, q);
+        }
+      }
+    } else if (x0 + TW <= SW && y0 + TH <= SH) {
       constexpr int ITEMS = TH * TW, PER = (ITEMS + 255) / 256;
       const T* origin = plane + (int64_t)y0 * SW + x0;
       T raw[PER];
@@ -619,17 +722,22 @@ moving_max_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata,
 
 template <typename T, int SIZE>
 static int launch_moving_max_quad(const Staged& in, Staged& out, T nd, int has_nodata, int bands,
-                                  int H, int W, cudaStream_t s) {
+                                  int H, int W, int SW, cudaStream_t s) {
   constexpr int R = Disc<SIZE>::R;
   constexpr int NQ = (4 + 2 * R + 3) / 4;
   constexpr int TW = MM2_TX - 4 + 4 * NQ, TH = MM2_TY + 2 * R;
-  const size_t smem = ((size_t)TW * TH + (size_t)Disc<SIZE>::n_planes() * TH * MM2_TX) * sizeof(T);
+  const size_t smem = ((size_t)TW * TH + (size_t)Disc<SIZE>::n_planes() * TH * MM2_TX) * sizeof(T) + 128;
   auto kernel = moving_max_quad_kernel<T, SIZE>;
   if (smem > 48 * 1024)
     GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int aligned = ((uintptr_t)out.dev % 16 == 0) && (W % 4 == 0);
+  static_assert((TW * TH) % 4 == 0 && (TW * sizeof(T)) % 16 == 0, "tile rows are whole 16-byte groups");
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  const int SH = H + 2 * R;
+  const int use_tma = make_tile_map(&map, in.dev, (int64_t)bands * SH, SW, SW, TH, TW, std::is_same<T, float>::value);
   kernel<<<grid3(W, H, bands, MM2_TX, MM2_TY), 256, smem, s>>>((const T*)in.dev, (T*)out.dev, nd,
-                                                               has_nodata, bands, H, W, aligned);
+                                                               has_nodata, bands, H, W, SW, aligned, use_tma, map);
   GM_LAUNCH_CHECK();
   return 0;
 }
@@ -637,18 +745,19 @@ static int launch_moving_max_quad(const Staged& in, Staged& out, T nd, int has_n
 // 0: launched, 1: error, -1: no compile-time footprint for this dtype / size
 template <typename T>
 static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, int has_nodata,
-                                int bands, int H, int W, cudaStream_t s) {
+                                int bands, int H, int W, int SW, cudaStream_t s) {
   if constexpr (std::is_same<T, float>::value || std::is_same<T, double>::value ||
                 std::is_same<T, int16_t>::value || std::is_same<T, uint8_t>::value ||
                 std::is_same<T, int32_t>::value) {
     if constexpr (sizeof(T) == 4) {
       switch (size) {
-#define GM_CASE(N) case N: return launch_moving_max_quad<T, N>(in, out, nd, has_nodata, bands, H, W, s);
+#define GM_CASE(N) case N: return launch_moving_max_quad<T, N>(in, out, nd, has_nodata, bands, H, W, SW, s);
         GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
 #undef GM_CASE
         default: break;
       }
     }
+    if (SW != W + 2 * (size / 2)) return -1;   // only the quad kernel reads a padded pitch
     switch (size) {
 #define GM_CASE(N) case N: return launch_moving_max_fixed<T, N>(in, out, nd, has_nodata, bands, H, W, s);
       GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
@@ -887,6 +996,22 @@ smooth_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_
 }
 
 
+__device__ __forceinline__ double smooth_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float smooth_fma(float a, float b, float c) { return fmaf(a, b, c); }
+
+static std::atomic<int> g_smooth_mode{-1};
+static int smooth_mode() {
+  int m = g_smooth_mode.load();
+  if (m < 0) {
+    const char* env = getenv("GM_SMOOTH");
+    m = GM_SMOOTH_FMA;
+    if (env && !strcmp(env, "exact")) m = GM_SMOOTH_EXACT;
+    else if (env && !strcmp(env, "float32")) m = GM_SMOOTH_FLOAT32;
+    g_smooth_mode.store(m);
+  }
+  return m;
+}
+
 // Fast path for ly == lx == L <= SMF_MAXL (every "exact"-mode request: size_px <= 6 gives
 // L = int(4 * size_px / 3 + 0.5) <= 8).  Same arithmetic as smooth_kernel -- double
 // accumulation in SciPy's tap order, array-dtype rounding after each pass -- organised so
@@ -902,7 +1027,15 @@ smooth_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_
 // Bound: 22 FP64 operations per pass per pixel (1 + 3L at L = 7) on a 64-lane FP64 pipe.
 constexpr int SMF_TW = 128, SMF_TY = 32, SMF_RUN = 8, SMF_PITCH = SMF_TW + 1, SMF_MAXL = 8;
 
-template <typename T, int L>
+// ARITH: how a pass accumulates its 2 L + 1 taps
+//   GM_SMOOTH_EXACT    double, multiply and add rounded separately: SciPy's correlate1d bit for bit
+//   GM_SMOOTH_FMA      double, fused multiply-add: one rounding fewer per tap pair (the result can
+//                      differ from SciPy's by the last bit of the ARRAY dtype where a double sum
+//                      sits within 1e-16 of a rounding boundary); 1 + 2 L instead of 1 + 3 L FP64
+//                      operations per output
+//   GM_SMOOTH_FLOAT32  float32 rasters only: float accumulation with FFMA -- off the FP64 pipe
+//                      altogether; error <= (2 L + 1) * 2^-24 relative, inside the stated 1e-6
+template <typename T, int L, int ARITH>
 __global__ void __launch_bounds__(256)
 smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata, T fill,
                    int bands, int SH, int SW, int H, int W, int my, int mx,
@@ -974,16 +1107,22 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
     for (int task = tid; task < (SMF_TY / SMF_RUN) * SMF_TW; task += 256) {
       const int tx = task & (SMF_TW - 1), run = task >> 7;
       const T* c = tile + (run * SMF_RUN) * SMF_PITCH + tx;
-      double win[WIN];
+      typedef typename std::conditional<ARITH == GM_SMOOTH_FLOAT32, float, double>::type A;
+      A win[WIN], wk[L + 1];
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) win[i] = (double)c[i * SMF_PITCH];
+      for (int i = 0; i < WIN; ++i) win[i] = (A)c[i * SMF_PITCH];
+#pragma unroll
+      for (int k = 0; k <= L; ++k) wk[k] = (A)wts.wy[k];
       const int gx = x0 + mx - L + tx;
       const bool pad = gx < 0 || gx >= SW;   // columns outside the source: constant padding
 #pragma unroll
       for (int o = 0; o < SMF_RUN; ++o) {
-        double tmp = win[o + L] * wts.wy[0];
+        A tmp = win[o + L] * wk[0];
 #pragma unroll
-        for (int k = L; k >= 1; --k) tmp += (win[o + L - k] + win[o + L + k]) * wts.wy[k];
+        for (int k = L; k >= 1; --k) {
+          if (ARITH == GM_SMOOTH_EXACT) tmp += (win[o + L - k] + win[o + L + k]) * wk[k];
+          else tmp = smooth_fma(win[o + L - k] + win[o + L + k], wk[k], tmp);
+        }
         const T r = from_double<T>(tmp);
         mid[(run * SMF_RUN + o) * SMF_PITCH + tx] = pad ? fill : r;
       }
@@ -993,14 +1132,20 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
 #pragma unroll 1
     for (int run = warp; run * SMF_RUN < TX; run += 8) {
       const T* c = mid + lane * SMF_PITCH + run * SMF_RUN;
-      double win[WIN];
+      typedef typename std::conditional<ARITH == GM_SMOOTH_FLOAT32, float, double>::type A;
+      A win[WIN], wk[L + 1];
 #pragma unroll
-      for (int i = 0; i < WIN; ++i) win[i] = (double)c[i];  // may run into the next row / the slack: only feeds outputs >= TX
+      for (int i = 0; i < WIN; ++i) win[i] = (A)c[i];  // may run into the next row / the slack: only feeds outputs >= TX
+#pragma unroll
+      for (int k = 0; k <= L; ++k) wk[k] = (A)wts.wx[k];
 #pragma unroll
       for (int o = 0; o < SMF_RUN; ++o) {
-        double tmp = win[o + L] * wts.wx[0];
+        A tmp = win[o + L] * wk[0];
 #pragma unroll
-        for (int k = L; k >= 1; --k) tmp += (win[o + L - k] + win[o + L + k]) * wts.wx[k];
+        for (int k = L; k >= 1; --k) {
+          if (ARITH == GM_SMOOTH_EXACT) tmp += (win[o + L - k] + win[o + L + k]) * wk[k];
+          else tmp = smooth_fma(win[o + L - k] + win[o + L + k], wk[k], tmp);
+        }
         if (run * SMF_RUN + o < TX) stage[lane * TX + run * SMF_RUN + o] = from_double<T>(tmp);
       }
     }
@@ -1027,19 +1172,33 @@ smooth_fast_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int
     }
   }
 }
-template <typename T, int L>
-static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
-                              int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
-                              cudaStream_t s) {
+template <typename T, int L, int ARITH>
+static int launch_smooth_fast_as(const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
+                                 int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
+                                 cudaStream_t s) {
   constexpr int TX = SMF_TW - 2 * L;
   const size_t smem = (((size_t)(SMF_TY + 2 * L) + SMF_TY) * SMF_PITCH + 2 * SMF_MAXL) * sizeof(T);
-  auto kernel = smooth_fast_kernel<T, L>;
+  auto kernel = smooth_fast_kernel<T, L, ARITH>;
   if (smem > 48 * 1024)
     GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid3(W, H, bands, TX, SMF_TY), 256, smem, s>>>((const T*)in.dev, target, nd, has_nodata, fill,
                                                            bands, SH, SW, H, W, my, mx, wts);
   GM_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T, int L>
+static int launch_smooth_fast(const Staged& in, T* target, T nd, int has_nodata, T fill, int bands,
+                              int SH, int SW, int H, int W, int my, int mx, const SmoothWeights& wts,
+                              cudaStream_t s) {
+  const int mode = smooth_mode();
+  if constexpr (std::is_same<T, float>::value) {
+    if (mode == GM_SMOOTH_FLOAT32)
+      return launch_smooth_fast_as<T, L, GM_SMOOTH_FLOAT32>(in, target, nd, has_nodata, fill, bands, SH, SW, H, W, my, mx, wts, s);
+  }
+  if (mode == GM_SMOOTH_EXACT)
+    return launch_smooth_fast_as<T, L, GM_SMOOTH_EXACT>(in, target, nd, has_nodata, fill, bands, SH, SW, H, W, my, mx, wts, s);
+  return launch_smooth_fast_as<T, L, GM_SMOOTH_FMA>(in, target, nd, has_nodata, fill, bands, SH, SW, H, W, my, mx, wts, s);
 }
 
 // 0: launched, 1: error, -1: no fast path for this dtype / radius
@@ -1113,7 +1272,7 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
 
 template <typename T>
 static int run_moving_max(const Staged& in, Staged& out, const void* nodata, int has_nodata,
-                          int bands, int H, int W, int size, cudaStream_t s) {
+                          int bands, int H, int W, int SW, int size, cudaStream_t s) {
   const int r = size / 2;
   if (r > MM_MAXR) return fail("gm_moving_max: size too large (max 65)");
   // chord half-widths of the disc x^2 + y^2 < (size/2)^2 (utils.py:536-547)
@@ -1127,9 +1286,12 @@ static int run_moving_max(const Staged& in, Staged& out, const void* nodata, int
   }
   {
     const int fixed = try_moving_max_fixed<T>(size, in, out, has_nodata ? read_scalar<T>(nodata) : T(0),
-                                              has_nodata, bands, H, W, s);
+                                              has_nodata, bands, H, W, SW, s);
     if (fixed >= 0) return fixed;
   }
+  if (SW != W + 2 * r)
+    return fail("gm_moving_max: a source wider than the output plus its halo (pitch padding) is only "
+                "supported for 4-byte rasters and odd sizes 3..15");
   if (r >= 1 && r <= MM2_MAXR) {
     MMFootprint fp;
     memset(&fp, 0, sizeof(fp));
@@ -1303,9 +1465,12 @@ extern "C" int gm_moving_max(const GmArray* src, GmArray* dst, const void* nodat
     const int bands = (int)dst->shape[0], H = (int)dst->shape[1], W = (int)dst->shape[2];
     const int r = size / 2;
     if (src->dtype != dst->dtype) return fail("gm_moving_max: dtype mismatch");
-    if (src->shape[0] != bands || src->shape[1] != H + 2 * r || src->shape[2] != W + 2 * r)
+    // columns beyond W + 2 r are pitch padding (ignored): they make the row pitch a multiple of
+    // 16 bytes so that tiles can be fetched by TMA
+    if (src->shape[0] != bands || src->shape[1] != H + 2 * r || src->shape[2] < W + 2 * r)
       return fail("gm_moving_max: source must carry a size//2 pixel halo");
-    GM_DISPATCH_NUMERIC(src->dtype, run_moving_max<T>(in, out, nodata, has_nodata, bands, H, W, size, s));
+    const int SW = (int)src->shape[2];
+    GM_DISPATCH_NUMERIC(src->dtype, run_moving_max<T>(in, out, nodata, has_nodata, bands, H, W, SW, size, s));
   });
 }
 
@@ -1319,6 +1484,13 @@ extern "C" int gm_dilate(const GmArray* src, GmArray* dst, const void* values, i
     GM_DISPATCH_NUMERIC(src->dtype, run_dilate<T>(in, out, values, n_values, bands, H, W, s));
   });
 }
+
+extern "C" int gm_set_smooth_mode(int mode) {
+  if (mode < GM_SMOOTH_EXACT || mode > GM_SMOOTH_FLOAT32) return fail("gm_set_smooth_mode: bad mode");
+  g_smooth_mode.store(mode);
+  return 0;
+}
+extern "C" int gm_get_smooth_mode(void) { return smooth_mode(); }
 
 extern "C" int gm_smooth(const GmArray* src, GmArray* dst, const void* nodata, int has_nodata,
                          double fill, const double* wy, int ly, const double* wx, int lx, int my,

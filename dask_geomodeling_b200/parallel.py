@@ -185,15 +185,19 @@ def refresh_halo(haloed, halo_rows, halo_cols=0, group=None):
     return haloed
 
 
-def pad_columns(values, halo, fill):
+def pad_columns(values, halo, fill, pitch=1):
     """Add `halo` columns of `fill` on both sides (the x halo a stencil block requests;
-    stripes span the full width, so this is always the outer boundary)."""
+    stripes span the full width, so this is always the outer boundary).  With ``pitch`` > 1 the
+    row is padded further on the right to a multiple of `pitch` cells (MovingMax stages its tiles
+    by TMA when a row is a whole number of 16-byte groups; pass the extra columns as its ``pad``)."""
     import torch
 
-    if halo == 0:
-        return values
     bands, rows, width = values.shape
-    out = torch.full((bands, rows, width + 2 * halo), fill, dtype=values.dtype, device=values.device)
+    total = width + 2 * halo
+    total += (-total) % pitch
+    if total == width:
+        return values
+    out = torch.full((bands, rows, total), fill, dtype=values.dtype, device=values.device)
     out[:, :, halo:halo + width] = values
     return out
 

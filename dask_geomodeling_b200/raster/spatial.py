@@ -133,13 +133,25 @@ class MovingMax(BaseSingle):
     size = property(lambda self: self.args[1])
 
     def get_sources_and_requests(self, **request):
-        enlarged = expand_request_pixels(request, radius=int(self.size // 2))
+        radius = int(self.size // 2)
+        enlarged = expand_request_pixels(request, radius=radius)
         if enlarged is None:
             return [(self.store, request)]
-        return [(self.store, enlarged), (self.size, None)]
+        # 4-byte rasters: ask for a few more columns on the right so that a row of the window is
+        # a whole number of 16-byte groups -- the kernel then stages its tiles by TMA (a tensor
+        # map needs a 16-byte row pitch); the extra columns are never part of a footprint
+        pad = 0
+        if np.dtype(self.dtype).itemsize == 4 and self.size <= 15:
+            pad = (-enlarged["width"]) % 4
+        if pad:
+            x1, y1, x2, y2 = enlarged["bbox"]
+            cell = (request["bbox"][2] - request["bbox"][0]) / request["width"]
+            enlarged["bbox"] = (x1, y1, x2 + pad * cell, y2)
+            enlarged["width"] += pad
+        return [(self.store, enlarged), (self.size, None), (pad, None)]
 
     @staticmethod
-    def process(data, size=None):
+    def process(data, size=None, pad=0):
         if data is None or size is None or "values" not in data:
             return data
         source = data["values"]
@@ -147,7 +159,7 @@ class MovingMax(BaseSingle):
         t, h, w = source.shape
         holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
         out = _call_stencil(
-            source, (t, h - 2 * radius, w - 2 * radius), source.dtype,
+            source, (t, h - 2 * radius, w - 2 * radius - int(pad)), source.dtype,
             lambda lib, src, dst, stream: lib.gm_moving_max(src, dst, nodata_ptr, has_nodata,
                                                             int(size), stream),
         )

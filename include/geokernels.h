@@ -213,6 +213,17 @@ int  gm_dilate(const GmArray* src, GmArray* dst, const void* values, int n_value
 /* Gaussian: weights are scipy's _gaussian_kernel1d (host, float64), radius
  * ly/lx taps; margins my/mx are cropped ("exact" mode).  zoom=1 applies the
  * nearest-neighbour zoom-back instead (:296-305).                           */
+/* Arithmetic of the Gaussian's tap sums when both radii are <= 8 taps (every "exact"-mode request):
+ *   GM_SMOOTH_EXACT    float64, multiply and add rounded separately -- scipy.ndimage.gaussian_filter
+ *                      bit for bit;
+ *   GM_SMOOTH_FMA      (default; env GM_SMOOTH=exact|fma|float32) float64 with fused multiply-add:
+ *                      equal to SciPy except where a double sum lies within one rounding of a
+ *                      boundary of the array dtype (then the last bit of the result may differ);
+ *   GM_SMOOTH_FLOAT32  float32 rasters: float32 accumulation, relative error <= 1e-6.
+ * Other radii and the zoom mode always use the exact arithmetic.                               */
+enum GmSmoothMode { GM_SMOOTH_EXACT = 0, GM_SMOOTH_FMA = 1, GM_SMOOTH_FLOAT32 = 2 };
+int  gm_set_smooth_mode(int mode);
+int  gm_get_smooth_mode(void);
 int  gm_smooth(const GmArray* src, GmArray* dst, const void* nodata, int has_nodata,
                double fill, const double* wy, int ly, const double* wx, int lx,
                int my, int mx, int zoom, double zy, double zx, double oy, double ox,

@@ -23,3 +23,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _exact_smooth_arithmetic(request):
+    """GPU tests compare Smooth with SciPy bit for bit: they run with the exact tap arithmetic
+    (GM_SMOOTH_EXACT).  The default (fused multiply-add) and the float32 arithmetic have their own
+    tolerance tests in tests/test_spatial_gpu.py."""
+    if "gpu" not in request.keywords or not _has_gpu():
+        yield
+        return
+    from dask_geomodeling_b200 import _native
+
+    with _native.smooth_arithmetic("exact"):
+        yield

@@ -83,6 +83,37 @@ def test_hillshade(dtype, angles):
     assert (delta > 0).mean() <= 1e-3
 
 
+@pytest.mark.parametrize("dtype", ["f4", "i4"])
+@pytest.mark.parametrize("size", [3, 5, 11, 15])
+@pytest.mark.parametrize("pad", [0, 1, 2, 3])
+def test_moving_max_padded_pitch(dtype, size, pad):
+    """Windows whose rows are whole 16-byte groups (with `pad` extra columns on the right) take
+    the TMA tile staging for interior tiles; the padding never enters a footprint."""
+    r = size // 2
+    h, w = 150, 201 + ((-(201 + 2 * r + pad)) % 4)       # (w + 2 r + pad) % 4 == 0: TMA eligible
+    values, nodata = dem((2, h + 2 * r, w + 2 * r), 9, dtype=dtype, nodata_fraction=0.05)
+    expected, _ = R.moving_max(values, nodata, size)
+    padded = np.full((2, h + 2 * r, w + 2 * r + pad), nodata, dtype=values.dtype)
+    padded[:, :, :w + 2 * r] = values
+    if pad:
+        padded[:, :, w + 2 * r:] = R.dtype_max(dtype) - 1       # a value that would win if it were read
+    got = raster.MovingMax.process({"values": padded, "no_data_value": nodata}, size, pad)
+    np.testing.assert_array_equal(np.asarray(got["values"]), expected)
+
+
+def test_moving_max_view_pads_its_request():
+    a, _ = workloads.cfg1_arrays(160)
+    src = workloads.source(a, workloads.F32_MAX)
+    req = workloads.request(131, 131)
+    req["bbox"] = (10, 12, 141, 143)
+    view = raster.MovingMax(src, 11)
+    (_, enlarged), _, (pad, _) = view.get_sources_and_requests(**req)
+    assert (enlarged["width"] * 4) % 16 == 0 and pad == enlarged["width"] - 131 - 10
+    got = view.get_data(**req)
+    expected = R.moving_max(a[:, 160 - 143 - 5:160 - 12 + 5, 10 - 5:141 + 5], workloads.F32_MAX, 11)[0]
+    np.testing.assert_array_equal(got["values"], expected)
+
+
 def test_blocks_through_get_data():
     a, _ = workloads.cfg1_arrays(96)
     src = workloads.source(a, workloads.F32_MAX)
