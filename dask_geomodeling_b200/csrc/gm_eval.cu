@@ -473,16 +473,38 @@ __device__ __forceinline__ void exec_unary(const GmInstr& in, S (&acc)[V], const
 
 // FillNoData step (raster/elemwise.py:752-755): acc = isdata(b) ? astype(b) : acc; the
 // sentinel test (np.isclose for floats) runs in class T = class of b; To = class of acc.
+// With aux != 0 the step REDUCES instead of replacing (reduce_rasters, raster/reduction.py:38-119):
+// acc = isdata(b) ? red(acc, astype(b)) : acc with red = max / min / sum / product in a float
+// class where NaN marks "no value yet" (NaN cells of b are skipped as np.nan* functions do), or
+// count (acc += 1 in any class).
+template <typename To> __device__ __forceinline__ To overlay_reduce(int kind, To a, To b) {
+  if (kind == GM_RED_COUNT) return (To)(a + (To)1);
+  if constexpr (IsFloat<To>::value) {
+    if (b != b) return a;
+    if (a != a) return b;
+    switch (kind) {
+      case GM_RED_MAX: return b > a ? b : a;
+      case GM_RED_MIN: return b < a ? b : a;
+      case GM_RED_SUM: return a + b;
+      default: return a * b;
+    }
+  }
+  return b;
+}
+
 template <typename T, typename To, int V, typename S>
 __device__ __forceinline__ void exec_overlay(const GmInstr& in, S (&acc)[V], const S* __restrict__ bp) {
   const T nd = Raw<T>::get(in.k[2]), tol = Raw<T>::get(in.k[4]);
   const bool has = in.flags & GM_F_ND_T, cl = in.flags & GM_F_CLOSE, fin = in.flags & GM_F_ND_FINITE;
+  const int kind = (int)in.aux;
   const int tid = threadIdx.x;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const T y = Raw<T>::get(bp[i * THREADS + tid]);
     const bool nod = has && (cl ? close_(y, nd, tol, fin) : (y == nd));
-    acc[i] = nod ? acc[i] : (S)Raw<To>::put(astype<To>(y));
+    const To fresh = astype<To>(y);
+    const To next = kind == GM_RED_REPLACE ? fresh : overlay_reduce<To>(kind, Raw<To>::get(acc[i]), fresh);
+    acc[i] = nod ? acc[i] : (S)Raw<To>::put(next);
   }
 }
 

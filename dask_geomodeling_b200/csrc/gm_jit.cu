@@ -202,7 +202,7 @@ static std::string emit_instruction(const GmProgram* prog, const GmInstr& in) {
       if (class_fits(in.cls, word) && class_fits(in.cls_out, word))
         s = std::string("acc = overlay<") + class_type(in.cls) + ", " + class_type(in.cls_out) + ", " +
             tf(in.flags & GM_F_ND_T) + ", " + tf(in.flags & GM_F_CLOSE) + ", " + tf(in.flags & GM_F_ND_FINITE) +
-            ">(acc, " + b + ", " + hex(in.k[2]) + ", " + hex(in.k[4]) + ");";
+            ", " + num((int)in.aux) + ">(acc, " + b + ", " + hex(in.k[2]) + ", " + hex(in.k[4]) + ");";
       break;
     case GM_OP_EXP: case GM_OP_LOG: case GM_OP_LOG10:
       if (class_fits(in.cls, word) && class_is_float(in.cls) && in.cls == in.cls_a)

@@ -299,8 +299,10 @@ GM_DEV S classify(S a, const int64_t* keys, int n, uint64_t k1, uint64_t k3) {
   return (S)(uint32_t)lo;
 }
 
-// FillNoData step: acc = isdata(b) ? astype(b) : acc
-template <typename T, typename To, bool HAS, bool CL, bool FIN>
+// FillNoData step: acc = isdata(b) ? astype(b) : acc; KIND != 0: the reducing forms of
+// reduce_rasters (1 max, 2 min, 3 sum, 4 product over a float class with NaN = no value yet,
+// 5 count)
+template <typename T, typename To, bool HAS, bool CL, bool FIN, int KIND>
 GM_DEV S overlay(S a, uint64_t b, uint64_t k2, uint64_t k4) {
   const T y = Raw<T>::get(b);
   bool nod = false;
@@ -308,7 +310,20 @@ GM_DEV S overlay(S a, uint64_t b, uint64_t k2, uint64_t k4) {
     if constexpr (CL) nod = close_(y, Raw<T>::get(k2), Raw<T>::get(k4), FIN);
     else nod = y == Raw<T>::get(k2);
   }
-  return nod ? a : (S)Raw<To>::put((To)y);
+  To next = (To)y;
+  if constexpr (KIND == 5) {
+    next = (To)(Raw<To>::get(a) + (To)1);
+  } else if constexpr (KIND != 0) {
+    const To old = Raw<To>::get(a);
+    if (next != next) next = old;
+    else if (old == old) {
+      if constexpr (KIND == 1) next = next > old ? next : old;
+      else if constexpr (KIND == 2) next = next < old ? next : old;
+      else if constexpr (KIND == 3) next = old + next;
+      else next = old * next;
+    }
+  }
+  return nod ? a : (S)Raw<To>::put(next);
 }
 
 // Reclassify.  found: 0 miss, 1 mapped, 2 mapped onto the fill value

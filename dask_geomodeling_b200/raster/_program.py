@@ -30,6 +30,7 @@ F_ND_A, F_ND_B, F_CLOSE, F_ND_FINITE, F_B_BOOL, F_RIGHT, F_SELECT, F_ND_T = 1, 2
 F_NAN = 32  # LOAD / MATB / CVT: sentinel -> NaN (shares the bit of F_RIGHT)
 
 DENSE_TABLE_LIMIT = 4096
+RED_KINDS = {"max": 1, "min": 2, "sum": 3, "product": 4, "count": 5}   # GmReduce
 
 
 class FusionLimit(Exception):
@@ -519,6 +520,85 @@ class _Compiler(object):
                 self.free_reg(scratch)
             self.release(c)
         return _Typed(dtype, fill)
+
+    def _overlay_operand(self, c):
+        """Flags and constants of an OVERLAY step for child ``c`` (its has-data test is
+        utils.get_index: np.isclose for floats, == otherwise): (typed, cmp class, flags, k2, k4)."""
+        tc = self.operand_type(c)
+        flags, cmp_cls, k2, k4 = 0, tc.cls, 0, 0
+        if tc.nodata is not None:
+            if tc.dtype.kind == "f":
+                cmp_dtype, y, tol, fin = _isclose_terms(tc.dtype, tc.nodata)
+                cmp_cls = dtype_class(cmp_dtype)
+                flags = F_ND_T | F_CLOSE | (F_ND_FINITE if fin else 0)
+                k2, k4 = _bits(y, cmp_cls), _bits(tol, cmp_cls)
+            else:
+                s = sentinel(tc.dtype, tc.nodata)
+                if s is not None:
+                    flags, k2 = F_ND_T, _bits(s, cmp_cls)
+        return tc, cmp_cls, flags, k2, k4
+
+    def op_reduce(self, n):
+        """reduce_rasters (raster/reduction.py:38-119): 'last' / 'first' overlay the children,
+        'count' counts those with data, 'max' / 'min' / 'sum' / 'product' reduce them in the
+        float dtype NumPy's nan-functions would use (np.result_type(dtype, float16); a NaN
+        accumulator means "no value yet") and cast the result back, all-'no data' cells -> fill."""
+        p = n.params
+        statistic = p["statistic"]
+        dtype = np.dtype(p["dtype"])
+        nodata = p["fillvalue"]
+        T = dtype_class(dtype)
+        children = list(n.children)
+        if statistic == "first":
+            children = children[::-1]
+        for c in children:
+            if self.is_complex(c):
+                self.spill_to_reg(c)
+        if statistic in ("last", "first"):
+            kind, acc_dtype, init = 0, dtype, _cast_into(nodata, dtype)
+        elif statistic == "count":
+            kind, acc_dtype, init = RED_KINDS["count"], dtype, 0
+        else:
+            work = np.result_type(dtype, np.float16)
+            if statistic in ("sum", "product") and work != dtype:
+                raise NotImplementedError(
+                    "reduce_rasters('{}') of {} rasters accumulates in {} on the CPU path; the CUDA path "
+                    "reduces float32 / float64 rasters only".format(statistic, dtype, work))
+            acc_dtype = np.dtype("f8") if work == np.float64 else np.dtype("f4")
+            kind, init = RED_KINDS[statistic], float("nan")
+        A = dtype_class(acc_dtype)
+        self.emit("LOAD", cls_b=A, cls_out=A, src=(SRC_IMM, 0), k=(_bits(init, A),))
+        for c in children:
+            tc, cmp_cls, flags, k2, k4 = self._overlay_operand(c)
+            saved = None
+            if isinstance(c, Leaf):  # the sentinel test happens inside OVERLAY, in cmp_cls
+                saved, self.leaves[c.index] = self.leaves[c.index], _Typed(tc.dtype, None)
+            try:
+                src, _, _, _, _, scratch = self.b_operand(c, cmp_cls, nan_ok=False)
+            finally:
+                if saved is not None:
+                    self.leaves[c.index] = saved
+            self.emit("OVERLAY", cls=cmp_cls, cls_a=A, cls_b=cmp_cls, cls_out=A, src=src, flags=flags,
+                      aux=kind, k=(0, 0, k2, 0, k4))
+            if scratch is not None:
+                self.free_reg(scratch)
+            self.release(c)
+        if statistic in ("last", "first", "count"):
+            return _Typed(dtype, nodata)
+        # acc (float, NaN = every child was 'no data') -> out dtype, NaN cells -> fill
+        fill = 0 if statistic == "sum" else nodata
+        value_reg, mask_reg = self.alloc_reg(), self.alloc_reg()
+        self.emit("ST", cls_a=A, cls_out=A, aux=value_reg)
+        self.emit("EQ", cls=A, cls_a=A, cls_b=A, cls_out=C_I32, src=(SRC_REG, value_reg))   # NaN != NaN
+        self.emit("ST", aux=mask_reg)
+        self.emit("LOAD", cls_b=A, cls_out=A, src=(SRC_REG, value_reg))
+        if A != T:
+            self.emit("CVT", cls_a=A, cls_out=T)
+        self.emit("CLIP", cls_a=T, cls_b=C_I32, cls_out=T, src=(SRC_REG, mask_reg), flags=F_B_BOOL,
+                  k=(0, _bits(_cast_into(fill, dtype), T)))
+        self.free_reg(value_reg)
+        self.free_reg(mask_reg)
+        return _Typed(dtype, nodata)
 
     def op_clip(self, n):
         store, mask = n.children

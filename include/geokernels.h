@@ -70,7 +70,9 @@ enum GmOp {
   GM_OP_EQ, GM_OP_NE, GM_OP_GT, GM_OP_GE, GM_OP_LT, GM_OP_LE,
   GM_OP_AND, GM_OP_OR, GM_OP_XOR, GM_OP_NOT,
   GM_OP_ISDATA, GM_OP_ISNODATA,
-  GM_OP_OVERLAY,    /* FillNoData step: acc = isdata(b) ? b : acc           */
+  GM_OP_OVERLAY,    /* FillNoData step: acc = isdata(b) ? b : acc; with aux = a
+                       GmReduce kind the step reduces instead (reduce_rasters,
+                       raster/reduction.py:38-119): acc = isdata(b) ? red(acc, b) : acc */
   GM_OP_CLIP,       /* acc = masked(b) ? k1 : acc                           */
   GM_OP_MASK,       /* acc = isnodata(acc) ? k3 : k0                        */
   GM_OP_MASKBELOW,  /* acc = acc < k0 ? k1 : acc                            */
@@ -80,6 +82,11 @@ enum GmOp {
   GM_OP_MATB,       /* reg[aux] = convert(b: cls_b -> cls_out), acc untouched */
   GM_OP_COUNT_
 };
+
+/* reduction kinds of GM_OP_OVERLAY (aux): max / min / sum / product keep acc in a float class
+ * where NaN means "no value yet" and skip NaN cells like np.nanmax etc.; count adds one        */
+enum GmReduce { GM_RED_REPLACE = 0, GM_RED_MAX = 1, GM_RED_MIN = 2, GM_RED_SUM = 3, GM_RED_PRODUCT = 4,
+                GM_RED_COUNT = 5 };
 
 enum GmSrcKind { GM_SRC_NONE = 0, GM_SRC_REG = 1, GM_SRC_INPUT = 2, GM_SRC_IMM = 3 };
 

@@ -424,3 +424,70 @@ def zonal_from_labels(frame, nodata, label_sets, n_geometries, statistic, q=None
                                     labels=active_labels, index=chosen)
         agg[chosen] = res
     return agg, sorted(no_cells)
+
+
+# ---- reductions over several rasters --------------------------------------------------------
+
+_NAN_REDUCERS = {"sum": np.nansum, "min": np.nanmin, "max": np.nanmax, "product": np.nanprod}
+
+
+def reduce_rasters(stack, statistic, nodata=None, dtype=None):
+    """raster/reduction.py:38-119 for the statistics of the CUDA path.  ``stack`` = list of
+    (values, no data value); returns (values, no data value)."""
+    if dtype is None:
+        dtype = stack[0][0].dtype
+    if nodata is None:
+        nodata = stack[0][1]
+    dtype = np.dtype(dtype)
+    shape = stack[0][0].shape
+    out = np.full(shape, 0 if statistic in ("sum", "count") else nodata, dtype)
+    if statistic in ("last", "first"):
+        for values, nd in (stack if statistic == "last" else stack[::-1]):
+            index = has_data_close(values, nd)
+            out[index] = values[index]
+    elif statistic == "count":
+        for values, nd in stack:
+            out += has_data_close(values, nd)
+    else:
+        stacked = np.full((len(stack),) + shape, np.nan, np.result_type(dtype, np.float16))
+        for i, (values, nd) in enumerate(stack):
+            index = has_data_close(values, nd)
+            stacked[i, index] = values[index]
+        some = ~np.all(np.isnan(stacked), axis=0)
+        out[some] = _NAN_REDUCERS[statistic](stacked[:, some], axis=0)
+    return out, nodata
+
+
+def has_data_close(values, nodata):
+    """utils.get_index (utils.py:61-64): np.isclose decides for floats."""
+    if nodata is None:
+        return np.ones(values.shape, dtype=bool)
+    if values.dtype.kind == "f":
+        return ~np.isclose(values, nodata)
+    return values != nodata
+
+
+def group_by_bands(stack, bands, dtype, shape):
+    """Group._merge_vals_by_bands (raster/combine.py:371-387)."""
+    fill = dtype_max(dtype)
+    values = np.full(shape, fill, dtype=dtype)
+    for (source, nd), (a, b) in zip(stack, bands):
+        index = has_data_close(source, nd)
+        values[a:b][index] = source[index]
+    return values, fill
+
+
+def group_by_time(stack, times, dtype, start, stop):
+    """Group._merge_vals_by_time (raster/combine.py:316-343)."""
+    instants = sorted(set(t for ts in times for t in ts))
+    frame_of = {t: k for k, t in enumerate(instants)}
+    fill = dtype_max(dtype)
+    values = np.full((len(instants),) + stack[0][0].shape[1:], fill, dtype=dtype)
+    for (source, nd), ts in zip(stack, times):
+        for i, t in enumerate(ts):
+            index = has_data_close(source[i], nd)
+            values[frame_of[t]][index] = source[i][index]
+    if stop is None and len(instants) > 1:
+        k = len(instants) - 1 if start is None else min(range(len(instants)), key=lambda i: abs(instants[i] - start))
+        values = values[k:k + 1]
+    return values, fill

@@ -134,7 +134,7 @@ _loaded = None
 
 def load():
     """Namespace with the reference's hot-path modules (elemwise, misc, spatial,
-    temporal, aggregate, measurements, utils)."""
+    temporal, reduction, combine, aggregate, measurements, utils)."""
     global _loaded
     if _loaded is not None:
         return _loaded
@@ -153,5 +153,7 @@ def load():
     ns.temporal = importlib.import_module("dask_geomodeling.raster.temporal")
     ns.measurements = importlib.import_module("dask_geomodeling.measurements")
     ns.aggregate = importlib.import_module("dask_geomodeling.geometry.aggregate")
+    ns.reduction = importlib.import_module("dask_geomodeling.raster.reduction")
+    ns.combine = importlib.import_module("dask_geomodeling.raster.combine")
     _loaded = ns
     return ns

@@ -287,10 +287,56 @@ def zonal(ns):
     rec.save("zonal")
 
 
+def reductions(ns):
+    """reduce_rasters (raster/reduction.py:38-119) as Max and Place call it, and Group's two
+    merges (raster/combine.py:316-343, :371-387)."""
+    rec = Recorder()
+    seed = 700
+    for dtype in ("f4", "f8", "u1", "i2", "i4"):
+        for statistic in ("last", "first", "count", "max", "min", "sum", "product"):
+            if statistic in ("sum", "product") and dtype not in ("f4", "f8"):
+                continue
+            seed += 1
+            stack = [raster(dtype, seed * 10 + k, lo=1, hi=9 if statistic == "product" else 100,
+                            nodata_fraction=0.4) for k in range(3)]
+            # a second 'no data' value in the middle raster (sources need not agree on it)
+            values, nodata = stack[1]
+            other = np.dtype(dtype).type(7)
+            values = values.copy()
+            values[values == nodata] = other
+            stack[1] = (values, other.item())
+            res = ns.reduction.reduce_rasters([payload(p) for p in stack], statistic, dmax(dtype), dtype)
+            rec.add("reduce", statistic, {"dtype": dtype, "no_data_value": dmax(dtype)}, stack, res)
+    # Max over mixed dtypes: output dtype = result_type, no data value of the block
+    stack = [raster("u1", 801, nodata_fraction=0.5), raster("f4", 802, nodata_fraction=0.5)]
+    res = ns.reduction.reduce_rasters([payload(p) for p in stack], "max", dmax("f4"), "float32")
+    rec.add("reduce", "max", {"dtype": "float32", "no_data_value": dmax("f4")}, stack, res)
+    # defaults: dtype and no data value of the first raster
+    stack = [raster("i2", 803, nodata_fraction=0.5), raster("i2", 804, nodata_fraction=0.5)]
+    res = ns.reduction.reduce_rasters([payload(p) for p in stack], "last")
+    rec.add("reduce", "last", {"dtype": None, "no_data_value": None}, stack, res)
+    # Group, equidistant sources: frames [0, 2) from the first, [1, 3) from the second, ...
+    for dtype in ("f4", "u1"):
+        a, b, c = (raster(dtype, 810 + k, nodata_fraction=0.5, shape=(2, 23, 31)) for k in range(3))
+        bands = [(0, 2), (1, 3), (2, 4)]
+        res = ns.combine.Group._merge_vals_by_bands(
+            [payload(a), payload(b), payload(c)], bands, np.dtype(dtype), (4, 23, 31))
+        rec.add("group_bands", "group", {"bands": bands, "dtype": dtype, "shape": [4, 23, 31]}, [a, b, c], res)
+    # Group, sources with their own time stamps (integers stand in for datetimes)
+    a, b = raster("f4", 820, nodata_fraction=0.5, shape=(3, 23, 31)), raster("f4", 821, nodata_fraction=0.5)
+    times = [[0, 2, 5], [2, 3]]
+    for start, stop in ((0, 5), (3, None), (None, None)):
+        res = ns.combine.Group._merge_vals_by_time(
+            [payload(a), payload(b)], [{"time": t} for t in times],
+            {"dtype": np.dtype("f4"), "start": start, "stop": stop})
+        rec.add("group_time", "group", {"times": times, "dtype": "f4", "start": start, "stop": stop}, [a, b], res)
+    rec.save("reduce")
+
+
 if __name__ == "__main__":
     ns = refharness.load()
-    elementwise(ns)
-    misc(ns)
-    spatial(ns)
-    temporal(ns)
-    zonal(ns)
+    only = set(sys.argv[1:])
+    for name, build in (("elemwise", elementwise), ("misc", misc), ("spatial", spatial),
+                        ("temporal", temporal), ("zonal", zonal), ("reduce", reductions)):
+        if not only or name in only:
+            build(ns)

@@ -7,7 +7,7 @@ from datetime import datetime
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FAMILIES = ["elemwise", "misc", "spatial", "temporal", "zonal"]
+FAMILIES = ["elemwise", "misc", "spatial", "temporal", "zonal", "reduce"]
 
 # ops whose NumPy/libm result cannot be reproduced bit for bit: stated tolerances
 TRANSCENDENTAL = {"power", "exp", "log", "log10"}
@@ -112,6 +112,12 @@ def run_oracle(case, arrays):
         frame, labels = ins[0][0], ins[1][0]
         active = frame != np.finfo("f4").max
         return np.asarray(R._ZONAL[op](frame[active], labels=labels[active], index=args["index"])), None
+    if fam == "reduce":
+        return R.reduce_rasters(ins, op, args["no_data_value"], args["dtype"])
+    if fam == "group_bands":
+        return R.group_by_bands(ins, args["bands"], args["dtype"], tuple(args["shape"]))
+    if fam == "group_time":
+        return R.group_by_time(ins, args["times"], args["dtype"], args["start"], args["stop"])
     raise KeyError(fam)
 
 
@@ -167,6 +173,17 @@ def run_product(case, arrays):
     elif fam == "cumulative":
         kwargs, times = _temporal_kwargs(args)
         res = raster.Cumulative.process(kwargs, {"time": times}, ins[0])
+    elif fam == "reduce":
+        from dask_geomodeling_b200.raster.reduction import reduce_rasters
+
+        res = reduce_rasters(ins, op, args["no_data_value"], args["dtype"])
+    elif fam == "group_bands":
+        res = raster.Group._merge_vals_by_bands(ins, [tuple(b) for b in args["bands"]], np.dtype(args["dtype"]),
+                                                tuple(args["shape"]))
+    elif fam == "group_time":
+        res = raster.Group._merge_vals_by_time(
+            ins, [{"time": t} for t in args["times"]],
+            {"dtype": np.dtype(args["dtype"]), "start": args["start"], "stop": args["stop"]})
     else:
         raise KeyError(fam)
     return np.asarray(res["values"]), res["no_data_value"]
