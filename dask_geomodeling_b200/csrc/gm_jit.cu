@@ -19,8 +19,12 @@
 #include "gm_common.cuh"
 #include "gm_jit.h"
 #include <dlfcn.h>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace gm {
 
@@ -122,18 +126,33 @@ static JitLayout plan_layout(const GmProgram* prog, const int* in_dtype, const i
   return L;
 }
 
+// Constant k[i] of instruction pc.  The constants (sentinels, thresholds, fill values, scalar
+// operands) are NOT baked into the source: they travel in the kernel's parameter block
+// (p.k[pc][i], read through the constant bank like a literal would be), so that the compiled
+// kernel -- and its cache key -- depend on the structure of the program only.  Changing a
+// scalar of a view (a slider on Multiply(x, k), another threshold) reuses the kernel.
+//
+// A program that keeps being launched with the SAME constants on a large raster is compiled a
+// second time with the constants as literals (`bake`): the compiler then folds them (about 8 %
+// fewer instructions on the cfg2 chain).  See jit_launch.
+static thread_local const GmProgram* t_bake = nullptr;   // non-null while generating a baked kernel
+static std::string kref(int pc, int i) {
+  if (t_bake) return hex(t_bake->instr[pc].k[i]);
+  return "p.k[" + num(pc) + "][" + num(i) + "]";
+}
+
 // operand b of instruction `in` as an expression of type uint64_t
-static std::string operand_b(const GmInstr& in) {
+static std::string operand_b(const GmInstr& in, int pc) {
   if (in.src_kind == GM_SRC_REG) return "(uint64_t)r" + num(in.src);
   if (in.src_kind == GM_SRC_INPUT) return "(uint64_t)i" + num(in.src);
-  if (in.src_kind == GM_SRC_IMM) return hex(in.k[0]);
+  if (in.src_kind == GM_SRC_IMM) return kref(pc, 0);
   return "0ULL";
 }
 
-static std::string convert_expr(const std::string& x, int from, int to, bool nanify, uint64_t k, int word) {
+static std::string convert_expr(const std::string& x, int from, int to, bool nanify, const std::string& k, int word) {
   if (from == to || !class_fits(from, word) || !class_fits(to, word)) return x;
   return std::string("cvt<") + class_type(from) + ", " + class_type(to) + ", " + tf(nanify) + ">(" + x +
-         ", " + hex(k) + ")";
+         ", " + k + ")";
 }
 
 static std::string table_args(const GmProgram* prog, int t) {
@@ -149,42 +168,43 @@ static std::string table_args(const GmProgram* prog, int t) {
 
 static std::string emit_instruction(const GmProgram* prog, const GmInstr& in) {
   const int word = prog->word;
+  const int pc = (int)(&in - prog->instr);
   const bool fa = in.flags & GM_F_ND_A, fb = in.flags & GM_F_ND_B;
-  const std::string b = operand_b(in);
+  const std::string b = operand_b(in, pc);
   std::string s;
   switch (in.op) {
     case GM_OP_LOAD:
     case GM_OP_MATB: {
       std::string src = in.src_kind == GM_SRC_REG     ? "r" + num(in.src)
                         : in.src_kind == GM_SRC_INPUT ? "i" + num(in.src)
-                                                      : "(S)" + hex(in.k[0]);
+                                                      : "(S)" + kref(pc, 0);
       const bool nanify = (in.flags & GM_F_NAN) && fb;
-      const std::string v = convert_expr(src, in.cls_b, in.cls_out, nanify, in.k[2], word);
+      const std::string v = convert_expr(src, in.cls_b, in.cls_out, nanify, kref(pc, 2), word);
       s = (in.op == GM_OP_LOAD ? std::string("acc") : "r" + num(in.aux)) + " = " + v + ";";
       break;
     }
     case GM_OP_ST: s = "r" + num(in.aux) + " = acc;"; break;
     case GM_OP_OUT: s = "o" + num(in.aux) + " = acc;"; break;
     case GM_OP_CVT:
-      s = "acc = " + convert_expr("acc", in.cls_a, in.cls_out, (in.flags & GM_F_NAN) && fa, in.k[1], word) + ";";
+      s = "acc = " + convert_expr("acc", in.cls_a, in.cls_out, (in.flags & GM_F_NAN) && fa, kref(pc, 1), word) + ";";
       break;
     case GM_OP_ISDATA:
     case GM_OP_ISNODATA:
       if (class_fits(in.cls_a, word))
         s = std::string("acc = is_data<") + class_type(in.cls_a) + ", " + tf(fa) + ", " +
-            tf(in.op == GM_OP_ISNODATA) + ">(acc, " + hex(in.k[1]) + ");";
+            tf(in.op == GM_OP_ISNODATA) + ">(acc, " + kref(pc, 1) + ");";
       break;
     case GM_OP_CLIP: {
       int mode = (in.flags & GM_F_B_BOOL) ? 1 : (fb ? 2 : 0);
       if (mode == 2 && !class_fits(in.cls_b, word)) mode = 0;
       s = std::string("acc = clip<") + class_type(mode == 2 ? in.cls_b : GM_C_I32) + ", " + num(mode) +
-          ">(acc, " + b + ", " + hex(in.k[1]) + ", " + hex(in.k[2]) + ");";
+          ">(acc, " + b + ", " + kref(pc, 1) + ", " + kref(pc, 2) + ");";
       break;
     }
     case GM_OP_AND: case GM_OP_OR: case GM_OP_XOR: case GM_OP_NOT: {
       std::string y = b;
       if (in.op == GM_OP_NOT) y = "0ULL";
-      else if (in.src_kind == GM_SRC_IMM) y = in.k[0] != 0 ? "1ULL" : "0ULL";
+      else if (in.src_kind == GM_SRC_IMM) y = "(uint64_t)(" + kref(pc, 0) + " != 0)";
       s = "acc = logic<" + num(in.op) + ">(acc, " + y + ");";
       break;
     }
@@ -195,50 +215,50 @@ static std::string emit_instruction(const GmProgram* prog, const GmInstr& in) {
       s = std::string("acc = reclass<") + A + ", " + tf(g.kind == GM_TABLE_DENSE) + ", " +
           tf(in.flags & GM_F_ND_T) + ", " + tf(in.flags & GM_F_SELECT) + ", " + tf(fa) + ", " +
           tf(in.cls_out == GM_C_F64) + ">(acc, " + table_args(prog, in.aux) + ", " + num(g.n) + ", " +
-          num(g.base) + "LL, " + hex(in.k[1]) + ", " + hex(in.k[3]) + ");";
+          num(g.base) + "LL, " + kref(pc, 1) + ", " + kref(pc, 3) + ");";
       break;
     }
     case GM_OP_OVERLAY:
       if (class_fits(in.cls, word) && class_fits(in.cls_out, word))
         s = std::string("acc = overlay<") + class_type(in.cls) + ", " + class_type(in.cls_out) + ", " +
             tf(in.flags & GM_F_ND_T) + ", " + tf(in.flags & GM_F_CLOSE) + ", " + tf(in.flags & GM_F_ND_FINITE) +
-            ", " + num((int)in.aux) + ">(acc, " + b + ", " + hex(in.k[2]) + ", " + hex(in.k[4]) + ");";
+            ", " + num((int)in.aux) + ">(acc, " + b + ", " + kref(pc, 2) + ", " + kref(pc, 4) + ");";
       break;
     case GM_OP_EXP: case GM_OP_LOG: case GM_OP_LOG10:
       if (class_fits(in.cls, word) && class_is_float(in.cls) && in.cls == in.cls_a)
         s = "acc = transcend<" + num(in.op) + ", " + class_type(in.cls) + ", " + tf(fa) + ">(acc, " +
-            hex(in.k[1]) + ", " + hex(in.k[3]) + ");";
+            kref(pc, 1) + ", " + kref(pc, 3) + ");";
       break;
     case GM_OP_MASK:
       if (class_fits(in.cls, word) && class_fits(in.cls_a, word))
         s = std::string("acc = mask<") + class_type(in.cls) + ", " + class_type(in.cls_a) + ", " +
             tf(in.flags & GM_F_ND_T) + ", " + tf(in.flags & GM_F_CLOSE) + ", " + tf(in.flags & GM_F_ND_FINITE) +
-            ">(acc, " + hex(in.k[0]) + ", " + hex(in.k[1]) + ", " + hex(in.k[3]) + ", " + hex(in.k[4]) + ");";
+            ">(acc, " + kref(pc, 0) + ", " + kref(pc, 1) + ", " + kref(pc, 3) + ", " + kref(pc, 4) + ");";
       break;
     case GM_OP_MASKBELOW:
       if (class_fits(in.cls, word) && class_fits(in.cls_a, word))
         s = std::string("acc = mask_below<") + class_type(in.cls) + ", " + class_type(in.cls_a) + ">(acc, " +
-            hex(in.k[0]) + ", " + hex(in.k[5]) + ");";
+            kref(pc, 0) + ", " + kref(pc, 5) + ");";
       break;
     case GM_OP_STEP:
       if (class_fits(in.cls, word) && class_fits(in.cls_a, word))
         s = std::string("acc = step<") + class_type(in.cls) + ", " + class_type(in.cls_a) + ", " + tf(fa) +
-            ">(acc, " + hex(in.k[0]) + ", " + hex(in.k[1]) + ", " + hex(in.k[2]) + ", " + hex(in.k[3]) + ", " +
-            hex(in.k[4]) + ");";
+            ">(acc, " + kref(pc, 0) + ", " + kref(pc, 1) + ", " + kref(pc, 2) + ", " + kref(pc, 3) + ", " +
+            kref(pc, 4) + ");";
       break;
     case GM_OP_CLASSIFY:
       if (class_fits(in.cls, word) && class_fits(in.cls_a, word))
         s = std::string("acc = classify<") + class_type(in.cls) + ", " + class_type(in.cls_a) + ", " + tf(fa) +
             ", " + tf(in.flags & GM_F_RIGHT) + ">(acc, t" + num(in.aux) + "k, " + num(prog->tables[in.aux].n) +
-            ", " + hex(in.k[1]) + ", " + hex(in.k[3]) + ");";
+            ", " + kref(pc, 1) + ", " + kref(pc, 3) + ");";
       break;
     default: {  // binary arithmetic / comparison
       if (!class_fits(in.cls, word)) break;
       const bool imm = in.src_kind == GM_SRC_IMM;
       const bool is_cmp = in.op >= GM_OP_EQ && in.op <= GM_OP_LE;
       s = std::string("acc = ") + (is_cmp ? "compare<" : "math<") + num(in.op) + ", " + class_type(in.cls) +
-          ", " + tf(fa) + ", " + tf(fb && !imm) + ">(acc, " + b + ", " + hex(in.k[1]) + ", " + hex(in.k[2]) +
-          ", " + hex(in.k[3]) + ");";
+          ", " + tf(fa) + ", " + tf(fb && !imm) + ">(acc, " + b + ", " + kref(pc, 1) + ", " + kref(pc, 2) +
+          ", " + kref(pc, 3) + ");";
       break;
     }
   }
@@ -277,7 +297,8 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
   src += kPrelude;
   src += "\nstruct Params { const void* in[" + num(GM_MAX_INPUTS) + "]; void* out[" + num(GM_MAX_OUTPUTS) +
          "]; long long n; const int64_t* tk[" + num(GM_MAX_TABLES) + "]; const uint64_t* tv[" +
-         num(GM_MAX_TABLES) + "]; const uint8_t* th[" + num(GM_MAX_TABLES) + "]; };\n";
+         num(GM_MAX_TABLES) + "]; const uint8_t* th[" + num(GM_MAX_TABLES) + "]; unsigned long long k[" +
+         num(GM_MAX_INSTR) + "][6]; };\n";
   emit_table_data(src, prog, L);
 
   // Baked tables are file-scope __shared__ arrays (compile-time addresses); the others
@@ -298,8 +319,8 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
   }
 
   // ---- one pixel ---------------------------------------------------------------------
-  src += "GM_DEV void pixel(";
-  bool first = true;
+  src += "GM_DEV void pixel(const Params& p";
+  bool first = false;
   for (int i = 0; i < prog->n_inputs; ++i) { src += std::string(first ? "" : ", ") + "S i" + num(i); first = false; }
   for (int i = 0; i < prog->n_outputs; ++i) { src += std::string(first ? "" : ", ") + "S& o" + num(i); first = false; }
   src += tab_params + ") {\n  S acc = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0;\n";
@@ -311,16 +332,16 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
 
   // ---- one group of V pixels held in 32-bit words ---------------------------------------
   auto words = [&](int dt) { return std::max(1, V * dtype_size(dt) / 4); };
-  src += "GM_DEV void group(";
-  first = true;
+  src += "GM_DEV void group(const Params& p";
+  first = false;
   for (int i = 0; i < prog->n_inputs; ++i) { src += std::string(first ? "" : ", ") + "const uint32_t* a" + num(i); first = false; }
   for (int i = 0; i < prog->n_outputs; ++i) { src += std::string(first ? "" : ", ") + "uint32_t* w" + num(i); first = false; }
   src += tab_params + ") {\n";
   for (int j = 0; j < V; ++j) {
     src += "  {";
     for (int i = 0; i < prog->n_outputs; ++i) src += " S o" + num(i) + ";";
-    src += " pixel(";
-    first = true;
+    src += " pixel(p";
+    first = false;
     for (int i = 0; i < prog->n_inputs; ++i) {
       src += std::string(first ? "" : ", ") + "element<" + storage_type(in_dtype[i]) + ", " + num(j) + ">(a" + num(i) + ")";
       first = false;
@@ -372,8 +393,8 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
   src += "    #pragma unroll\n    for (int u = 0; u < " + num(U) + "; ++u) {\n";
   for (int i = 0; i < prog->n_outputs; ++i)
     src += "      uint32_t w" + num(i) + "[" + num(words(out_dtype[i])) + "];\n";
-  src += "      group(";
-  first = true;
+  src += "      group(p";
+  first = false;
   for (int i = 0; i < prog->n_inputs; ++i) { src += std::string(first ? "" : ", ") + "a" + num(i) + "[u]"; first = false; }
   for (int i = 0; i < prog->n_outputs; ++i) { src += std::string(first ? "" : ", ") + "w" + num(i); first = false; }
   src += tab_args + ");\n";
@@ -391,8 +412,8 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
   }
   for (int i = 0; i < prog->n_outputs; ++i)
     src += "    uint32_t w" + num(i) + "[" + num(words(out_dtype[i])) + "];\n";
-  src += "    group(";
-  first = true;
+  src += "    group(p";
+  first = false;
   for (int i = 0; i < prog->n_inputs; ++i) { src += std::string(first ? "" : ", ") + "a" + num(i); first = false; }
   for (int i = 0; i < prog->n_outputs; ++i) { src += std::string(first ? "" : ", ") + "w" + num(i); first = false; }
   src += tab_args + ");\n";
@@ -404,8 +425,8 @@ static std::string generate(const GmProgram* prog, const int* in_dtype, const in
   // ragged tail: fewer than V pixels, one thread each
   src += "  if (blockIdx.x == 0) {\n    const long long px = groups * " + num(V) + " + tid;\n    if (px < p.n) {\n";
   for (int i = 0; i < prog->n_outputs; ++i) src += "      S o" + num(i) + ";\n";
-  src += "      pixel(";
-  first = true;
+  src += "      pixel(p";
+  first = false;
   for (int i = 0; i < prog->n_inputs; ++i) {
     const std::string st = storage_type(in_dtype[i]);
     src += std::string(first ? "" : ", ") + "slot_of<" + st + ">(((const " + st + "*)in" + num(i) + ")[px])";
@@ -429,9 +450,19 @@ struct JitKernel {
   cudaKernel_t kernel = nullptr;
   JitLayout layout;
   int blocks_per_sm = 8;
+  ~JitKernel() { if (library) cudaLibraryUnload(library); }
 };
 
-static std::unordered_map<std::string, JitKernel*> g_kernels;
+// Kernels in memory: at most kMaxKernels, the oldest is unloaded first (a launch in flight keeps
+// its kernel alive through the shared pointer).  Compiled cubins are also kept on disk
+// (GM_JIT_CACHE=<dir>, default ~/.cache/dask_geomodeling_b200/jit, "off" disables), keyed by a
+// hash of the generated source, so that a new process does not pay the NVRTC compile again.
+static const size_t kMaxKernels = 256;
+static std::unordered_map<std::string, std::shared_ptr<JitKernel>> g_kernels;
+static std::deque<std::string> g_kernel_order;
+static std::unordered_map<std::string, std::string> g_last_constants;   // structure key -> constants of its last launch
+static const int64_t kBakeFromPixels = 1 << 22;
+static std::atomic<int64_t> g_disk_hits{0};
 static std::atomic<int64_t> g_compiles{0};
 static std::string g_last_source;
 
@@ -441,7 +472,11 @@ static std::string program_key(const GmProgram* prog, const int* in_dtype, const
   auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
   put(&prog->word, 4); put(&prog->n_instr, 4); put(&prog->n_inputs, 4); put(&prog->n_outputs, 4);
   put(&prog->n_tables, 4);
-  put(prog->instr, sizeof(GmInstr) * prog->n_instr);
+  for (int pc = 0; pc < prog->n_instr; ++pc) {     // the structure of an instruction, not its constants
+    GmInstr shape = prog->instr[pc];
+    memset(shape.k, 0, sizeof(shape.k));
+    put(&shape, sizeof(GmInstr));
+  }
   put(in_dtype, sizeof(int) * prog->n_inputs);
   put(out_dtype, sizeof(int) * prog->n_outputs);
   for (int t = 0; t < prog->n_tables; ++t) {
@@ -488,9 +523,73 @@ static int nvrtc_compile(const std::string& source, std::vector<char>& cubin) {
   return 0;
 }
 
+static std::string cache_dir() {
+  const char* env = getenv("GM_JIT_CACHE");
+  if (env && (!strcmp(env, "off") || !strcmp(env, "0"))) return "";
+  if (env && *env) return env;
+  const char* xdg = getenv("XDG_CACHE_HOME");
+  const char* home = getenv("HOME");
+  if (xdg && *xdg) return std::string(xdg) + "/dask_geomodeling_b200/jit";
+  if (home && *home) return std::string(home) + "/.cache/dask_geomodeling_b200/jit";
+  return "";
+}
+
+static std::string source_hash(const std::string& source) {
+  // two independent 64-bit FNV-1a style hashes of the whole source (prelude included: a new
+  // library version never picks up an old cubin)
+  uint64_t a = 1469598103934665603ULL, b = 0x9E3779B97F4A7C15ULL;
+  for (unsigned char c : source) {
+    a = (a ^ c) * 1099511628211ULL;
+    b = (b + c) * 0xD6E8FEB86659FD93ULL;
+    b ^= b >> 29;
+  }
+  char buf[40];
+  snprintf(buf, sizeof(buf), "%016llx%016llx", (unsigned long long)a, (unsigned long long)b);
+  return buf;
+}
+
+static void make_dirs(const std::string& path) {
+  for (size_t i = 1; i <= path.size(); ++i)
+    if (i == path.size() || path[i] == '/') mkdir(path.substr(0, i).c_str(), 0755);
+}
+
+static bool read_cached_cubin(const std::string& path, std::vector<char>& cubin) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) {
+    cubin.resize((size_t)n);
+    ok = fread(cubin.data(), 1, (size_t)n, f) == (size_t)n;
+  }
+  fclose(f);
+  return ok;
+}
+
+static void write_cached_cubin(const std::string& dir, const std::string& path, const std::vector<char>& cubin) {
+  make_dirs(dir);
+  const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+  fclose(f);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+}
+
 static int compile_kernel(const std::string& source, JitKernel* k) {
   std::vector<char> cubin;
-  if (nvrtc_compile(source, cubin)) return 1;
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? "" : dir + "/" + source_hash(source) + ".cubin";
+  if (!path.empty() && read_cached_cubin(path, cubin)) {
+    g_disk_hits.fetch_add(1);
+  } else {
+    cubin.clear();
+    if (nvrtc_compile(source, cubin)) return 1;
+    g_compiles.fetch_add(1);
+    if (!path.empty()) write_cached_cubin(dir, path, cubin);
+  }
   cudaError_t e = cudaLibraryLoadData(&k->library, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
   if (e != cudaSuccess) return fail(std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
   e = cudaLibraryGetKernel(&k->kernel, k->library, "gm_fused");
@@ -501,7 +600,6 @@ static int compile_kernel(const std::string& source, JitKernel* k) {
     k->blocks_per_sm = per_sm;
   else
     cudaGetLastError();
-  g_compiles.fetch_add(1);
   return 0;
 }
 
@@ -512,6 +610,7 @@ struct JitParams {
   const int64_t* tk[GM_MAX_TABLES];
   const uint64_t* tv[GM_MAX_TABLES];
   const uint8_t* th[GM_MAX_TABLES];
+  unsigned long long k[GM_MAX_INSTR][6];
 };
 
 int jit_tables_baked(const GmProgram* prog) {
@@ -525,20 +624,44 @@ int jit_launch(const GmProgram* prog, const void* const* in, const int* in_dtype
                const void* const* thit, int64_t n, cudaStream_t s) {
   const JitLayout L = plan_layout(prog, in_dtype, out_dtype);
   const std::string key = program_key(prog, in_dtype, out_dtype, L);
-  JitKernel* k = nullptr;
+  // the constants of this launch (they select the baked variant, if there is one)
+  std::string constants;
+  for (int pc = 0; pc < prog->n_instr; ++pc) constants.append((const char*)prog->instr[pc].k, sizeof(prog->instr[pc].k));
+  const std::string baked_key = key + '#' + constants;
+  std::shared_ptr<JitKernel> k;
   {
     std::lock_guard<std::mutex> lock(g_jit_mutex);
-    auto it = g_kernels.find(key);
-    if (it != g_kernels.end()) k = it->second;
-    else {
+    auto build = [&](const std::string& as, bool bake) -> std::shared_ptr<JitKernel> {
+      t_bake = bake ? prog : nullptr;
       std::string source = generate(prog, in_dtype, out_dtype, L);
-      JitKernel* fresh = new JitKernel();
-      fresh->key = key;
+      t_bake = nullptr;
+      std::shared_ptr<JitKernel> fresh = std::make_shared<JitKernel>();
+      fresh->key = as;
       fresh->layout = L;
       g_last_source = source;
-      if (compile_kernel(source, fresh)) { delete fresh; return 1; }
-      g_kernels[key] = fresh;
-      k = fresh;
+      if (compile_kernel(source, fresh.get())) return nullptr;
+      if (g_kernels.size() >= kMaxKernels && !g_kernel_order.empty()) {
+        g_kernels.erase(g_kernel_order.front());     // unloaded when its last launch has returned
+        g_kernel_order.pop_front();
+      }
+      g_kernels[as] = fresh;
+      g_kernel_order.push_back(as);
+      return fresh;
+    };
+    auto baked = g_kernels.find(baked_key);
+    if (baked != g_kernels.end()) {
+      k = baked->second;
+    } else {
+      auto it = g_kernels.find(key);
+      k = it != g_kernels.end() ? it->second : build(key, false);
+      if (!k) return 1;
+      // the same constants again on a large raster: from now on the literal-specialised kernel
+      std::string& last = g_last_constants[key];
+      if (n >= kBakeFromPixels && last == constants && !getenv("GM_JIT_NO_BAKE")) {
+        std::shared_ptr<JitKernel> special = build(baked_key, true);
+        if (special) k = special;
+      }
+      last = constants;
     }
   }
   JitParams p;
@@ -546,6 +669,8 @@ int jit_launch(const GmProgram* prog, const void* const* in, const int* in_dtype
   for (int i = 0; i < prog->n_inputs; ++i) p.in[i] = in[i];
   for (int i = 0; i < prog->n_outputs; ++i) p.out[i] = out[i];
   p.n = n;
+  for (int pc = 0; pc < prog->n_instr; ++pc)
+    for (int i = 0; i < 6; ++i) p.k[pc][i] = prog->instr[pc].k[i];
   for (int t = 0; t < prog->n_tables; ++t) {
     p.tk[t] = (const int64_t*)tkeys[t];
     p.tv[t] = (const uint64_t*)tvals[t];
