@@ -273,11 +273,10 @@ class AggregateRaster(GeometryBlock):
             agg_geometries = list(column.to_crs(agg_srs))
         elif utils.same_projection(req_srs, agg_srs):
             agg_geometries = column.values
-            prepared = features.attrs.get("polygon_soup")
-            prepared = prepared.value if prepared is not None else None
-            if (prepared is not None and len(prepared[1]) == len(features) and len(features)
-                    and agg_geometries[0] is prepared[2][prepared[1][0]]
-                    and agg_geometries[-1] is prepared[2][prepared[1][-1]]):
+            from .sources import prepared_soup_of
+
+            prepared = prepared_soup_of(features)
+            if prepared is not None:
                 # the frame still holds the source's geometries: reuse their CSR form
                 # (kept resident in HBM when it is the source's full set)
                 full, positions, _ = prepared

@@ -44,6 +44,25 @@ class Literal(object):
         return self
 
 
+def prepared_soup_of(features):
+    """The CSR form a MemoryGeometrySource attached to ``features`` -- (full soup, positions of the
+    frame's rows in it, the source's geometry objects) -- if the frame still holds exactly those
+    geometries in that order, else None.  ``DataFrame.attrs`` travels through most pandas
+    operations, so a block in between may have dropped, reordered or replaced rows: the length and
+    the identity of up to 64 evenly spaced rows (first and last included) are checked."""
+    prepared = features.attrs.get("polygon_soup") if "geometry" in features else None
+    prepared = getattr(prepared, "value", None)
+    n = len(features)
+    if prepared is None or n == 0 or len(prepared[1]) != n:
+        return None
+    full, positions, geometries = prepared
+    column = features["geometry"].values
+    for k in np.unique(np.linspace(0, n - 1, min(n, 64)).astype(np.int64)):
+        if column[k] is not geometries[positions[k]]:
+            return None
+    return prepared
+
+
 def _unwrap(x):
     return x.value if isinstance(x, Literal) else x
 

@@ -25,7 +25,7 @@ calls themselves always go through libgeokernels.so.
 import numpy as np
 
 __all__ = [
-    "stripe_rows", "stripe_request", "get_data_striped", "exchange_halo", "pad_columns",
+    "stripe_rows", "stripe_request", "get_data_striped", "get_data_tiled", "exchange_halo", "pad_columns",
     "stencil_striped", "refresh_halo", "stencil_haloed", "smooth_halo", "allreduce_partials", "finalize_partials", "zonal_striped",
     "exchange_segments", "segment_order_statistic",
 ]
@@ -97,18 +97,65 @@ def get_data_striped(view, group=None, gather=False, **request):
     dist = _dist()
     parts = [None] * world
     dist.all_gather_object(parts, local, group=group)
-    parts = [p for p in parts if p is not None]
-    if not parts:
+    filled = [p for p in parts if p is not None]
+    if not filled:
         return None, (0, request["height"])
-    if "values" not in parts[0]:
-        return parts[0], (0, request["height"])
-    values = np.concatenate([p["values"] for p in parts], axis=1)
-    return {"values": values, "no_data_value": parts[0]["no_data_value"]}, (0, request["height"])
+    if "values" not in filled[0]:
+        return filled[0], (0, request["height"])
+    # a stripe without data (None) becomes 'no data' rows, so that the result keeps its height
+    first = filled[0]
+    bands, _, width = first["values"].shape
+    stitched = []
+    for part, (a, b) in zip(parts, stripe_rows(request["height"], world)):
+        if part is not None:
+            stitched.append(np.asarray(part["values"]))
+        elif b > a:
+            stitched.append(np.full((bands, b - a, width), first["no_data_value"], dtype=first["values"].dtype))
+    values = np.concatenate(stitched, axis=1)
+    return {"values": values, "no_data_value": first["no_data_value"]}, (0, request["height"])
+
+
+def get_data_tiled(view, tile_size, group=None, **request):
+    """``RasterTiler`` (raster/parallelize.py) as a multi-GPU scheduler: the request is cut in
+    tiles of at most ``tile_size`` cells exactly as the block does, tile i is evaluated by rank
+    i mod world (each rank on its own GPU), the tiles are all-gathered and every rank stitches
+    the full result.  Suits views whose tiles are independent (element-wise chains, stencils
+    whose request margin equals their reach); returns what ``view.get_data(**request)`` returns."""
+    from .raster.parallelize import RasterTiler
+
+    rank, world = _world(group)
+    tiler = RasterTiler(view, tile_size)
+    plan = tiler.get_sources_and_requests(**request)
+    kwargs, tiles = plan[0][0], [r for _, r in plan[1:]]
+    if kwargs is None:                 # time / meta / point requests are not tiled
+        return view.get_data(**request)
+    mine = {i: view.get_data(**tiles[i]) for i in range(rank, len(tiles), world)}
+    if world > 1:
+        gathered = [None] * world
+        _dist().all_gather_object(gathered, mine, group=group)
+        mine = {}
+        for part in gathered:
+            mine.update(part)
+    return RasterTiler.process(kwargs, *[mine[i] for i in range(len(tiles))])
 
 
 # ---------------------------------------------------------------------------
 # stencils: halo exchange
 # ---------------------------------------------------------------------------
+
+
+def _all_stripes_hold(rows, halo, group):
+    """Every rank learns the thinnest stripe: a stripe thinner than the halo cannot serve its
+    neighbour, and ALL ranks must refuse together (a rank that raised alone would leave its
+    neighbours waiting in the grouped send/recv)."""
+    import torch
+
+    dist = _dist()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    thinnest = torch.tensor([int(rows)], dtype=torch.int64, device=dev)
+    dist.all_reduce(thinnest, op=dist.ReduceOp.MIN, group=group)
+    if int(thinnest[0]) < halo:
+        raise ValueError("a stripe of {} rows is thinner than the halo of {} rows".format(int(thinnest[0]), halo))
 
 
 def exchange_halo(local, halo, fill, group=None):
@@ -123,8 +170,7 @@ def exchange_halo(local, halo, fill, group=None):
     out[:, halo:halo + rows] = local
     if halo == 0 or world == 1:
         return out
-    if rows < halo:
-        raise ValueError("stripe of {} rows is thinner than the halo of {} rows".format(rows, halo))
+    _all_stripes_hold(rows, halo, group)
     dist = _dist()
     # gloo moves host memory: CUDA stripes are staged through the CPU (one-GPU tests);
     # under NCCL the halos go GPU to GPU over NVLink
@@ -163,8 +209,12 @@ def refresh_halo(haloed, halo_rows, halo_cols=0, group=None):
         return haloed
     dist = _dist()
     rows = haloed.shape[1] - 2 * halo_rows
-    if rows < halo_rows:
-        raise ValueError("stripe of {} rows is thinner than the halo of {} rows".format(rows, halo_rows))
+    if not getattr(haloed, "_stripes_checked", False):     # once per stored stripe, not per step
+        _all_stripes_hold(rows, halo_rows, group)
+        try:
+            haloed._stripes_checked = True
+        except AttributeError:
+            pass
     staged = haloed.is_cuda and dist.get_backend(group) != "nccl"
     edge = (lambda t: t.cpu()) if staged else (lambda t: t.contiguous())
     ops, landing = [], []

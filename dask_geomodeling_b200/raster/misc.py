@@ -350,14 +350,13 @@ class Rasterize(_NonTemporalRaster):
             return {"values": empty, "no_data_value": no_data_value}
 
         # the geometry source's CSR form of these geometries, if the frame still carries it
+        from ..geometry.sources import prepared_soup_of
+
         soup = None
-        prepared = features.attrs.get("polygon_soup") if "geometry" in features else None
-        prepared = getattr(prepared, "value", None)
-        if prepared is not None and len(prepared[1]) == len(features) and len(features):
-            column = features["geometry"].values
-            if column[0] is prepared[2][prepared[1][0]] and column[-1] is prepared[2][prepared[1][-1]]:
-                full, positions, _ = prepared
-                soup = full if len(positions) == full.n_polygons else full.subset(positions)
+        prepared = prepared_soup_of(features)
+        if prepared is not None:
+            full, positions, _ = prepared
+            soup = full if len(positions) == full.n_polygons else full.subset(positions)
         burned = utils.rasterize_geoseries(
             geoseries=features["geometry"] if "geometry" in features else None,
             values=values,

@@ -7,6 +7,7 @@ import pytest
 from dask_geomodeling_b200 import _native, raster, workloads
 from dask_geomodeling_b200.core import fusion
 from dask_geomodeling_b200._compat import config
+from oracle import raster as R
 from oracle import workloads as oracle_workloads
 
 pytestmark = pytest.mark.gpu
@@ -129,18 +130,19 @@ def test_raster_tiler_equals_untiled(tile_size):
     view = workloads.cfg1_view(a, b)
     request = workloads.request(size, size)
     request.update(bbox=(10, 20, 190, 170), width=180, height=150)
-    expected = view.get_data(**request)
+    # the oracle on the requested window: rows 200 - 170 .. 200 - 20, columns 10 .. 190
+    expected, expected_nodata = oracle_workloads.cfg1(a[:, 30:180, 10:190], b[:, 30:180, 10:190])
     tiled = raster.RasterTiler(view, tile_size)
     got = tiled.get_data(**request)
-    assert got["values"].dtype == expected["values"].dtype
-    np.testing.assert_array_equal(got["values"], expected["values"])
-    assert got["no_data_value"] == expected["no_data_value"]
+    assert got["values"].dtype == expected.dtype
+    np.testing.assert_array_equal(got["values"], expected)
+    assert got["no_data_value"] == expected_nodata
     assert tiled.get_data(**dict(request, mode="meta")) == view.get_data(**dict(request, mode="meta"))
     # a stencil whose request margin equals its reach tiles exactly as well (Smooth does not:
     # its Gaussian reaches beyond the margin it requests, in the reference too)
     stencil = raster.MovingMax(workloads.source(a, workloads.F32_MAX), 7)
-    plain = stencil.get_data(**request)
-    np.testing.assert_array_equal(raster.RasterTiler(stencil, [64, 50]).get_data(**request)["values"], plain["values"])
+    expected, _ = R.moving_max(a[:, 27:183, 7:193], workloads.F32_MAX, 7)
+    np.testing.assert_array_equal(raster.RasterTiler(stencil, [64, 50]).get_data(**request)["values"], expected)
 
 
 def test_device_cache_serves_later_requests_from_hbm():

@@ -92,6 +92,83 @@ def test_exchange_halo_three_ranks():
     spawn(_halo_worker, 3, world=3)
 
 
+def _thin_stripe_worker(rank, world):
+    import torch
+
+    # 7 rows over 3 ranks: stripes of 3, 2, 2 rows; a halo of 3 rows fits only the first one.
+    # EVERY rank must raise (a rank raising alone would leave the others in the send/recv)
+    r0, r1 = parallel.stripe_rows(7, world)[rank]
+    local = torch.zeros((1, r1 - r0, 4))
+    with pytest.raises(ValueError, match="thinner than the halo"):
+        parallel.exchange_halo(local, 3, -1.0)
+    stored = torch.zeros((1, r1 - r0 + 6, 4))
+    with pytest.raises(ValueError, match="thinner than the halo"):
+        parallel.refresh_halo(stored, 3)
+    got = parallel.exchange_halo(local, 2, -1.0)          # 2 rows fit every stripe
+    assert got.shape == (1, r1 - r0 + 4, 4)
+
+
+def test_thin_stripes_fail_on_every_rank():
+    spawn(_thin_stripe_worker, world=3)
+
+
+class _HalfEmptyView(object):
+    """get_data answers None for requests in the southern half (y < 5), values elsewhere."""
+
+    def get_data(self, **request):
+        x1, y1, x2, y2 = request["bbox"]
+        if y2 <= 5:
+            return None
+        return {"values": np.full((2, request["height"], request["width"]), 3, dtype="u1"), "no_data_value": 255}
+
+
+def _gather_worker(rank, world):
+    request = dict(mode="vals", bbox=(0, 0, 4, 10), width=4, height=10, projection="EPSG:28992")
+    full, rows = parallel.get_data_striped(_HalfEmptyView(), gather=True, **request)
+    assert rows == (0, 10) and full["values"].shape == (2, 10, 4)      # the height is kept
+    assert (full["values"][:, :5] == 3).all() and (full["values"][:, 5:] == 255).all()
+
+
+def test_gather_fills_stripes_without_data():
+    spawn(_gather_worker)
+
+
+class _CoordinateView(object):
+    """A view whose cell value is a function of the cell's position: 100 * row + column of a
+    40 x 30 grid with unit cells (no data outside x < 25)."""
+
+    dtype = np.dtype("i4")
+    fillvalue = np.iinfo("i4").max
+
+    def get_data(self, **request):
+        if request["mode"] != "vals":
+            return {request["mode"]: ["whole"]}
+        x1, y1, x2, y2 = request["bbox"]
+        cols = np.arange(int(x1), int(x2))
+        rows = np.arange(30 - int(y2), 30 - int(y1))
+        values = (100 * rows[:, None] + cols[None, :]).astype("i4")
+        values[:, cols >= 25] = self.fillvalue
+        return {"values": values[np.newaxis], "no_data_value": self.fillvalue}
+
+
+def _tiler_worker(rank, world):
+    from dask_geomodeling_b200.raster.base import RasterBlock
+
+    view = type("V", (_CoordinateView, RasterBlock), {"__init__": lambda self: None, "token": "v"})()
+    request = dict(mode="vals", bbox=(2, 3, 40, 28), width=38, height=25, projection="EPSG:28992")
+    expected = _CoordinateView().get_data(**request)
+    for tile_size in (7, [16, 9], 100):
+        got = parallel.get_data_tiled(view, tile_size, **request)
+        np.testing.assert_array_equal(got["values"], expected["values"])
+        assert got["no_data_value"] == expected["no_data_value"]
+    assert parallel.get_data_tiled(view, 8, **dict(request, mode="meta")) == {"meta": ["whole"]}
+
+
+def test_raster_tiler_over_ranks():
+    spawn(_tiler_worker)
+    spawn(_tiler_worker, world=3)
+
+
 # ---- zonal partials ---------------------------------------------------------------------------
 
 

@@ -64,6 +64,26 @@ def test_fused_chain_in_stripes():
     spawn(_chain_worker)
 
 
+def _tiler_worker(rank, world):
+    from dask_geomodeling_b200 import parallel, workloads
+    from oracle import workloads as oracle_workloads
+
+    size = 300
+    ints, floats = workloads.cfg2_arrays(size, chunk=128)
+    isdata, step = workloads.cfg2_views(ints, floats)
+    (e_isdata, _), (e_step, _) = oracle_workloads.cfg2(ints, floats, workloads.CFG2_PAIRS)
+    request = workloads.request(size, size)
+    got = parallel.get_data_tiled(step, [128, 77], **request)       # 3 x 4 tiles over the ranks
+    np.testing.assert_array_equal(got["values"], e_step)
+    got = parallel.get_data_tiled(isdata, 64, **request)
+    np.testing.assert_array_equal(got["values"], e_isdata)
+
+
+def test_raster_tiler_over_ranks():
+    # RasterTiler as the multi-GPU scheduler, against the oracle
+    spawn(_tiler_worker)
+
+
 def _stencil_worker(rank, world):
     import torch
 
@@ -132,16 +152,24 @@ def _zonal_worker(rank, world, on_device=False):
     local = np.ascontiguousarray(frame[:, r0:r1])
     if on_device:   # stripes resident in HBM: partials and boundary rows never touch the host
         local = torch.from_numpy(local).cuda()
+    # the oracle: GDAL-rule labels per polygon + scipy labelled statistics / measurements.percentile
+    from oracle import polyfill
+    from oracle import raster as R
+
+    rings = [[np.asarray(p.exterior.coords)] for p in polys]
+    label_sets = []
+    for i, ring in enumerate(rings):
+        labels = polyfill.burn_index([ring], bbox, h, w)
+        label_sets.append((np.where(labels == 0, i, np.iinfo(np.int32).max).astype(np.int32), [i]))
     for stat, q in (("mean", None), ("max", None), ("count", None), ("sum", None), ("min", None),
                     ("median", None), ("percentile", 90.0), ("percentile", 12.5)):
-        expected, expected_no_cells = geometry.aggregate.aggregate_polygons(
-            polys, frame, nodata, bbox, workloads.PROJECTION, None, stat, q)
+        expected, expected_no_cells = R.zonal_from_labels(frame[0], nodata, label_sets, len(polys), stat, q)
         got, no_cells = parallel.zonal_striped(polys, local, nodata, bbox, h, (r0, r1), stat, q)
         assert got.dtype == np.float32 and sorted(no_cells) == sorted(expected_no_cells)
         if stat in ("sum", "mean"):
-            np.testing.assert_allclose(got, expected[0], rtol=1e-6, equal_nan=True)
+            np.testing.assert_allclose(got, expected, rtol=1e-6, equal_nan=True)
         else:
-            np.testing.assert_array_equal(got, expected[0])
+            np.testing.assert_array_equal(got, expected)
 
 
 def _zonal_worker_device(rank, world):
