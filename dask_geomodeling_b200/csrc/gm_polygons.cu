@@ -355,38 +355,6 @@ __device__ __forceinline__ void scan_polygon(const PolyDev& P, int64_t p, int* b
   }
 }
 
-// ---- rasterise ---------------------------------------------------------------------------
-struct LabelVisitor {
-  int* idx; int width; int label;
-  __device__ __forceinline__ void span(int y, int x0, int x1) {
-    int* row = idx + (int64_t)y * width;
-    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) atomicMax(row + x, label);
-  }
-  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int*, int) { span(y, x0, x1); }
-};
-
-__global__ void __launch_bounds__(PG_THREADS)
-rasterize_kernel(const PolyDev P, int* __restrict__ idx) {
-  extern __shared__ int pg_smem[];
-  const int warp = threadIdx.x >> 5;
-  int* buf = pg_smem + warp * P.cap;
-  int* hbuf = pg_smem + PG_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
-  for (int64_t p = blockIdx.x; p < P.n_polygons; p += gridDim.x) {
-    LabelVisitor vis{idx, P.width, (int)p};
-    scan_polygon(P, p, buf, hbuf, vis);
-  }
-}
-
-template <typename T>
-__global__ void resolve_labels_kernel(const int* __restrict__ idx, const T* __restrict__ burn,
-                                      T nodata, T* __restrict__ dst, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int l = idx[i];
-    dst[i] = l < 0 ? nodata : burn[l];
-  }
-}
-
 // ---- zonal statistics ------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long order_f64(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -2117,6 +2085,164 @@ zonal_select_final_kernel(int stat, double q, int64_t p_begin, int64_t p_end, in
   }
 }
 
+// ---- rasterise ---------------------------------------------------------------------------
+// Tiles instead of atomics on the output: the raster is cut in tiles of RT_ROWS x RT_COLS cells,
+// every polygon is listed with the tiles its bounding box touches (count, scan, fill), and ONE
+// block per tile scan-converts its polygons into a tile of polygon indices in SHARED memory --
+// atomicMax on shared memory, so that the LAST feature wins as in GDAL whatever order the warps
+// work in -- and then writes the tile's burn values once, coalesced.  The output is written
+// exactly once (its itemsize per cell), there is no index raster in HBM and no second pass.
+constexpr int RT_ROWS = 16, RT_COLS = 256, RT_WARPS = 4;
+
+// columns a polygon can touch (clamped to the raster; empty: lo > hi)
+__global__ void poly_cols_kernel(const double* __restrict__ px, const int64_t* __restrict__ ring_offsets,
+                                 const int64_t* __restrict__ poly_offsets, int64_t n_polygons, int width,
+                                 int* __restrict__ minx, int* __restrict__ maxx) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_polygons) return;
+  const int64_t v0 = ring_offsets[poly_offsets[p]], v1 = ring_offsets[poly_offsets[p + 1]];
+  int lo = 1, hi = 0;
+  if (v1 > v0) {
+    double dmin = px[v0], dmax = px[v0];
+    for (int64_t i = v0 + 1; i < v1; ++i) { dmin = fmin(dmin, px[i]); dmax = fmax(dmax, px[i]); }
+    // crossings are floor(x + 0.5): one cell of slack either side covers every rounding
+    lo = clamp_to_int(floor(dmin)) - 1;
+    hi = clamp_to_int(floor(dmax)) + 1;
+    if (lo < 0) lo = 0;
+    if (hi >= width) hi = width - 1;
+  }
+  minx[p] = lo;
+  maxx[p] = hi;
+}
+
+// pass 0: counts[tile] += 1 for every tile a polygon's box touches; pass 1: the polygon's id into
+// the tile's list (cursor = running position, starts at the tile's offset)
+__global__ void tile_bin_kernel(const int* __restrict__ miny, const int* __restrict__ maxy,
+                                const int* __restrict__ minx, const int* __restrict__ maxx, int64_t n_polygons,
+                                int tiles_x, int* __restrict__ counts_or_cursor, int* __restrict__ list) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_polygons) return;
+  if (miny[p] > maxy[p] || minx[p] > maxx[p]) return;
+  const int ty0 = miny[p] / RT_ROWS, ty1 = maxy[p] / RT_ROWS, tx0 = minx[p] / RT_COLS, tx1 = maxx[p] / RT_COLS;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const int at = atomicAdd(counts_or_cursor + (int64_t)ty * tiles_x + tx, 1);
+      if (list) list[at] = (int)p;
+    }
+}
+
+// exclusive scan of n ints in place by ONE block (n = number of tiles, a few hundred thousand);
+// total[0] receives the sum
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int* __restrict__ data, int64_t n, int* __restrict__ total) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + tid;
+    const int v = i < n ? data[i] : 0;
+    int incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int before = carry + (warp > 0 ? warp_sums[warp - 1] : 0);
+    if (i < n) data[i] = before + incl - v;
+    __syncthreads();
+    if (tid == 1023) carry = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *total = carry;
+}
+
+struct TileVisitor {
+  int* tile; int x_lo, x_hi, y_lo; int label;       // tile = RT_ROWS x RT_COLS indices, columns x_lo..x_hi
+  __device__ __forceinline__ void span(int y, int x0, int x1) {
+    x0 = x0 < x_lo ? x_lo : x0;
+    x1 = x1 > x_hi ? x_hi : x1;
+    int* row = tile + (y - y_lo) * RT_COLS - x_lo;
+    for (int x = x0 + (threadIdx.x & 31); x <= x1; x += 32) atomicMax(row + x, label);
+  }
+  __device__ __forceinline__ void hspan(int y, int x0, int x1, const int*, int) { span(y, x0, x1); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(32 * RT_WARPS)
+rasterize_tile_kernel(const PolyDev P, const int* __restrict__ tile_offsets, const int* __restrict__ tile_list,
+                      int tiles_x, const T* __restrict__ burn, T nodata, T* __restrict__ dst) {
+  extern __shared__ __align__(16) int rt_smem[];
+  int* tile = rt_smem;                                        // RT_ROWS x RT_COLS polygon indices
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* buf = tile + RT_ROWS * RT_COLS + warp * P.cap;         // crossings of the generic scanline
+  int* hbuf = tile + RT_ROWS * RT_COLS + RT_WARPS * P.cap + warp * 2 * PG_MAX_HSPANS;
+  __shared__ double s_px[RT_WARPS][ZW_MAXV], s_py[RT_WARPS][ZW_MAXV];
+  __shared__ int s_prev[RT_WARPS][ZW_MAXV];
+  __shared__ __align__(16) int s_cross[RT_WARPS][ZW_MAXC][32];
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int x_lo = tx * RT_COLS, y_lo = ty * RT_ROWS;
+  const int x_hi = min(x_lo + RT_COLS, P.width) - 1, y_hi = min(y_lo + RT_ROWS, P.height) - 1;
+  for (int i = threadIdx.x; i < RT_ROWS * RT_COLS; i += blockDim.x) tile[i] = -1;
+  __syncthreads();
+  const int first = tile_offsets[blockIdx.x], last = tile_offsets[blockIdx.x + 1];
+  for (int item = first + warp; item < last; item += RT_WARPS) {
+    const int64_t p = tile_list[item];
+    const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
+    if (r1 <= r0) continue;
+    const int64_t v0 = P.ring_offsets[r0], v1 = P.ring_offsets[r1];
+    const int nv = (int)min((int64_t)(ZW_MAXV + 1), v1 - v0);
+    const int ya = max(P.miny[p], y_lo), yb = min(P.maxy[p], y_hi);
+    if (ya > yb) continue;
+    TileVisitor vis{tile, x_lo, x_hi, y_lo, (int)p};
+    if (nv == 1) {                 // point feature (GDALdllImagePoint): the cell that contains it
+      const int x = clamp_to_int(floor(P.px[v0]));
+      if (x >= x_lo && x <= x_hi) vis.span(ya, x, x);
+      continue;
+    }
+    if (nv > ZW_MAXV) {            // many vertices: the whole warp works on one row at a time
+      for (int y = ya; y <= yb; ++y) generic_scanline(P, r0, r1, y, P.cap, buf, hbuf, vis);
+      continue;
+    }
+    stage_polygon(P, r0, r1, v0, nv, s_px[warp], s_py[warp], s_prev[warp], lane);
+    for (int base = ya; base <= yb; base += 32) {
+      const int y = base + lane;
+      int cnt = 0;
+      if (y <= yb) cnt = row_crossings(s_px[warp], s_py[warp], s_prev[warp], nv, y, s_cross[warp], lane);
+      __syncwarp();
+      const int rows_here = min(32, yb - base + 1);
+      for (int r = 0; r < rows_here; ++r) {
+        const int c = __shfl_sync(0xffffffffu, cnt, r);
+        if (c < 0) { generic_scanline(P, r0, r1, base + r, P.cap, buf, hbuf, vis); continue; }
+        for (int i = 0; i + 1 < c; i += 2) {
+          const int xa = s_cross[warp][i][r], xb = s_cross[warp][i + 1][r] - 1;
+          if (xa <= x_hi && xb >= x_lo) vis.span(base + r, xa, xb);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // the tile leaves once: burn value of the winning polygon, `nodata` where there is none
+  for (int i = threadIdx.x; i < RT_ROWS * RT_COLS; i += blockDim.x) {
+    const int y = y_lo + i / RT_COLS, x = x_lo + i % RT_COLS;
+    if (y <= y_hi && x <= x_hi) {
+      const int l = tile[i];
+      dst[(int64_t)y * P.width + x] = l < 0 ? nodata : burn[l];
+    }
+  }
+}
+
 // ---- multi-GPU order statistics: raw values out, segments in ---------------------------------
 // Append the ACTIVE cell values under polygon p at values[offsets[p] ...] (any order).
 template <typename T>
@@ -2316,39 +2442,58 @@ static unsigned poly_grid(int64_t n) {
 template <typename T>
 static int run_rasterize(PolyUpload& u, const void* burn, const void* nodata, Staged& out,
                          int64_t n_pixels, cudaStream_t s) {
-  void *idx = nullptr, *dburn = nullptr;
-  GM_CUDA(cudaMallocAsync(&idx, sizeof(int) * (size_t)n_pixels, s));
-  GM_CUDA(cudaMemsetAsync(idx, 0xff, sizeof(int) * (size_t)n_pixels, s));
-  int rc = 0;
   const int64_t np_ = u.dev.n_polygons;
+  const int H = u.dev.height, W = u.dev.width;
+  const int tiles_x = (W + RT_COLS - 1) / RT_COLS, tiles_y = (H + RT_ROWS - 1) / RT_ROWS;
+  const int64_t n_tiles = (int64_t)tiles_x * tiles_y;
+  T nd;
+  memcpy(&nd, nodata, sizeof(T));
+  void *dburn = nullptr, *dminx = nullptr, *dmaxx = nullptr, *doffsets = nullptr, *dcursor = nullptr;
+  void *dlist = nullptr, *dtotal = nullptr;
+  auto cleanup = [&]() {
+    void* all[] = {dburn, dminx, dmaxx, doffsets, dcursor, dlist, dtotal};
+    for (void* p : all) if (p) cudaFreeAsync(p, s);
+  };
+#define GM_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  if (upload(&dburn, burn, sizeof(T) * (size_t)(np_ > 0 ? np_ : 1), s)) { cleanup(); return 1; }
+  GM_TRY(cudaMallocAsync(&doffsets, sizeof(int) * (size_t)(n_tiles + 1), s));
+  GM_TRY(cudaMemsetAsync(doffsets, 0, sizeof(int) * (size_t)(n_tiles + 1), s));
+  int total = 0;
   if (np_ > 0) {
-    const size_t smem = scan_smem(u.dev.cap, PG_WARPS);
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024)
-      e = cudaFuncSetAttribute(rasterize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) {
-      rasterize_kernel<<<poly_grid(np_), PG_THREADS, smem, s>>>(u.dev, (int*)idx);
-      e = cudaGetLastError();
-    }
-    if (e != cudaSuccess) rc = fail(std::string("rasterize launch: ") + cudaGetErrorString(e));
-    else count_launch();
+    // polygons -> tiles: count, scan, fill
+    GM_TRY(cudaMallocAsync(&dminx, sizeof(int) * np_, s));
+    GM_TRY(cudaMallocAsync(&dmaxx, sizeof(int) * np_, s));
+    GM_TRY(cudaMallocAsync(&dcursor, sizeof(int) * (size_t)(n_tiles + 1), s));
+    GM_TRY(cudaMallocAsync(&dtotal, sizeof(int), s));
+    const unsigned pb = (unsigned)((np_ + 255) / 256);
+    poly_cols_kernel<<<pb, 256, 0, s>>>(u.dev.px, u.dev.ring_offsets, u.dev.poly_offsets, np_, W,
+                                        (int*)dminx, (int*)dmaxx);
+    tile_bin_kernel<<<pb, 256, 0, s>>>(u.dev.miny, u.dev.maxy, (const int*)dminx, (const int*)dmaxx, np_,
+                                       tiles_x, (int*)doffsets, nullptr);
+    tile_scan_kernel<<<1, 1024, 0, s>>>((int*)doffsets, n_tiles + 1, (int*)dtotal);
+    GM_TRY(cudaGetLastError());
+    count_launch(3);
+    GM_TRY(cudaMemcpyAsync(&total, dtotal, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GM_TRY(cudaMemcpyAsync(dcursor, doffsets, sizeof(int) * (size_t)(n_tiles + 1), cudaMemcpyDeviceToDevice, s));
+    GM_TRY(cudaStreamSynchronize(s));
+    GM_TRY(cudaMallocAsync(&dlist, sizeof(int) * (size_t)(total > 0 ? total : 1), s));
+    tile_bin_kernel<<<pb, 256, 0, s>>>(u.dev.miny, u.dev.maxy, (const int*)dminx, (const int*)dmaxx, np_,
+                                       tiles_x, (int*)dcursor, (int*)dlist);
+    GM_TRY(cudaGetLastError());
+    count_launch();
+  } else {
+    GM_TRY(cudaMallocAsync(&dlist, sizeof(int), s));
   }
-  if (!rc) rc = upload(&dburn, burn, sizeof(T) * (size_t)(np_ > 0 ? np_ : 1), s);
-  if (!rc) {
-    T nd;
-    memcpy(&nd, nodata, sizeof(T));
-    int64_t blocks = (n_pixels + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    resolve_labels_kernel<T><<<(unsigned)blocks, 256, 0, s>>>((const int*)idx, (const T*)dburn, nd,
-                                                              (T*)out.dev, n_pixels);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) rc = fail(std::string("resolve launch: ") + cudaGetErrorString(e));
-    else count_launch();
-  }
-  cudaFreeAsync(idx, s);
-  if (dburn) cudaFreeAsync(dburn, s);
-  return rc;
+  const size_t smem = (size_t)RT_ROWS * RT_COLS * sizeof(int) + scan_smem(u.dev.cap, RT_WARPS);
+  GM_TRY(cudaFuncSetAttribute(rasterize_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rasterize_tile_kernel<T><<<(unsigned)n_tiles, 32 * RT_WARPS, smem, s>>>(
+      u.dev, (const int*)doffsets, (const int*)dlist, tiles_x, (const T*)dburn, nd, (T*)out.dev);
+  GM_TRY(cudaGetLastError());
+  count_launch();
+#undef GM_TRY
+  cleanup();
+  (void)n_pixels;
+  return 0;
 }
 
 template <typename T>

@@ -7,6 +7,8 @@ evaluator (``_lowering``), polygon burning in the CUDA scanline rasteriser
 """
 import numpy as np
 
+from .. import _native
+
 from .. import utils
 from .._compat import config
 from . import _lowering
@@ -367,6 +369,10 @@ class Rasterize(_NonTemporalRaster):
             soup=soup,
         )
         raw = burned["values"]
+        if _native.is_device(raw):
+            if raw.dtype == dtype and burned["no_data_value"] == no_data_value:
+                return {"values": raw, "no_data_value": no_data_value}    # stays in HBM
+            raw = np.asarray(raw)
         with np.errstate(over="ignore", under="ignore"):
             result = raw.astype(dtype)
         if burned["no_data_value"] != no_data_value:

@@ -448,9 +448,11 @@ def _ring_moments(c):
     return area, ((x0 + x1) * cross).sum() / 6.0, ((y0 + y1) * cross).sum() / 6.0
 
 
-def geometry_rings(geometry):
+def geometry_rings(geometry, points=False):
     """All rings (N x 2 float64 arrays, closed) of a (multi)polygon; works for
-    the classes above and for shapely geometries."""
+    the classes above and for shapely geometries.  ``points=True`` turns a Point into a
+    one-vertex ring, which the rasteriser burns into the cell that contains it (GDAL's
+    GDALdllImagePoint)."""
     if geometry is None or getattr(geometry, "is_empty", False):
         return []
     if hasattr(geometry, "geoms"):
@@ -463,6 +465,8 @@ def geometry_rings(geometry):
         rings.extend(_ring(np.asarray(r.coords)[:, :2]) for r in geometry.interiors)
         return rings
     kind = getattr(geometry, "geom_type", type(geometry).__name__)
+    if kind == "Point" and points:
+        return [np.array([[float(geometry.x), float(geometry.y)]], dtype=np.float64)]
     if kind in ("Point", "MultiPoint"):
         # no area: nothing to scan-convert.  AggregateRaster samples such features at the cell
         # that contains them (the cell GDAL's point burn would label); rasterize_geoseries
@@ -505,16 +509,17 @@ class PolygonSoup(object):
     """CSR layout the CUDA rasteriser consumes: interleaved xy, ring offsets,
     polygon -> ring offsets (GmPolygons in include/geokernels.h)."""
 
-    def __init__(self, geometries):
+    def __init__(self, geometries, points=False):
         xy, ring_offsets, poly_offsets = [], [0], [0]
         n_vertices = 0
         # features without area (points) hold no rings; consumers that cannot sample them
         # (rasterize_geoseries) check this flag instead of dropping them silently
         self.has_points = False
         for geometry in geometries:
-            if getattr(geometry, "geom_type", None) in ("Point", "MultiPoint"):
+            kind = getattr(geometry, "geom_type", None)
+            if kind == "MultiPoint" or (kind == "Point" and not points):
                 self.has_points = True
-            for ring in geometry_rings(geometry):
+            for ring in geometry_rings(geometry, points):
                 xy.append(ring)
                 n_vertices += len(ring)
                 ring_offsets.append(n_vertices)
@@ -590,6 +595,8 @@ class PolygonSoup(object):
 
 
 def _finalize_rasterize_result(array, no_data_value):
+    if array.dtype == bool:         # burned on the device straight into a boolean raster
+        return {"values": array, "no_data_value": None}
     if array.dtype == np.uint8:
         return {"values": array.astype(bool), "no_data_value": None}
     return {"values": array, "no_data_value": no_data_value}
@@ -660,20 +667,27 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None,
             array[:] = True if values is None else values.values[np.nonzero(hits)[0][-1]]
         return _finalize_rasterize_result(array, no_data_value)
 
-    if soup is None:
-        soup = PolygonSoup(geoseries.values)
+    if soup is None or soup.has_points:
+        # (points are burned into the cell that contains them: one-vertex rings)
+        soup = PolygonSoup(geoseries.values, points=True)
     elif len(positions) != soup.n_polygons:
         soup = soup.subset(positions)
     if soup.has_points:
         raise NotImplementedError(
-            "point geometries cannot be burned by the CUDA rasteriser (polygons only)")
+            "MultiPoint geometries cannot be burned by the CUDA rasteriser (polygons and points only)")
     burn = (
         np.ones(soup.n_polygons, dtype=dtype)
         if values is None
         else np.ascontiguousarray(values.values, dtype=dtype)
     )
     geo = (ctypes.c_double * 6)(*GeoTransform.from_bbox(bbox, height, width))
-    array = _native.pinned_empty((1, height, width), dtype)
+    from . import _state
+
+    if _state.keep_on_device():
+        # inside a view the burned raster stays in HBM (Rasterize -> Clip / Mask fuse on it)
+        array = _native.DeviceArray((1, height, width), bool if dtype == np.uint8 else dtype)
+    else:
+        array = _native.pinned_empty((1, height, width), dtype)
     nodata_holder, nodata_ptr = _native.scalar_ptr(no_data_value, dtype)
     dst = _native.as_gm_array(array)
     polys = soup.as_struct()

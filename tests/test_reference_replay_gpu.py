@@ -270,6 +270,16 @@ def test_geoseries_categorical(geoseries):
     assert (got["values"][0, 6:8, 2:4] == 1.2).all()
 
 
+def test_geoseries_burns_points_into_their_cell():
+    # GDAL burns a point feature into the cell that contains it (GDALdllImagePoint)
+    series = pd.Series([utils.Point(2.5, 7.5), box(6, 6, 8, 8), utils.Point(9.99, 0.01), utils.Point(12, 3)],
+                       dtype=object)
+    got = utils.rasterize_geoseries(series, values=pd.Series([5, 6, 7, 8]), **BOX)
+    values = got["values"][0]
+    assert values[2, 2] == 5 and values[9, 9] == 7 and (values[2:4, 6:8] == 6).all()
+    assert (values != got["no_data_value"]).sum() == 1 + 4 + 1
+
+
 def test_geoseries_rejects_lines_loudly():
     class LineString(object):
         geom_type = "LineString"

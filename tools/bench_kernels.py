@@ -160,8 +160,9 @@ def main():
         import pandas as pd
 
         ids = pd.Series(np.arange(len(polys)))
+        series = pd.Series(polys, dtype=object)
         measure("rasterize_int32_%dpolys" % len(polys),
-                lambda: utils.rasterize_geoseries(polys, bbox, workloads.PROJECTION, n, n, values=ids),
+                lambda: utils.rasterize_geoseries(series, bbox, workloads.PROJECTION, n, n, values=ids, soup=soup),
                 n * n, n * n * 4, iters=max(2, args.iters // 3))
         del r, rd
         torch.cuda.empty_cache()
