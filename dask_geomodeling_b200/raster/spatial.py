@@ -13,7 +13,7 @@ import numpy as np
 from .. import _native, _state, utils
 from .base import BaseSingle
 
-__all__ = ["Dilate", "Smooth", "MovingMax", "HillShade"]
+__all__ = ["Dilate", "Smooth", "MovingMax", "HillShade", "Place"]
 
 
 def expand_request_pixels(request, radius=1):
@@ -280,3 +280,172 @@ class HillShade(BaseSingle):
                 stream),
         )
         return {"values": out, "no_data_value": 256}
+
+
+class Place(BaseSingle):
+    """Place a raster at given coordinates: the cell of ``store`` under ``anchor`` lands on each
+    of ``coordinates``; where copies overlap they are merged with ``statistic``
+    (reference: raster/spatial.py:440-731).
+
+    The reference scatters the store's data cells into a fresh array per coordinate (np.where
+    indices, :679-719) and merges the stack with ``reduce_rasters``.  Here a copy is one
+    integer-shift gather on the device (``gm_resample_nn`` with unit steps) and the merge is the
+    reduction program of raster/reduction.py.  Anchor and coordinates must be given in the
+    projection of the request (this build has no PROJ)."""
+
+    def __init__(self, store, place_projection, anchor, coordinates, statistic="last"):
+        from .base import RasterBlock
+        from .reduction import check_statistic
+
+        if not isinstance(store, RasterBlock):
+            raise TypeError("'{}' object is not allowed".format(type(store)))
+        if not isinstance(place_projection, str) or not place_projection.strip():
+            raise ValueError("'{}' is not a valid projection string".format(place_projection))
+        anchor = list(anchor)
+        if len(anchor) != 2:
+            raise ValueError("Expected 2 numbers in the 'anchor' parameter")
+        for x in anchor:
+            if not isinstance(x, (int, float)):
+                raise TypeError("'{}' object is not allowed".format(type(x)))
+        if coordinates is None or len(coordinates) == 0:
+            coordinates = []
+        else:
+            coordinates = np.asarray(coordinates, dtype=float)
+            if coordinates.ndim != 2 or coordinates.shape[1] != 2:
+                raise ValueError("Expected a list of lists of 2 numbers in the 'coordinates' parameter")
+            coordinates = coordinates.tolist()
+        check_statistic(statistic)
+        super().__init__(store, utils.get_epsg_or_wkt(place_projection), anchor, coordinates, statistic)
+
+    place_projection = property(lambda self: self.args[1])
+    anchor = property(lambda self: self.args[2])
+    coordinates = property(lambda self: self.args[3])
+    statistic = property(lambda self: self.args[4])
+
+    @property
+    def projection(self):
+        store_projection = self.store.projection
+        if store_projection is not None and utils.same_projection(self.place_projection, store_projection):
+            return store_projection
+        return None
+
+    @property
+    def geo_transform(self):
+        return self.store.geo_transform if self.projection is not None else None
+
+    @property
+    def geometry(self):
+        store_geometry = self.store.geometry
+        if store_geometry is None or not self.coordinates:
+            return None
+        x1, y1, x2, y2 = utils.Extent.from_geometry(store_geometry).transformed(self.place_projection).bbox
+        p, q = self.anchor
+        xs, ys = zip(*self.coordinates)
+        return utils.Extent((x1 + min(xs) - p, y1 + min(ys) - q, x2 + max(xs) - p, y2 + max(ys) - q),
+                            self.place_projection).as_geometry()
+
+    @property
+    def extent(self):
+        geometry = self.geometry
+        if geometry is None:
+            return None
+        return utils.Extent.from_geometry(geometry, self.place_projection).transformed("EPSG:4326").bbox
+
+    def get_sources_and_requests(self, **request):
+        import math
+
+        if request["mode"] != "vals":
+            return ({"mode": request["mode"]}, None), (self.store, request)
+        if not utils.same_projection(self.place_projection, request["projection"]):
+            raise NotImplementedError(
+                "Place: anchor / coordinates in {} cannot be transformed to {} (no PROJ in this build)".format(
+                    self.place_projection, request["projection"]))
+        anchor, coordinates = tuple(self.anchor), [tuple(c) for c in self.coordinates]
+        source_geometry = self.store.geometry
+        if source_geometry is None:
+            return (({"mode": "null"}, None),)
+        xmin, ymin, xmax, ymax = utils.Extent.from_geometry(source_geometry).transformed(request["projection"]).bbox
+        x1, y1, x2, y2 = request["bbox"]
+        size_x, size_y = (x2 - x1) / request["width"], (y2 - y1) / request["height"]
+        if size_x > 0 and size_y > 0:
+            # when the whole store is smaller than the request: fetch it once, shift it on the device
+            full_height = math.ceil((ymax - ymin) / size_y)
+            full_width = math.ceil((xmax - xmin) / size_x)
+            if full_height * full_width <= request["width"] * request["height"]:
+                whole = dict(request, width=full_width, height=full_height,
+                             bbox=(xmin, ymin, xmin + full_width * size_x, ymin + full_height * size_y))
+                kwargs = {"mode": "warp", "anchor": anchor, "coordinates": coordinates, "src_bbox": whole["bbox"],
+                          "dst_bbox": request["bbox"], "cellsize": (size_x, size_y), "statistic": self.statistic}
+                return [(kwargs, None), (self.store, whole)]
+        # otherwise: one request per coordinate, shifted backwards by (coordinate - anchor)
+        shifted = []
+        for cx, cy in coordinates:
+            bbox = [x1 + anchor[0] - cx, y1 + anchor[1] - cy, x2 + anchor[0] - cx, y2 + anchor[1] - cy]
+            # cells span [xmin, xmax) x (ymin, ymax]: a box that only touches xmax / ymin holds no data
+            if bbox[0] >= xmax or bbox[1] > ymax or bbox[2] < xmin or bbox[3] <= ymin:
+                continue
+            shifted.append((self.store, dict(request, bbox=bbox)))
+        if not shifted:
+            kwargs = {"mode": "empty", "dtype": self.dtype, "fillvalue": self.fillvalue,
+                      "width": request["width"], "height": request["height"], "statistic": self.statistic}
+            return [(kwargs, None), (self.store, dict(request, mode="time"))]
+        return [({"mode": "group", "statistic": self.statistic}, None)] + shifted
+
+    @staticmethod
+    def process(process_kwargs, *multi):
+        from .reduction import reduce_rasters
+
+        mode = process_kwargs["mode"]
+        if mode in ("meta", "time"):
+            return multi[0]
+        if mode == "null":
+            return None
+        if mode == "empty":
+            data = multi[0]
+            if data is None:
+                return None
+            shape = (len(data["time"]), process_kwargs["height"], process_kwargs["width"])
+            fill, dtype = process_kwargs["fillvalue"], process_kwargs["dtype"]
+            return {"values": np.full(shape, fill, dtype), "no_data_value": fill}
+        if mode == "group":
+            stack = [d for d in multi if d is not None]
+            if not stack:
+                return None
+            return reduce_rasters(stack, process_kwargs["statistic"])
+        # "warp": ONE source raster (cell size already that of the request), shifted per coordinate
+        data = multi[0]
+        if data is None:
+            return None
+        source, nodata = data["values"], data["no_data_value"]
+        dtype = source.dtype
+        size_x, size_y = process_kwargs["cellsize"]
+        anchor, src_bbox = process_kwargs["anchor"], process_kwargs["src_bbox"]
+        anchor_px = ((anchor[0] - src_bbox[0]) / size_x, (anchor[1] - src_bbox[1]) / size_y)
+        x1, y1, x2, y2 = process_kwargs["dst_bbox"]
+        dst_h, dst_w = round((y2 - y1) / size_y), round((x2 - x1) / size_x)
+        depth, src_h, src_w = source.shape
+        shape = (depth, dst_h, dst_w)
+        if not _native.is_device(source):
+            source = _native.DeviceArray.from_host(np.ascontiguousarray(source))
+        holder, nodata_ptr = _native.scalar_ptr(nodata, dtype)
+        lib, stream = _native.lib(), _native.current_stream()
+        src_desc = _native.as_gm_array(source)
+        stack = []
+        for cx, cy in process_kwargs["coordinates"]:
+            di = round((cx - x1) / size_x - anchor_px[0])
+            dj = round((cy - y1) / size_y - anchor_px[1])
+            dj = dst_h - src_h - dj          # rows count from the northern edge
+            if di <= -src_w or di >= dst_w or dj <= -src_h or dj >= dst_h:
+                continue                      # shifted completely outside
+            placed = _native.DeviceArray(shape, dtype)
+            dst_desc = _native.as_gm_array(placed)
+            # placed[:, j, i] = source[:, j - dj, i - di], 'no data' outside the source
+            _native.check(lib.gm_resample_nn(ctypes.byref(src_desc), ctypes.byref(dst_desc), nodata_ptr,
+                                             float(-di), 1.0, float(-dj), 1.0, stream))
+            stack.append({"values": placed, "no_data_value": nodata})
+        if not stack:
+            return {"values": np.full(shape, nodata, dtype), "no_data_value": nodata}
+        result = reduce_rasters(stack, process_kwargs["statistic"])
+        if not _state.keep_on_device() and _native.is_device(result["values"]):
+            result["values"] = result["values"].to_host()
+        return result

@@ -491,3 +491,34 @@ def group_by_time(stack, times, dtype, start, stop):
         k = len(instants) - 1 if start is None else min(range(len(instants)), key=lambda i: abs(instants[i] - start))
         values = values[k:k + 1]
     return values, fill
+
+
+def place_warp(values, nodata, kwargs):
+    """Place.process, mode "warp" (raster/spatial.py:657-731): the source is shifted onto every
+    coordinate and the copies are merged with reduce_rasters."""
+    size_x, size_y = kwargs["cellsize"]
+    anchor, src_bbox = kwargs["anchor"], kwargs["src_bbox"]
+    anchor_px = ((anchor[0] - src_bbox[0]) / size_x, (anchor[1] - src_bbox[1]) / size_y)
+    x1, y1, x2, y2 = kwargs["dst_bbox"]
+    dst_h, dst_w = round((y2 - y1) / size_y), round((x2 - x1) / size_x)
+    depth, src_h, src_w = values.shape
+    shape = (depth, dst_h, dst_w)
+    k, j, i = np.where(has_data_close(values, nodata))
+    stack = []
+    for x, y in kwargs["coordinates"]:
+        if i.size == 0:
+            break
+        di = round((x - x1) / size_x - anchor_px[0])
+        dj = dst_h - src_h - round((y - y1) / size_y - anchor_px[1])
+        if di <= -src_w or di >= dst_w or dj <= -src_h or dj >= dst_h:
+            continue
+        i_s, j_s = i + di, j + dj
+        m = (i_s >= 0) & (j_s >= 0) & (i_s < dst_w) & (j_s < dst_h)
+        if not m.any():
+            continue
+        placed = np.full(shape, nodata, values.dtype)
+        placed[k[m], j_s[m], i_s[m]] = values[k[m], j[m], i[m]]
+        stack.append((placed, nodata))
+    if not stack:
+        return np.full(shape, nodata, values.dtype), nodata
+    return reduce_rasters(stack, kwargs["statistic"])

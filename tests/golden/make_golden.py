@@ -330,6 +330,18 @@ def reductions(ns):
             [payload(a), payload(b)], [{"time": t} for t in times],
             {"dtype": np.dtype("f4"), "start": start, "stop": stop})
         rec.add("group_time", "group", {"times": times, "dtype": "f4", "start": start, "stop": stop}, [a, b], res)
+    # Place, warp mode (raster/spatial.py:657-731): one source shifted onto every coordinate
+    src = raster("f4", 830, nodata_fraction=0.3, shape=(2, 6, 8))
+    for statistic in ("last", "first", "max", "count", "sum"):
+        kwargs = {"mode": "warp", "anchor": (12.0, 22.0), "src_bbox": (10.0, 20.0, 18.0, 26.0),
+                  "dst_bbox": (0.0, 0.0, 30.0, 20.0), "cellsize": (1.0, 1.0), "statistic": statistic,
+                  "coordinates": [(5.0, 5.0), (12.0, 10.0), (29.0, 19.0), (100.0, 100.0), (14.0, 6.0), (1.0, 1.0)]}
+        res = ns.spatial.Place.process(kwargs, payload(src))
+        rec.add("place_warp", statistic, kwargs, [src], res)
+    kwargs = {"mode": "warp", "anchor": (12.0, 22.0), "src_bbox": (10.0, 20.0, 18.0, 26.0),
+              "dst_bbox": (0.0, 0.0, 30.0, 20.0), "cellsize": (1.0, 1.0), "statistic": "last",
+              "coordinates": [(500.0, 5.0)]}
+    rec.add("place_warp", "last", kwargs, [src], ns.spatial.Place.process(kwargs, payload(src)))
     rec.save("reduce")
 
 

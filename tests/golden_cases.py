@@ -118,6 +118,8 @@ def run_oracle(case, arrays):
         return R.group_by_bands(ins, args["bands"], args["dtype"], tuple(args["shape"]))
     if fam == "group_time":
         return R.group_by_time(ins, args["times"], args["dtype"], args["start"], args["stop"])
+    if fam == "place_warp":
+        return R.place_warp(ins[0][0], ins[0][1], args)
     raise KeyError(fam)
 
 
@@ -180,6 +182,8 @@ def run_product(case, arrays):
     elif fam == "group_bands":
         res = raster.Group._merge_vals_by_bands(ins, [tuple(b) for b in args["bands"]], np.dtype(args["dtype"]),
                                                 tuple(args["shape"]))
+    elif fam == "place_warp":
+        res = raster.Place.process(args, ins[0])
     elif fam == "group_time":
         res = raster.Group._merge_vals_by_time(
             ins, [{"time": t} for t in args["times"]],

@@ -86,3 +86,32 @@ def test_group_of_non_temporal_sources_fills_gaps():
     got = view.get_data(**workloads.request(48, 48))
     expected, _ = R.reduce_rasters([(a, nd), (b, nd)], "last", nd, "float32")
     np.testing.assert_array_equal(got["values"], expected)
+
+
+def test_place_through_get_data():
+    """Place as a view (reference: raster/spatial.py:440-731): the source placed at three
+    coordinates, overlapping copies merged with 'last' and 'max'; against the oracle."""
+    rng = np.random.default_rng(4)
+    data = rng.uniform(1, 100, (1, 6, 8)).astype("f4")
+    nodata = workloads.F32_MAX
+    data[rng.random(data.shape) < 0.3] = nodata
+    src = raster.MemorySource(data, nodata, workloads.PROJECTION, pixel_size=1.0, pixel_origin=(10, 26))
+    coordinates = [(5.0, 5.0), (12.0, 10.0), (14.0, 6.0)]
+    request = dict(mode="vals", bbox=(0, 0, 30, 20), width=30, height=20, projection=workloads.PROJECTION)
+    for statistic in ("last", "max"):
+        view = raster.Place(src, workloads.PROJECTION, (12.0, 22.0), coordinates, statistic)
+        got = view.get_data(**request)
+        kwargs = {"anchor": (12.0, 22.0), "src_bbox": (10.0, 20.0, 18.0, 26.0), "dst_bbox": (0.0, 0.0, 30.0, 20.0),
+                  "cellsize": (1.0, 1.0), "statistic": statistic, "coordinates": coordinates}
+        expected, _ = R.place_warp(data, nodata, kwargs)
+        np.testing.assert_array_equal(got["values"], expected)
+    # a request finer than the source: one shifted request per coordinate ("group" mode)
+    fine = dict(mode="vals", bbox=(4, 4, 8, 8), width=2, height=2, projection=workloads.PROJECTION)
+    view = raster.Place(src, workloads.PROJECTION, (12.0, 22.0), [(5.0, 5.0)], "last")
+    plan = view.get_sources_and_requests(**fine)
+    assert plan[0][0]["mode"] == "group" and len(plan) == 2
+    assert view.get_data(**fine)["values"].shape == (1, 2, 2)
+    with pytest.raises(ValueError):
+        raster.Place(src, workloads.PROJECTION, (1, 2, 3), coordinates)
+    with pytest.raises(ValueError):
+        raster.Place(src, workloads.PROJECTION, (1, 2), coordinates, "nonsense")
