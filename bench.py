@@ -396,7 +396,7 @@ def run_stencils(ctx):
     ops = [
         ("smooth", "Smooth(size=5.0), exact mode", lw, 5, raster.Smooth.process,
          (dict(smooth_mode="exact", fill=0, size=[5.0, 5.0], margin=(lw, 5)),), 8, "smooth_fast_kernel"),
-        ("movingmax", "MovingMax(size=11)", 5, 5, raster.MovingMax.process, (11,), 8, "moving_max_quad_kernel"),
+        ("movingmax", "MovingMax(size=11)", 5, 5, raster.MovingMax.process, (11,), 8, "moving_max_block_kernel"),
         ("hillshade", "HillShade(altitude=45, azimuth=315)", 1, 1, raster.HillShade.process,
          (dict(resolution=(1.0, 1.0), altitude=45.0, azimuth=315.0, fill=0),), 5, "hillshade_quad_kernel"),
     ]

@@ -517,15 +517,7 @@ static int launch_moving_max_fixed(const Staged& in, Staged& out, T nd, int has_
   return 0;
 }
 
-// Register-blocked version for 4-byte rasters: the same three phases, but a thread owns FOUR
-// adjacent columns, so that every shared-memory access is a conflict-free 16-byte one.
-//   phase 2: a thread reads the 4 + 2R source values of its row segment once (4 quads at
-//            size 11) and grows the chord maxima of its four pixels in registers -- one 3-input
-//            maximum per step outwards (FMNMX3) -- storing one quad per chord-width plane;
-//   phase 3: a thread reads one quad per footprint row from the plane of that row's chord
-//            and reduces the 2R + 1 quads with 3-input maxima.
-// Shared-memory traffic per output pixel drops from 136 to 92 bytes and the instruction count
-// from ~70 to ~30 at size 11.
+// 16-byte groups of four 4-byte cells (conflict-free shared-memory accesses)
 template <typename T> struct Quad { T v[4]; };
 template <typename T> __device__ __forceinline__ T vmin4(const T (&v)[4]) {
   const T a = v[0] < v[1] ? v[0] : v[1], b = v[2] < v[3] ? v[2] : v[3];
@@ -543,9 +535,17 @@ template <typename T> __device__ __forceinline__ void sts_quad(T* p, const Quad<
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Register-blocked version for 4-byte rasters: ONE phase after the tile is staged.  A
+// thread owns 4 adjacent columns x MMB_ROWS rows of outputs and walks the MMB_ROWS + 2R tile rows
+// they depend on: per tile row it reads its 4 + 2R values once (NQ conflict-free LDS.128), grows
+// the nested chord maxima of its four columns in registers and folds the chord that footprint row
+// dy = (tile row - output row) asks for into each of the (up to 2R + 1) output rows in reach.
+// No chord planes in shared memory: 4 NQ (MMB_ROWS + 2R) / MMB_ROWS bytes of shared-memory reads per
+// pixel (36 at size 11) instead of 92, and one block barrier per tile instead of three.
+constexpr int MMB_TX = 128, MMB_ROWS = 8, MMB_TY = 8 * MMB_ROWS;
+
 template <typename T, int SIZE, int D>
-__device__ __forceinline__ void chord_quads(const T* w, T (&m)[4], T* chord_row, int plane_stride) {
-  // w[0 .. 4 + 2R): the window of this segment; pixel i's centre is w[R + i]
+__device__ __forceinline__ void chord_regs(const T* w, T (&m)[4], T (*c)[4]) {
   constexpr int R = Disc<SIZE>::R;
   if constexpr (D <= Disc<SIZE>::wmax()) {
     if constexpr (D > 0) {
@@ -553,70 +553,130 @@ __device__ __forceinline__ void chord_quads(const T* w, T (&m)[4], T* chord_row,
       for (int i = 0; i < 4; ++i) m[i] = vmax<T>(m[i], vmax<T>(w[R + i - D], w[R + i + D]));
     }
     if constexpr (Disc<SIZE>::used(D)) {
-      Quad<T> q;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) q.v[i] = m[i];
-      sts_quad<T>(chord_row + Disc<SIZE>::plane_of(D) * plane_stride, q);
+      for (int i = 0; i < 4; ++i) c[Disc<SIZE>::plane_of(D)][i] = m[i];
     }
-    chord_quads<T, SIZE, D + 1>(w, m, chord_row, plane_stride);
+    chord_regs<T, SIZE, D + 1>(w, m, c);
   }
 }
 
-template <typename T, int SIZE, int DY>
-__device__ __forceinline__ void disc_quads(const T* chord_px, int plane_stride, T (&best)[4]) {
+template <typename T> __device__ __forceinline__ T vmax3(T a, T b, T c) { return vmax<T>(a, vmax<T>(b, c)); }
+
+// folds the chords of tile rows RW (c0) and RW + 1 (c1) into output row J: one 3-input maximum
+// when both rows are in the footprint of that output row
+template <typename T, int SIZE, int RW, int J>
+__device__ __forceinline__ void fold_rows(T (*c0)[4], T (*c1)[4], T (*best)[4]) {
   constexpr int R = Disc<SIZE>::R;
-  if constexpr (DY <= R) {
-    constexpr int w = Disc<SIZE>::half_width(DY);
-    if constexpr (w >= 0) {
-      const Quad<T> q = lds_quad<T>(chord_px + Disc<SIZE>::plane_of(w) * plane_stride + (DY + R) * MM2_TX);
+  if constexpr (J < MMB_ROWS) {
+    constexpr int dy0 = RW - J - R, dy1 = dy0 + 1;
+    constexpr int hw0 = (dy0 >= -R && dy0 <= R) ? Disc<SIZE>::half_width(dy0 < 0 ? -dy0 : dy0) : -1;
+    constexpr int hw1 = (dy1 >= -R && dy1 <= R && RW + 1 < MMB_ROWS + 2 * R) ? Disc<SIZE>::half_width(dy1 < 0 ? -dy1 : dy1) : -1;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) best[i] = vmax<T>(best[i], q.v[i]);
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (hw0 >= 0 && hw1 >= 0)
+        best[J][i] = vmax3<T>(best[J][i], c0[Disc<SIZE>::plane_of(hw0)][i], c1[Disc<SIZE>::plane_of(hw1)][i]);
+      else if constexpr (hw0 >= 0)
+        best[J][i] = vmax<T>(best[J][i], c0[Disc<SIZE>::plane_of(hw0)][i]);
+      else if constexpr (hw1 >= 0)
+        best[J][i] = vmax<T>(best[J][i], c1[Disc<SIZE>::plane_of(hw1)][i]);
     }
-    disc_quads<T, SIZE, DY + 1>(chord_px, plane_stride, best);
+    fold_rows<T, SIZE, RW, J + 1>(c0, c1, best);
   }
 }
 
+template <typename T, int SIZE, int TW, int RW>
+__device__ __forceinline__ void row_chords(const T* seg, T (*c)[4]) {
+  constexpr int R = Disc<SIZE>::R;
+  constexpr int NQ = (4 + 2 * R + 3) / 4;
+  if constexpr (RW < MMB_ROWS + 2 * R) {
+    T w[4 * NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      const Quad<T> q = lds_quad<T>(seg + RW * TW + 4 * k);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[4 * k + i] = q.v[i];
+    }
+    T m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = w[R + i];
+    chord_regs<T, SIZE, 0>(w, m, c);
+  }
+}
+
+template <typename T, int SIZE, int TW, int RW>
+__device__ __forceinline__ void walk_rows(const T* seg, T (*best)[4]) {
+  constexpr int R = Disc<SIZE>::R;
+  if constexpr (RW < MMB_ROWS + 2 * R) {
+    T c0[Disc<SIZE>::n_planes()][4], c1[Disc<SIZE>::n_planes()][4];
+    row_chords<T, SIZE, TW, RW>(seg, c0);
+    row_chords<T, SIZE, TW, RW + 1>(seg, c1);
+    fold_rows<T, SIZE, RW, 0>(c0, c1, best);
+    walk_rows<T, SIZE, TW, RW + 2>(seg, best);
+  }
+}
+
+// Tiles are walked by persistent blocks (two per SM), x fastest so that the blocks running at
+// one time share their halos in L2.  Two tile buffers per block: the bulk tensor copy of tile
+// k + 1 is issued before tile k is computed, so its latency hides behind the arithmetic.
 template <typename T, int SIZE>
-__global__ void __launch_bounds__(256)
-moving_max_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
-                       int bands, int H, int W, int SW, int dst_aligned, int use_tma,
-                       const __grid_constant__ CUtensorMap tile_map) {
+__global__ void __launch_bounds__(256, 2)
+moving_max_block_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata, int has_nodata,
+                        int bands, int H, int W, int SW, int dst_aligned, int use_tma,
+                        const __grid_constant__ CUtensorMap tile_map) {
   static_assert(sizeof(T) == 4, "quads of four 4-byte cells");
   extern __shared__ __align__(128) unsigned char mm_smem[];
-  __shared__ __align__(8) uint64_t tile_bar;
+  __shared__ __align__(8) uint64_t tile_bar[2];
   constexpr int R = Disc<SIZE>::R;
   constexpr int NQ = (4 + 2 * R + 3) / 4;                // quads per segment window
-  constexpr int TW = MM2_TX - 4 + 4 * NQ;                // tile row stride: every window in bounds
-  constexpr int TH = MM2_TY + 2 * R;
-  constexpr int PLANE = TH * MM2_TX;
-  constexpr int SEGS = MM2_TX / 4;
+  constexpr int TW = MMB_TX - 4 + 4 * NQ;                // tile row stride: every window in bounds
+  constexpr int TH = MMB_TY + 2 * R;
+  constexpr int TILE_BYTES = (TH * TW * (int)sizeof(T) + 127) / 128 * 128;
   // (the bulk tensor copy wants a 128-byte aligned destination: 128 spare bytes are allocated)
-  T* tile = reinterpret_cast<T*>(mm_smem + ((128u - (st_smem_u32(mm_smem) & 127u)) & 127u));   // TH x TW
-  T* chord = tile + TH * TW;                             // n_planes x TH x MM2_TX
+  unsigned char* base = mm_smem + ((128u - (st_smem_u32(mm_smem) & 127u)) & 127u);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int SH = H + 2 * R;                 // SW >= W + 2 R: the window may carry pitch padding
   const int64_t in_plane = (int64_t)SH * SW, out_plane = (int64_t)H * W;
-  const int x0 = blockIdx.x * MM2_TX, y0 = blockIdx.y * MM2_TY;
+  const int tiles_x = (W + MMB_TX - 1) / MMB_TX, tiles_y = (H + MMB_TY - 1) / MMB_TY;
+  const int64_t n_tiles = (int64_t)tiles_x * tiles_y * bands;
   const T lowest = Lowest<T>::value();
-  uint32_t tile_phase = 0;
+  uint32_t phases = 0u;                     // bit i: parity to wait for on tile_bar[i]
   if (use_tma) {
-    if (threadIdx.x == 0) st_mbar_init(&tile_bar, 1);
+    if (threadIdx.x == 0) {
+      st_mbar_init(&tile_bar[0], 1);
+      st_mbar_init(&tile_bar[1], 1);
+    }
     __syncthreads();
   }
-  for (int b = blockIdx.z; b < bands; b += gridDim.z) {
+  // tile t -> (band, y0, x0); a tile takes the bulk copy when it lies wholly inside the window
+  auto locate = [&](int64_t t, int& b, int& y0, int& x0) {
+    const int64_t per_band = (int64_t)tiles_x * tiles_y;
+    b = (int)(t / per_band);
+    const int r = (int)(t - b * per_band);
+    y0 = (r / tiles_x) * MMB_TY;
+    x0 = (r % tiles_x) * MMB_TX;
+    return use_tma && x0 + TW <= SW && y0 + TH <= SH;
+  };
+  auto prefetch = [&](int64_t t, int buf) {
+    int b, y0, x0;
+    if (t < n_tiles && locate(t, b, y0, x0) && threadIdx.x == 0) {
+      st_mbar_expect_tx(&tile_bar[buf], (uint32_t)(TH * TW * sizeof(T)));
+      st_tma_load_2d(base + buf * TILE_BYTES, &tile_map, x0, b * SH + y0, &tile_bar[buf]);
+    }
+  };
+  prefetch(blockIdx.x, 0);
+  int buf = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    int b, y0, x0;
+    const bool bulk = locate(t, b, y0, x0);
     const T* plane = src + (int64_t)b * in_plane;
-    if (use_tma) st_fence_async();          // patches of the previous tile before the next bulk copy
+    T* tile = reinterpret_cast<T*>(base + buf * TILE_BYTES);    // TH x TW
+    // every thread is done with the other buffer (tile t - gridDim.x): its next tile may land
+    if (use_tma) st_fence_async();
     __syncthreads();
-    // phase 1: the tile with its halo; tiles that lie inside the array (all but the last
-    // row / column of tiles) skip every bound test
-    if (use_tma && x0 + TW <= SW && y0 + TH <= SH) {
-      // one bulk tensor copy for the whole TH x TW tile (bands are stacked along y in the map)
-      if (threadIdx.x == 0) {
-        st_mbar_expect_tx(&tile_bar, (uint32_t)(TH * TW * sizeof(T)));
-        st_tma_load_2d(tile, &tile_map, x0, b * SH + y0, &tile_bar);
-      }
-      st_mbar_wait(&tile_bar, tile_phase);
-      tile_phase ^= 1u;
+    prefetch(t + gridDim.x, buf ^ 1);
+    if (bulk) {
+      st_mbar_wait(&tile_bar[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
       if (has_nodata) {     // "no data" -> lowest, in place, a quad at a time
         constexpr int QUADS = TH * TW / 4;
         for (int i = threadIdx.x; i < QUADS; i += 256) {
@@ -631,113 +691,96 @@ moving_max_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, T nodata,
           if (hit) sts_quad<T>(tile + 4 * i, q);
         }
       }
-    } else if (x0 + TW <= SW && y0 + TH <= SH) {
-      constexpr int ITEMS = TH * TW, PER = (ITEMS + 255) / 256;
-      const T* origin = plane + (int64_t)y0 * SW + x0;
-      T raw[PER];
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int i = threadIdx.x + 256 * k;
-        const int ty = i / TW, tx = i - ty * TW;
-        raw[k] = i < ITEMS ? __ldg(origin + (int64_t)ty * SW + tx) : lowest;
-      }
-#pragma unroll
-      for (int k = 0; k < PER; ++k) {
-        const int i = threadIdx.x + 256 * k;
-        if (i < ITEMS) tile[i] = (has_nodata && raw[k] == nodata) ? lowest : raw[k];
-      }
     } else {
+      // clamped loads, four tile rows in flight per warp
       constexpr int NJ = (TW + 31) / 32;
-      for (int ty = warp; ty < TH; ty += 16) {
-        T raw[2][NJ];
+      for (int ty = warp; ty < TH; ty += 32) {
+        T raw[4][NJ];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
           const int gy = min(y0 + ty + 8 * h, SH - 1);
 #pragma unroll
           for (int j = 0; j < NJ; ++j)
             raw[h][j] = __ldg(plane + (int64_t)gy * SW + min(x0 + lane + 32 * j, SW - 1));
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 4; ++h) {
           const int row = ty + 8 * h;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             const int tx = lane + 32 * j;
-            const bool inside = y0 + row < SH && x0 + tx < SW;
-            const T v = (!inside || (has_nodata && raw[h][j] == nodata)) ? lowest : raw[h][j];
+            const bool in = y0 + row < SH && x0 + tx < SW;
+            const T v = (!in || (has_nodata && raw[h][j] == nodata)) ? lowest : raw[h][j];
             if (tx < TW && row < TH) tile[row * TW + tx] = v;
           }
         }
       }
     }
-    __syncthreads();
-    // phase 2: chord maxima of four pixels per thread
-    for (int item = threadIdx.x; item < TH * SEGS; item += 256) {
-      const int ty = item / SEGS, seg = item - ty * SEGS;
-      T w[4 * NQ];
+    if (has_nodata || !bulk) __syncthreads();
+    const int ty0 = warp * MMB_ROWS, x = x0 + 4 * lane;
+    if (y0 + ty0 >= H || x >= W) continue;
+    T best[MMB_ROWS][4];
 #pragma unroll
-      for (int k = 0; k < NQ; ++k) {
-        const Quad<T> q = lds_quad<T>(tile + ty * TW + 4 * seg + 4 * k);
+    for (int j = 0; j < MMB_ROWS; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[4 * k + i] = q.v[i];
-      }
-      T m[4];
+      for (int i = 0; i < 4; ++i) best[j][i] = lowest;
+    walk_rows<T, SIZE, TW, 0>(tile + ty0 * TW + 4 * lane, best);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) m[i] = w[R + i];
-      chord_quads<T, SIZE, 0>(w, m, chord + ty * MM2_TX + 4 * seg, PLANE);
-    }
-    __syncthreads();
-    // phase 3: the disc = one chord per footprint row
-    for (int item = threadIdx.x; item < MM2_TY * SEGS; item += 256) {
-      const int ty = item / SEGS, seg = item - ty * SEGS;
-      const int y = y0 + ty, x = x0 + 4 * seg;
-      if (y >= H || x >= W) continue;
-      T best[4] = {lowest, lowest, lowest, lowest};
-      disc_quads<T, SIZE, -R>(chord + ty * MM2_TX + 4 * seg, PLANE, best);
-      // restore no data only where the centre was no data and nothing was found (rare:
-      // one test for the quad)
-      if (has_nodata && vmin4(best) == lowest) {
+    for (int j = 0; j < MMB_ROWS; ++j) {
+      const int y = y0 + ty0 + j;
+      if (y >= H) break;
+      // restore no data only where the centre was no data and nothing was found (rare: one test
+      // for the quad)
+      if (has_nodata && vmin4(best[j]) == lowest) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (best[i] == lowest && x + i < W &&
+          if (best[j][i] == lowest && x + i < W &&
               __ldg(plane + (int64_t)(y + R) * SW + (x + i + R)) == nodata)
-            best[i] = nodata;
+            best[j][i] = nodata;
       }
       T* o = dst + (int64_t)b * out_plane + (int64_t)y * W + x;
       if (dst_aligned && x + 3 < W) {
         Quad<T> q;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) q.v[i] = best[i];
+        for (int i = 0; i < 4; ++i) q.v[i] = best[j][i];
         uint4 u;
         memcpy(&u, &q, 16);
-        *reinterpret_cast<uint4*>(o) = u;
+        __stcs(reinterpret_cast<uint4*>(o), u);
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (x + i < W) o[i] = best[i];
+          if (x + i < W) o[i] = best[j][i];
       }
     }
   }
 }
 
 template <typename T, int SIZE>
-static int launch_moving_max_quad(const Staged& in, Staged& out, T nd, int has_nodata, int bands,
-                                  int H, int W, int SW, cudaStream_t s) {
+static int launch_moving_max_block(const Staged& in, Staged& out, T nd, int has_nodata, int bands,
+                                   int H, int W, int SW, cudaStream_t s) {
   constexpr int R = Disc<SIZE>::R;
   constexpr int NQ = (4 + 2 * R + 3) / 4;
-  constexpr int TW = MM2_TX - 4 + 4 * NQ, TH = MM2_TY + 2 * R;
-  const size_t smem = ((size_t)TW * TH + (size_t)Disc<SIZE>::n_planes() * TH * MM2_TX) * sizeof(T) + 128;
-  auto kernel = moving_max_quad_kernel<T, SIZE>;
-  if (smem > 48 * 1024)
-    GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int TW = MMB_TX - 4 + 4 * NQ, TH = MMB_TY + 2 * R;
+  constexpr size_t TILE_BYTES = ((size_t)TW * TH * sizeof(T) + 127) / 128 * 128;
+  const size_t smem = 2 * TILE_BYTES + 128;
+  auto kernel = moving_max_block_kernel<T, SIZE>;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    GM_CUDA(cudaGetDevice(&dev));
+    GM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int aligned = ((uintptr_t)out.dev % 16 == 0) && (W % 4 == 0);
   static_assert((TW * TH) % 4 == 0 && (TW * sizeof(T)) % 16 == 0, "tile rows are whole 16-byte groups");
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   const int SH = H + 2 * R;
   const int use_tma = make_tile_map(&map, in.dev, (int64_t)bands * SH, SW, SW, TH, TW, std::is_same<T, float>::value);
-  kernel<<<grid3(W, H, bands, MM2_TX, MM2_TY), 256, smem, s>>>((const T*)in.dev, (T*)out.dev, nd,
-                                                               has_nodata, bands, H, W, SW, aligned, use_tma, map);
+  const int64_t n_tiles = (int64_t)((W + MMB_TX - 1) / MMB_TX) * ((H + MMB_TY - 1) / MMB_TY) * bands;
+  const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)sms);
+  kernel<<<grid, 256, smem, s>>>((const T*)in.dev, (T*)out.dev, nd, has_nodata, bands, H, W, SW, aligned,
+                                 use_tma, map);
   GM_LAUNCH_CHECK();
   return 0;
 }
@@ -751,7 +794,7 @@ static int try_moving_max_fixed(int size, const Staged& in, Staged& out, T nd, i
                 std::is_same<T, int32_t>::value) {
     if constexpr (sizeof(T) == 4) {
       switch (size) {
-#define GM_CASE(N) case N: return launch_moving_max_quad<T, N>(in, out, nd, has_nodata, bands, H, W, SW, s);
+#define GM_CASE(N) case N: return launch_moving_max_block<T, N>(in, out, nd, has_nodata, bands, H, W, SW, s);
         GM_CASE(3) GM_CASE(5) GM_CASE(7) GM_CASE(9) GM_CASE(11) GM_CASE(13) GM_CASE(15)
 #undef GM_CASE
         default: break;

@@ -90,7 +90,7 @@ def test_moving_max_padded_pitch(dtype, size, pad):
     """Windows whose rows are whole 16-byte groups (with `pad` extra columns on the right) take
     the TMA tile staging for interior tiles; the padding never enters a footprint."""
     r = size // 2
-    h, w = 150, 201 + ((-(201 + 2 * r + pad)) % 4)       # (w + 2 r + pad) % 4 == 0: TMA eligible
+    h, w = 215, 401 + ((-(401 + 2 * r + pad)) % 4)       # (w + 2 r + pad) % 4 == 0: TMA eligible
     values, nodata = dem((2, h + 2 * r, w + 2 * r), 9, dtype=dtype, nodata_fraction=0.05)
     expected, _ = R.moving_max(values, nodata, size)
     padded = np.full((2, h + 2 * r, w + 2 * r + pad), nodata, dtype=values.dtype)

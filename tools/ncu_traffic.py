@@ -104,7 +104,6 @@ PER_LAUNCH = {
     "temporal_median": "temporal_sort_reg_kernel<float",
     "cumulative_sum": "temporal_cumulative_stream_kernel<float",
     "smooth_fast_kernel": "smooth_fast_kernel<float",
-    "moving_max_quad_kernel": "moving_max_quad_kernel<float",
     "moving_max_block_kernel": "moving_max_block_kernel<float",
     "hillshade_quad_kernel": "hillshade_quad_kernel<float",
 }

@@ -28,7 +28,7 @@ full zonal_select_main zonal_select_main 3 python tools/bench_kernels.py --only 
 full zonal_select_final zonal_select_final 3 python tools/bench_kernels.py --only zonal_p90 --zonal-size 40000 --zonal-grid 316 --iters 3
 full rasterize_tile rasterize_tile 2 python tools/bench_kernels.py --only rasterize --iters 3
 full smooth_fast smooth_fast 2 python tools/bench_kernels.py --only smooth --scale 2 --iters 3
-full moving_max_quad moving_max_quad 2 python tools/bench_kernels.py --only movingmax_11 --scale 2 --iters 3
+full moving_max_block moving_max_block 2 python tools/bench_kernels.py --only movingmax_11 --scale 2 --iters 3
 full hillshade_quad hillshade_quad 2 python tools/bench_kernels.py --only hillshade --scale 2 --iters 3
 full temporal_stream temporal_stream 2 python tools/bench_kernels.py --only temporal_sum --temporal-frames 64 --temporal-size 8192 --temporal-stats sum --iters 4
 full temporal_cumulative temporal_cumulative_stream 2 python bench.py --steps 5 --warmup 3 --legs chain,temporal --temporal-frames 64 --size 4096
