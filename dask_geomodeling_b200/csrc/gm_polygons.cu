@@ -1615,8 +1615,9 @@ __device__ __noinline__ int row_crossings(const double* px, const double* py, co
 //   main kernel      the pass over all cells -> counts + the bracket's cells in the polygon's table
 //                    (polygons with an exact histogram are finished here)
 //   final kernel     ranks among the table's cells -> out[p]
-// Polygons are processed in chunks so that the tables (WS_CAP x 32 words + 32 counts each) stay
-// bounded and L2-warm between the main and the final kernel.
+// Polygons are processed in chunks of at most 131072 (GM_SELECT_CHUNK) so that the tables
+// (WS_CAP x 32 words + 32 counts each, 2.2 GB per chunk) stay bounded; cfg4 is one chunk -- with
+// four chunks of 32768 the tails of twelve launches cost 0.3 ms of 3.3.
 enum { WS_SKIP = 0, WS_TABLE = 1, WS_EXACT = 2 };
 struct SelectState { unsigned lo, hi; int what; int n_active; int below; int kept; };
 constexpr int WS_TABLE_WORDS = WS_CAP * 32 + 32;     // cells + per-lane counts
@@ -2544,7 +2545,8 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       // polygons; the bracket's cells of a chunk wait in per-polygon tables between the last two
       GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
       GM_TRY(cudaMemsetAsync(dlist, 0, 2 * sizeof(int), s));
-      const int64_t chunk = np_ < 32768 ? np_ : 32768;
+      static const int64_t chunk_cap = getenv("GM_SELECT_CHUNK") ? atoll(getenv("GM_SELECT_CHUNK")) : 131072;
+      const int64_t chunk = np_ < chunk_cap ? np_ : chunk_cap;
       const int64_t n_chunks = (np_ + chunk - 1) / chunk;
       void *dstate = nullptr, *dcounters = nullptr;
       GM_TRY(cudaMallocAsync(&dstate, sizeof(SelectState) * np_, s));

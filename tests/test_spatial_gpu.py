@@ -57,6 +57,29 @@ def test_smooth_exact(dtype, size_px):
     np.testing.assert_array_equal(got["values"], expected)
 
 
+@pytest.mark.parametrize("mode,ulps", [("fma", 1), ("float32", 16)])
+@pytest.mark.parametrize("dtype", ["f4", "f8"])
+def test_smooth_arithmetic_modes(mode, ulps, dtype):
+    """The two relaxed arithmetics of the tap sums (gm_set_smooth_mode; the default is 'fma'):
+    stated tolerance 1e-6 of the value range; 'fma' differs from SciPy only
+    by the rounding of the fused multiply-adds (at most the last bit of a float32 result)."""
+    from dask_geomodeling_b200 import _native
+
+    values, nodata = dem((2, 150, 333), 5, dtype=dtype)
+    kwargs = dict(smooth_mode="exact", fill=0, size=[5.0, 5.0])
+    expected, _ = R.smooth(values, nodata, (5.0, 5.0), 0, "exact")
+    with _native.smooth_arithmetic(mode):
+        got = np.asarray(raster.Smooth.process({"values": values, "no_data_value": nodata}, kwargs)["values"])
+    data = values[values != nodata]
+    value_range = float(data.max() - data.min())
+    delta = np.abs(got.astype("f8") - expected.astype("f8"))
+    assert delta.max() <= 1e-6 * value_range
+    if dtype == "f4":
+        assert delta.max() <= ulps * np.spacing(np.float32(np.abs(expected).max()))
+    if mode == "fma" and dtype == "f4":
+        assert (delta > 0).mean() < 0.05
+
+
 @pytest.mark.parametrize("fill", [0, 7.5])
 def test_smooth_zoom(fill):
     values, nodata = dem((1, 64, 80), 4)
