@@ -610,9 +610,31 @@ def run_temporal(ctx):
             "roofline": ctx.roofline(2 * px64 * 4, ms, "temporal_cumulative_stream_kernel", traffic_key="cumulative_sum"),
             "bytes": "2 * T * itemsize per pixel (every frame read once, every running sum written once)"}
         del sub
-    resident.__exit__(None, None, None)
     del stack, sd, whole
     torch.cuda.empty_cache()
+    if ctx.world == 1:
+        # the int16 variant of cfg5: the same stack shape, 2-byte cells, no data = 32767
+        i16 = torch.empty((T, m, m), dtype=torch.int16, device="cuda")
+        gen = torch.Generator(device="cuda").manual_seed(301)
+        for a in range(0, T, 8):
+            block = i16[a:a + 8]
+            block.copy_(torch.randint(0, 1000, block.shape, device="cuda", generator=gen, dtype=torch.int16))
+            block[torch.rand(block.shape, device="cuda", generator=gen) < 0.03] = 32767
+            del block
+        si = wrap(i16)
+        for stat, out_bytes in (("sum", 4), ("max", 2)):
+            kw = kwargs_for(stat, dtype="i4" if stat == "sum" else "i2")
+            ms, launches, _ = ctx.time_calls(lambda kw=kw: raster.TemporalAggregate.process(
+                kw, {"time": times}, {"values": si, "no_data_value": 32767}), iters)
+            nb = T * m * m * 2 + m * m * out_bytes
+            out["{}_int16".format(stat)] = {
+                "ms": ms, "gpx_s": px / ms / 1e6, "gpu_launches_per_call": launches,
+                "roofline": ctx.roofline(nb, ms, "temporal_stream_kernel<short, {}>".format(stat),
+                                         traffic_key="temporal_{}_int16".format(stat)),
+                "bytes": "T * 2 in + out itemsize per pixel"}
+        del i16, si
+        torch.cuda.empty_cache()
+    resident.__exit__(None, None, None)
     return out
 
 
