@@ -729,9 +729,16 @@ static int run_temporal(const GmArray* src, GmArray* dst, const void* nodata, in
   a.bins = (const int*)dbins; a.frames = (const int*)dframes; a.out_frame = (const int*)dout;
   if (!rc && a.plane > 0 && array_count(*dst) > 0) {
     if (CUMULATIVE) {
-      // frames that belong to no bin keep the (extensive) fill 0
-      cudaError_t e = cudaMemsetAsync(out.dev, 0, out.bytes, s);
-      if (e != cudaSuccess) rc = fail("temporal: memset failed");
+      // output frames that no bin writes keep the (extensive) fill 0; the others are written in
+      // full by the kernel (clearing all T frames first cost as much as half the kernel)
+      std::vector<char> written((size_t)dst->shape[0], 0);
+      for (int i = 0; i < n_frames; ++i)
+        if (out_frame[i] >= 0 && out_frame[i] < dst->shape[0]) written[out_frame[i]] = 1;
+      const size_t frame_bytes = out.bytes / (size_t)dst->shape[0];
+      for (int64_t f = 0; f < dst->shape[0] && !rc; ++f)
+        if (!written[f] &&
+            cudaMemsetAsync((char*)out.dev + (size_t)f * frame_bytes, 0, frame_bytes, s) != cudaSuccess)
+          rc = fail("temporal: memset failed");
     }
     if (!rc) rc = dispatch_src<CUMULATIVE>(src->dtype, dst->dtype, in, out, a, s);
   }

@@ -100,6 +100,8 @@ PER_LAUNCH = {
     "temporal_sum": "temporal_stream_kernel<float, float, float, 0>",
     "temporal_max": "temporal_stream_kernel<float, float, float, 3>",
     "temporal_mean": "temporal_stream_kernel<float, float, float, 4>",
+    "temporal_sum_int16": "temporal_stream_kernel<short, double, int, 0>",
+    "temporal_max_int16": "temporal_stream_kernel<short, float, short, 3>",
     "temporal_std": "temporal_moments_stream_kernel<float",
     "temporal_median": "temporal_sort_reg_kernel<float",
     "cumulative_sum": "temporal_cumulative_stream_kernel<float",
