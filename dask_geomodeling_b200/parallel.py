@@ -616,27 +616,25 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
         near_soup.to_device()
     tensor = _as_tensor(local) if r1 > r0 else None
     stripe_bbox = (x1, y2 - r1 * dy, x2, y2 - r0 * dy)
-    # owners publish their results and covered-cell counts in one all-gather of a (2, N) block:
-    # row 0 the statistic of the polygons this rank owns (others stay 0), row 1 their covered
-    # cells.  Page-locked staging buffers and the owner -> slot index are kept with the soup.
+    # owners publish their results in one all-gather of a (2, N) float32 block: row 0 the
+    # statistic of the polygons this rank owns (others stay 0), row 1 whether they cover any cell
+    # (all the caller needs of the counts: polygons without cells take the centroid fallback).
+    # Under NCCL the owners' entries are picked on the device, so only (2, N) floats come back to
+    # the host however many ranks there are.  Page-locked staging buffers and the owner -> slot
+    # index are kept with the soup.
     dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     key = (tuple(bbox), int(height), int(world), dev)
     buffers = getattr(soup, "_gather_buffers", None)
     if buffers is None or buffers[0] != key:
         top, bottom = _polygon_rows(soup, bbox, height)
-        stage_in = torch.empty((2, n), dtype=torch.float64)
-        stage_out = torch.empty((world, 2, n), dtype=torch.float64)
+        stage_in = torch.empty((2, n), dtype=torch.float32)
+        stage_out = torch.empty((2, n), dtype=torch.float32)
         if dev == "cuda":
             stage_in, stage_out = stage_in.pin_memory(), stage_out.pin_memory()
-        # polygons usually come sorted by position: the owners then form a few runs of ids and
-        # the results are picked run by run (slices) instead of through a 100 k-entry index
-        cuts = np.flatnonzero(np.diff(owner)) + 1
-        starts = np.concatenate([[0], cuts]) if n else np.zeros(0, dtype=np.int64)
-        stops = np.concatenate([cuts, [n]]) if n else np.zeros(0, dtype=np.int64)
-        runs = [(int(owner[a]), int(a), int(b)) for a, b in zip(starts, stops)] if len(starts) <= 4096 else None
-        pick = owner.astype(np.int64) * (2 * n) + np.arange(n)
-        buffers = soup._gather_buffers = (key, stage_in, stage_out, pick, (bottom < 0) | (top > height - 1), runs)
-    _, stage_in, stage_out, pick, nowhere, runs = buffers
+        pick = torch.from_numpy(owner.astype(np.int64) * (2 * n) + np.arange(n))
+        pick = torch.stack([pick, pick + n]).to(dev)
+        buffers = soup._gather_buffers = (key, stage_in, stage_out, pick, (bottom < 0) | (top > height - 1))
+    _, stage_in, stage_out, pick, nowhere = buffers
     mine = stage_in.numpy()
     mine[...] = 0
 
@@ -658,7 +656,7 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
     if r1 > r0 and len(inside_ids):
         got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
                                     statistic, percentile)
-        mine[0, inside_ids], mine[1, inside_ids] = got, cov
+        mine[0, inside_ids], mine[1, inside_ids] = got, cov > 0
     _trace("select inside the stripe")
     for work in pending:
         work.wait()
@@ -670,29 +668,21 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
             torch.cuda.current_stream().synchronize()   # the strip is complete before the library reads it
         got, cov = _order_stat_call(near_soup, _as_payload(strip), no_data_value, strip_bbox,
                                     thresholds_of(near_ids), statistic, percentile)
-        mine[0, near_ids], mine[1, near_ids] = got, cov
+        mine[0, near_ids], mine[1, near_ids] = got, cov > 0
     _trace("select on the boundary strip")
     block = stage_in.to(dev, non_blocking=True)
     gathered = torch.empty((world,) + tuple(block.shape), dtype=block.dtype, device=dev)
     if dev == "cuda":
         dist.all_gather_into_tensor(gathered, block, group=group)
-        stage_out.copy_(gathered, non_blocking=True)
+        stage_out.copy_(gathered.reshape(-1)[pick], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         table = stage_out.numpy()
     else:
         dist.all_gather(list(gathered.unbind(0)), block, group=group)
-        table = gathered.numpy()
+        table = gathered.reshape(-1)[pick].numpy()
     _trace("all-gather + download")
-    if runs is not None:
-        result = np.empty(n, dtype=np.float32)
-        covered = np.empty(n, dtype=np.int64)
-        for who, a, b in runs:
-            result[a:b] = table[who, 0, a:b]
-            covered[a:b] = table[who, 1, a:b]
-    else:
-        flat = table.reshape(-1)
-        result = flat[pick].astype(np.float32)
-        covered = flat[pick + n].astype(np.int64)
+    result = table[0].copy()
+    covered = table[1].astype(np.int64)       # 0 / 1: only "covers no cell" is reported
     result[nowhere] = np.nan          # outside the raster: nobody selected them
     covered[nowhere] = 0
     if far.any():   # same on every rank: the collectives inside line up
