@@ -160,8 +160,8 @@ def _streamable_source(task):
     if type(task) is not tuple or len(task) != 2 or task[0] is not RasterSourceBase.process:
         return None
     kw = task[1]
-    if not isinstance(kw, dict) or kw.get("mode") != "vals":
-        return None
+    if not isinstance(kw, dict) or kw.get("mode") != "vals" or "array" not in kw:
+        return None    # (file sources decode their window first: not part of the chunk pipeline)
     bbox = kw["bbox"]
     if bbox[0] == bbox[2] or bbox[1] == bbox[3] or kw["width"] == 0 or kw["height"] == 0:
         return None

@@ -57,6 +57,13 @@ class RasterBlock(Block):
 
         return Invert(self)
 
+    def to_file(self, *args, **kwargs):
+        """Export this block to tiled GeoTIFFs + a VRT: ``to_file(url, tile_size, **request)``
+        (raster/base.py:51-73, raster/sinks.py:148-204)."""
+        from .sinks import to_file
+
+        return to_file(self, *args, **kwargs)
+
     def __len__(self):
         """Number of frames on the time axis."""
         period = self.period

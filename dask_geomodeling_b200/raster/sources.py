@@ -1,4 +1,4 @@
-"""In-memory raster source feeding the CUDA path.
+"""Raster sources feeding the CUDA path: arrays in host memory and GeoTIFF / VRT files.
 
 ``MemorySource`` keeps the reference's constructor, attributes and request
 handling (raster/sources.py:157-393).  Its ``process`` replaces the GDAL
@@ -7,17 +7,22 @@ source window the request touches (pinned host memory -> HBM), followed by a
 nearest-neighbour gather kernel that also pads with no data outside the
 source.  For aligned requests this equals the crop/pad GDAL produces.
 Requests in another projection than the source need GDAL/pyproj and raise.
+
+``RasterFileSource`` (raster/sources.py:396-564) reads a GeoTIFF or VRT without GDAL
+(``dask_geomodeling_b200/geotiff.py``): only the tiles under the requested window are inflated,
+then the window takes the same upload + gather path.
 """
 import ctypes
+import os
 from datetime import datetime, timedelta, timezone
 
 import numpy as np
 
-from .. import _native, _state, utils
+from .. import _native, _state, geotiff, utils
 from .._compat import config
 from .base import RasterBlock
 
-__all__ = ["MemorySource"]
+__all__ = ["MemorySource", "RasterFileSource"]
 
 
 def utc_from_ms_timestamp(timestamp):
@@ -81,18 +86,29 @@ def resident_copy(array):
     return copy
 
 
+def source_window(geo_transform, bbox, height, width, src_h, src_w):
+    """(r_lo, r_hi, c_lo, c_hi): the cells of a (src_h, src_w) source that a request reads."""
+    col0, col_step, row0, row_step = window_geometry(geo_transform, bbox, height, width)
+    c_lo, c_hi = _window(width, col0, col_step, src_w)
+    r_lo, r_hi = _window(height, row0, row_step, src_h)
+    return r_lo, max(r_hi, r_lo), c_lo, max(c_hi, c_lo)
+
+
 def resample_window(array, bands, geo_transform, no_data_value, bbox, height, width, keep_on_device,
-                    row_range=None):
+                    row_range=None, origin=(0, 0)):
     """Nearest-neighbour resample of ``array[bands[0]:bands[1]]`` into the request grid.
 
     ``row_range=(r0, r1)`` produces only rows [r0, r1) of the request (used by the chunk
-    pipeline for pixel-aligned requests, where row_step == 1 keeps the arithmetic exact)."""
+    pipeline for pixel-aligned requests, where row_step == 1 keeps the arithmetic exact).
+    ``origin=(row, col)``: ``array`` holds only the part of the source that starts at that cell
+    (a window decoded from a file); ``geo_transform`` is still the whole source's."""
     lib = _native.lib()
     stream = _native.current_stream()
     b0, b1 = bands
     n_bands = b1 - b0
     _, src_h, src_w = array.shape
     col0, col_step, row0, row_step = window_geometry(geo_transform, bbox, height, width)
+    row0, col0 = row0 - origin[0], col0 - origin[1]
     if row_range is not None:
         row0 = row0 + row_range[0] * row_step
         height = row_range[1] - row_range[0]
@@ -164,22 +180,34 @@ class RasterSourceBase(RasterBlock):
         if mode == "time":
             start, delta = process_kwargs["start"], process_kwargs["delta"]
             return {"time": [start + i * delta for i in range(b1 - b0)]}
+        dataset = None
+        if "url" in process_kwargs:      # coming from a RasterFileSource block
+            dataset = open_dataset(utils.safe_abspath(process_kwargs["url"]))
         if mode == "meta":
+            if dataset is not None:
+                return {"meta": [dataset.metadata(i) for i in range(b0, b1)]}
             return {"meta": list(process_kwargs["metadata"][b0:b1])}
 
-        array = process_kwargs["array"]
+        array = process_kwargs.get("array")
         dtype = process_kwargs["dtype"]
         bbox = process_kwargs["bbox"]
         width, height = process_kwargs["width"], process_kwargs["height"]
-        no_data_value = process_kwargs["fillvalue"].item()
+        fillvalue = process_kwargs["fillvalue"]
+        # (a file without a no data tag: the dtype's maximum marks the cells outside it)
+        no_data_value = utils.get_dtype_max(dtype) if fillvalue is None else fillvalue.item()
         if width == 0 or height == 0:
             return np.empty((b1 - b0, height, width), dtype=dtype)
+        if dataset is not None:
+            process_kwargs = dict(process_kwargs, source_projection=dataset.projection,
+                                  geo_transform=dataset.geo_transform)
         if not utils.same_projection(process_kwargs["projection"], process_kwargs["source_projection"]):
             raise NotImplementedError(
-                "MemorySource: reprojection {} -> {} needs GDAL and is outside the CUDA raster "
+                "raster source: reprojection {} -> {} needs GDAL and is outside the CUDA raster "
                 "path".format(process_kwargs["source_projection"], process_kwargs["projection"])
             )
         geo_transform = utils.GeoTransform(process_kwargs["geo_transform"])
+        if dataset is not None:
+            return _file_values(dataset, (b0, b1), geo_transform, dtype, no_data_value, bbox, height, width)
 
         if bbox[0] == bbox[2] or bbox[1] == bbox[3]:
             # point request: the cell that contains the point (raster/sources.py:95-117)
@@ -200,6 +228,46 @@ class RasterSourceBase(RasterBlock):
             _state.keep_on_device(),
         )
         return {"values": values, "no_data_value": no_data_value}
+
+
+_DATASETS = {}
+
+
+def open_dataset(path):
+    """Header of a GeoTIFF / VRT file, kept until the file changes on disk."""
+    stat = os.stat(path)
+    key = (stat.st_mtime_ns, stat.st_size)
+    hit = _DATASETS.get(path)
+    if hit is None or hit[0] != key:
+        if len(_DATASETS) >= 64:
+            _DATASETS.clear()
+        hit = _DATASETS[path] = (key, geotiff.open_raster(path))
+    return hit[1]
+
+
+def _file_values(dataset, bands, geo_transform, dtype, no_data_value, bbox, height, width):
+    """'vals' response of a file source: point requests read one cell, other requests inflate the
+    tiles under their window and resample it on the device."""
+    b0, b1 = bands
+    n_all, src_h, src_w = dataset.shape
+    if bbox[0] == bbox[2] or bbox[1] == bbox[3]:
+        rows, cols = geo_transform.get_indices(np.array([[bbox[0], bbox[1]]]))
+        i, j = int(rows[0]), int(cols[0])
+        result = np.full((b1 - b0, 1, 1), no_data_value, dtype=dtype)
+        if 0 <= i < src_h and 0 <= j < src_w:
+            result[:, 0, 0] = dataset.read_window(b0, b1, i, i + 1, j, j + 1)[:, 0, 0]
+        if result.dtype.kind == "f":
+            result[~np.isfinite(result)] = no_data_value
+        return {"values": result, "no_data_value": no_data_value}
+    r_lo, r_hi, c_lo, c_hi = source_window(geo_transform, bbox, height, width, src_h, src_w)
+    window = dataset.read_window(b0, b1, r_lo, r_hi, c_lo, c_hi)
+    if window.dtype != dtype:
+        window = window.astype(dtype)
+    if window.size == 0:     # nothing of the file under the request: all no data
+        window = np.empty((b1 - b0, 0, 0), dtype=dtype)
+    values = resample_window(window, (0, b1 - b0), geo_transform, no_data_value, bbox, height, width,
+                             _state.keep_on_device(), origin=(r_lo, c_lo))
+    return {"values": values, "no_data_value": no_data_value}
 
 
 class MemorySource(RasterSourceBase):
@@ -338,6 +406,117 @@ class MemorySource(RasterSourceBase):
         elif mode == "time":
             kwargs = {"mode": "time", "start": start, "delta": self.timedelta or timedelta(0),
                       "bands": bands}
+        else:
+            raise RuntimeError("Unknown mode '{}'".format(mode))
+        return [(kwargs, None)]
+
+
+class RasterFileSource(RasterSourceBase):
+    """A raster source that interfaces data from a file path (GeoTIFF or VRT).
+
+    The value at raster cell with its topleft corner at [x, y] is assumed to define a value for
+    ranges [x, x + dx) and (y - dy, y].
+
+    :param url: the path to the file, inside the ``geomodeling.root`` setting when relative
+    :param time_first: the timestamp of the first frame (ms since 1-1-1970 or datetime)
+    :param time_delta: the difference between two consecutive frames (ms or timedelta),
+        defaults to 5 minutes
+
+    The object keeps the parsed file header; ``close_dataset`` drops it.
+    """
+
+    def __init__(self, url, time_first=0, time_delta=300000):
+        url = utils.safe_file_url(url)
+        time_first = utils.dt_to_ms(time_first) if isinstance(time_first, datetime) else int(time_first)
+        if isinstance(time_delta, timedelta):
+            time_delta = int(time_delta.total_seconds() * 1000)
+        else:
+            time_delta = int(time_delta)
+        super().__init__(url, time_first, time_delta)
+
+    url = property(lambda self: self.args[0])
+    time_first = property(lambda self: self.args[1])
+    time_delta = property(lambda self: self.args[2])
+
+    @property
+    def dataset(self):
+        try:
+            return self._dataset
+        except AttributeError:
+            self._dataset = open_dataset(utils.safe_abspath(self.url))
+            return self._dataset
+
+    gdal_dataset = dataset     # the reference's name for the open file
+
+    def close_dataset(self):
+        if hasattr(self, "_dataset"):
+            del self._dataset
+
+    @property
+    def projection(self):
+        return self.dataset.projection
+
+    @property
+    def dtype(self):
+        return self.dataset.dtype
+
+    @property
+    def fillvalue(self):
+        value = self.dataset.no_data_value
+        return None if value is None else self.dtype.type(value)
+
+    @property
+    def geo_transform(self):
+        return utils.GeoTransform(self.dataset.geo_transform)
+
+    def _get_extent(self):
+        bbox = self.geo_transform.get_bbox((0, 0), (self.dataset.height, self.dataset.width))
+        return utils.Extent(bbox, self.projection)
+
+    @property
+    def extent(self):
+        return self._get_extent().transformed("EPSG:4326").bbox
+
+    @property
+    def geometry(self):
+        return self._get_extent().as_geometry()
+
+    def __len__(self):
+        return self.dataset.bands
+
+    @property
+    def period(self):
+        n = len(self)
+        if n == 0:
+            return None
+        first = utc_from_ms_timestamp(self.time_first)
+        return (first, first) if n == 1 else (first, first + (n - 1) * self.timedelta)
+
+    @property
+    def timedelta(self):
+        return None if len(self) <= 1 else timedelta(milliseconds=self.time_delta)
+
+    @property
+    def temporal(self):
+        return len(self) > 1
+
+    def get_sources_and_requests(self, **request):
+        mode = request["mode"]
+        start, stop, first_i, last_i = utils.snap_start_stop(
+            request.get("start"), request.get("stop"),
+            utc_from_ms_timestamp(self.time_first), self.timedelta, len(self),
+        )
+        if start is None:
+            return [({"mode": "empty_" + mode}, None)]
+        bands = (first_i, last_i + 1)
+        if mode == "vals":
+            kwargs = {"mode": "vals", "url": self.url, "bbox": request["bbox"], "width": request["width"],
+                      "height": request["height"], "projection": request["projection"], "bands": bands,
+                      "dtype": self.dtype, "fillvalue": self.fillvalue}
+        elif mode == "meta":
+            kwargs = {"mode": "meta", "url": self.url, "bands": bands}
+        elif mode == "time":
+            kwargs = {"mode": "time", "start": start, "delta": self.timedelta or timedelta(0), "bands": bands}
         else:
             raise RuntimeError("Unknown mode '{}'".format(mode))
         return [(kwargs, None)]

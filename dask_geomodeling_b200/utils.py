@@ -6,7 +6,9 @@ works without GDAL/pyproj: projections are compared by their normalised
 string, and anything that needs an actual coordinate transformation raises.
 """
 import math
+import os
 import re
+import warnings
 from datetime import timedelta
 
 import numpy as np
@@ -699,6 +701,40 @@ def rasterize_geoseries(geoseries, bbox, projection, height, width, values=None,
         )
     )
     return _finalize_rasterize_result(array, no_data_value)
+
+
+def safe_file_url(url, start=None):
+    """``file://`` URL with an absolute path: relative paths are taken from ``geomodeling.root``,
+    other protocols raise NotImplementedError, and with ``geomodeling.strict-file-paths`` the path
+    must lie inside the root (reference utils.py:767-807)."""
+    from ._compat import config
+
+    try:
+        protocol, path = url.split("://")
+    except ValueError:
+        protocol, path = "file", url
+    else:
+        if protocol != "file":
+            raise NotImplementedError('Unknown protocol: "{}"'.format(protocol))
+    if start is not None:
+        warnings.warn("Using the start argument in safe_file_url is deprecated. Use the "
+                      "'geomodeling.root' in the dask config", DeprecationWarning)
+    else:
+        start = config.get("geomodeling.root")
+    if not os.path.isabs(path):
+        if start is None:
+            raise IOError("Relative path '{}' provided but start was not given.".format(path))
+        abspath = os.path.abspath(os.path.join(start, path))
+    else:
+        abspath = os.path.abspath(path)
+    if config.get("geomodeling.strict-file-paths") and not abspath.startswith(start):
+        raise IOError("'{}' is not contained in '{}'".format(path, start))
+    return "://".join([protocol, abspath])
+
+
+def safe_abspath(url, start=None):
+    """The path of ``safe_file_url`` without the protocol (reference utils.py:759-764)."""
+    return safe_file_url(url, start).split("://")[1]
 
 
 def offset_to_timedelta(freq):
