@@ -161,7 +161,7 @@ SYMBOLS = {
     "gm_segment_order_stat": (_i, [_vp, ctypes.c_int32, _vp, _i64, _i, _d, _vp, _vp]),
     "gm_zonal_partials_device": (_i, [_P(GmArray), _vp, _i, _P(GmPolygons), _P(_d), _vp, _i64, _i64,
                                       _vp, _vp, _i, _vp]),
-    "gm_zonal_finalize_device": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "gm_zonal_finalize_device": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _P(GmPolygons), _vp]),
 }
 
 _lib = None

@@ -22,7 +22,10 @@
 #include <cfloat>
 #include <cstdlib>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 namespace gm {
 
@@ -47,6 +50,8 @@ struct PolyDev {
   int height, width;
   int cap;                      // crossing capacity per warp (power of two)
   int* error;                   // device flag: 1 = crossing overflow
+  const int* active;            // stripe calls: ids of the polygons with rows here (else nullptr)
+  const int* n_active;          // device scalar: length of `active`
 };
 
 // ---- preparation -------------------------------------------------------------------
@@ -88,6 +93,28 @@ __global__ void poly_rows_kernel(const double* __restrict__ py, const int64_t* _
   }
   miny[p] = lo;
   maxy[p] = hi;
+}
+
+// Stripe calls: most polygons have no row in this stripe.  Their ids are compacted away once, so
+// that the reduce kernel's work counter only hands out polygons that do something (every hand-out
+// is an atomic on ONE address plus a dependent chain of offset loads: 87 000 of them cost more
+// than the 12 500 polygons of a 1/8 stripe of configs[3]).  Order inside a warp is kept, so
+// neighbouring polygons still travel together.
+__global__ void poly_active_kernel(const int* __restrict__ miny, const int* __restrict__ maxy,
+                                   const int64_t* __restrict__ ring_offsets,
+                                   const int64_t* __restrict__ poly_offsets, int64_t n_polygons,
+                                   int* __restrict__ active, int* __restrict__ n_active) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  bool on = false;
+  if (p < n_polygons)
+    on = miny[p] <= maxy[p] && ring_offsets[poly_offsets[p + 1]] > ring_offsets[poly_offsets[p]];
+  const unsigned mask = __ballot_sync(0xffffffffu, on);
+  if (!mask) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(mask) - 1) base = atomicAdd(n_active, __popc(mask));
+  base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+  if (on) active[base + __popc(mask & ((1u << lane) - 1u))] = (int)p;
 }
 
 // ---- warp-level scanline walk ---------------------------------------------------------
@@ -755,11 +782,17 @@ zonal_reduce_warp_kernel(const PolyDev P, const T* __restrict__ raster, T nodata
   vis.active.nodata = nodata; vis.active.has_nodata = has_nodata;
   vis.active.has_threshold = thresholds != nullptr;
   const bool f32_fast = std::is_same<T, float>::value && has_nodata && thresholds == nullptr;
+  // (with an active list the partials of the other polygons were cleared by the caller)
+  const int64_t n_work = P.active ? (int64_t)*P.n_active : P.n_polygons;
   for (;;) {
     int64_t p = 0;
-    if (lane == 0) p = atomicAdd(work + 1, 1);
+    if (lane == 0) {
+      p = atomicAdd(work + 1, 1);
+      if (P.active && p < n_work) p = P.active[p];
+      else if (p >= n_work) p = -1;
+    }
     p = __shfl_sync(0xffffffffu, p, 0);
-    if (p >= P.n_polygons) break;
+    if (p < 0) break;
     const int64_t r0 = P.poly_offsets[p], r1 = P.poly_offsets[p + 1];
     const int miny = P.miny[p], maxy = P.maxy[p];
     int64_t v0 = 0, v1 = 0;
@@ -2344,20 +2377,46 @@ __global__ void big_offsets_kernel(const long long* __restrict__ area, int64_t n
 // ---- host side ---------------------------------------------------------------------------------
 // Polygon soup kept in HBM between calls (gm_polygons_upload): the CSR arrays and the
 // largest vertex count, so that a request only runs the two small preparation kernels.
+// What prepare_polygons derives from a soup for ONE raster grid (pixel-space vertices, row
+// ranges, the active list): a resident soup keeps the last few, so that a repeated request --
+// the same stripe of the same grid, step after step -- launches no preparation kernel at all.
+struct PreparedPolygons {
+  double geo[6];
+  int height = 0, width = 0;
+  int64_t row_begin = 0, row_end = 0;
+  void *px = nullptr, *py = nullptr, *miny = nullptr, *maxy = nullptr, *active = nullptr, *n_active = nullptr;
+  cudaEvent_t ready = nullptr;
+  ~PreparedPolygons() {
+    // (plain cudaFree waits for the device: kernels of other streams may still read these)
+    void* all[] = {px, py, miny, maxy, active, n_active};
+    for (void* p : all) if (p) cudaFree(p);
+    if (ready) cudaEventDestroy(ready);
+  }
+};
+
 struct ResidentPolygons {
   void *xy = nullptr, *rings = nullptr, *polys = nullptr;
   int64_t n_polygons = 0, n_rings = 0, n_vertices = 0, max_vertices = 1;
+  int* error = nullptr;       // crossing-overflow flag of calls whose check is deferred
+  std::mutex lock;
+  std::vector<std::shared_ptr<PreparedPolygons>> prepared;   // most recent last, <= 4
 };
 
 struct PolyUpload {
   void *xy = nullptr, *px = nullptr, *py = nullptr, *rings = nullptr, *polys = nullptr;
-  void *miny = nullptr, *maxy = nullptr, *error = nullptr;
+  void *miny = nullptr, *maxy = nullptr, *error = nullptr, *active = nullptr, *n_active = nullptr;
   bool borrowed = false;   // xy / rings / polys belong to a ResidentPolygons
+  bool deferred_error = false;                 // `error` is the resident soup's flag
+  std::shared_ptr<PreparedPolygons> shared;    // px ... n_active belong to it
   PolyDev dev;
   cudaStream_t s;
   void release() {
-    void* own[] = {px, py, miny, maxy, error};
-    for (void* p : own) if (p) cudaFreeAsync(p, s);
+    if (!shared) {
+      void* own[] = {px, py, miny, maxy, active, n_active};
+      for (void* p : own) if (p) cudaFreeAsync(p, s);
+    }
+    shared.reset();
+    if (error && !deferred_error) cudaFreeAsync(error, s);
     if (!borrowed) {
       void* csr[] = {xy, rings, polys};
       for (void* p : csr) if (p) cudaFreeAsync(p, s);
@@ -2376,18 +2435,24 @@ static int64_t largest_polygon(const GmPolygons* polys) {
 }
 
 static int prepare_polygons(const GmPolygons* polys, const double* geo, int height, int width,
-                            int64_t row_begin, int64_t row_end, PolyUpload& u, cudaStream_t s) {
+                            int64_t row_begin, int64_t row_end, PolyUpload& u, cudaStream_t s,
+                            bool stripe_call = false, bool cache = false) {
+  // stripe_call (gm_zonal_partials_device): build the list of polygons with rows in this window
+  // and leave the overflow flag of a resident soup to the finalisation; stripe_call or cache:
+  // keep the prepared arrays with a resident soup
   u.s = s;
   if (!polys || !geo) return fail("polygons: null argument");
   if (geo[2] != 0.0 || geo[4] != 0.0 || geo[1] == 0.0 || geo[5] == 0.0)
     return fail("polygons: rotated or degenerate geotransform");
   const int64_t nv = polys->n_vertices, nr = polys->n_rings, np_ = polys->n_polygons;
-  const ResidentPolygons* resident = static_cast<const ResidentPolygons*>(polys->resident);
+  ResidentPolygons* resident = static_cast<ResidentPolygons*>(const_cast<void*>(polys->resident));
   if (resident && (resident->n_polygons != np_ || resident->n_rings != nr || resident->n_vertices != nv))
     return fail("polygons: resident handle does not match the descriptor");
   const int64_t max_vertices = resident ? resident->max_vertices : largest_polygon(polys);
   int cap = 32;
   while (cap < max_vertices && cap < PG_MAX_CROSSINGS) cap <<= 1;
+  u.dev.n_polygons = np_; u.dev.height = height; u.dev.width = width; u.dev.cap = cap;
+  u.dev.active = nullptr; u.dev.n_active = nullptr;
   if (resident) {
     u.borrowed = true;
     u.xy = resident->xy; u.rings = resident->rings; u.polys = resident->polys;
@@ -2396,30 +2461,88 @@ static int prepare_polygons(const GmPolygons* polys, const double* geo, int heig
     if (upload(&u.rings, polys->ring_offsets, sizeof(int64_t) * (nr + 1), s)) return 1;
     if (upload(&u.polys, polys->poly_offsets, sizeof(int64_t) * (np_ + 1), s)) return 1;
   }
-  GM_CUDA(cudaMallocAsync(&u.px, sizeof(double) * (nv > 0 ? nv : 1), s));
-  GM_CUDA(cudaMallocAsync(&u.py, sizeof(double) * (nv > 0 ? nv : 1), s));
-  GM_CUDA(cudaMallocAsync(&u.miny, sizeof(int) * (np_ > 0 ? np_ : 1), s));
-  GM_CUDA(cudaMallocAsync(&u.maxy, sizeof(int) * (np_ > 0 ? np_ : 1), s));
-  GM_CUDA(cudaMallocAsync(&u.error, sizeof(int), s));
-  GM_CUDA(cudaMemsetAsync(u.error, 0, sizeof(int), s));
-  const double inv0 = -geo[0] / geo[1], inv1 = 1.0 / geo[1];
-  const double inv3 = -geo[3] / geo[5], inv5 = 1.0 / geo[5];
-  if (nv > 0) {
-    poly_transform_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(
-        (const double*)u.xy, (double*)u.px, (double*)u.py, nv, inv0, inv1, inv3, inv5);
-    GM_LAUNCH_CHECK();
+  u.dev.ring_offsets = (const int64_t*)u.rings; u.dev.poly_offsets = (const int64_t*)u.polys;
+  const bool keep = (stripe_call || cache) && resident != nullptr;
+  if (keep && stripe_call && resident->error) {
+    u.error = resident->error; u.deferred_error = true;
+  } else {
+    GM_CUDA(cudaMallocAsync(&u.error, sizeof(int), s));
+    GM_CUDA(cudaMemsetAsync(u.error, 0, sizeof(int), s));
   }
-  if (np_ > 0) {
-    poly_rows_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
-        (const double*)u.py, (const int64_t*)u.rings, (const int64_t*)u.polys, np_, height,
-        (int)row_begin, (int)row_end, (int*)u.miny, (int*)u.maxy);
-    GM_LAUNCH_CHECK();
+  u.dev.error = (int*)u.error;
+  auto adopt = [&](const PreparedPolygons& q) {
+    u.px = q.px; u.py = q.py; u.miny = q.miny; u.maxy = q.maxy; u.active = q.active; u.n_active = q.n_active;
+  };
+  if (keep) {
+    std::lock_guard<std::mutex> guard(resident->lock);
+    for (size_t i = 0; i < resident->prepared.size(); ++i) {
+      std::shared_ptr<PreparedPolygons> q = resident->prepared[i];
+      if (memcmp(q->geo, geo, sizeof(q->geo)) == 0 && q->height == height && q->width == width &&
+          q->row_begin == row_begin && q->row_end == row_end && (!stripe_call || q->active)) {
+        resident->prepared.erase(resident->prepared.begin() + (long)i);
+        resident->prepared.push_back(q);
+        GM_CUDA(cudaStreamWaitEvent(s, q->ready, 0));
+        u.shared = q;
+        adopt(*q);
+        break;
+      }
+    }
+  }
+  if (!u.shared) {
+    // (plain cudaMalloc for arrays that outlive the call: stream-ordered frees of another
+    //  stream's pool blocks are not wanted here)
+    auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t {
+      return keep ? cudaMalloc(ptr, bytes) : cudaMallocAsync(ptr, bytes, s);
+    };
+    std::shared_ptr<PreparedPolygons> q;
+    if (keep) q = std::make_shared<PreparedPolygons>();
+    void *px = nullptr, *py = nullptr, *miny = nullptr, *maxy = nullptr, *active = nullptr, *n_active = nullptr;
+    cudaError_t e = alloc(&px, sizeof(double) * (nv > 0 ? nv : 1));
+    if (e == cudaSuccess) e = alloc(&py, sizeof(double) * (nv > 0 ? nv : 1));
+    if (e == cudaSuccess) e = alloc(&miny, sizeof(int) * (np_ > 0 ? np_ : 1));
+    if (e == cudaSuccess) e = alloc(&maxy, sizeof(int) * (np_ > 0 ? np_ : 1));
+    if (e == cudaSuccess && stripe_call) e = alloc(&active, sizeof(int) * (np_ > 0 ? np_ : 1));
+    if (e == cudaSuccess && stripe_call) e = alloc(&n_active, sizeof(int));
+    if (q) { q->px = px; q->py = py; q->miny = miny; q->maxy = maxy; q->active = active; q->n_active = n_active; }
+    else { u.px = px; u.py = py; u.miny = miny; u.maxy = maxy; u.active = active; u.n_active = n_active; }
+    if (e != cudaSuccess) return fail(std::string("polygons: ") + cudaGetErrorString(e));
+    const double inv0 = -geo[0] / geo[1], inv1 = 1.0 / geo[1];
+    const double inv3 = -geo[3] / geo[5], inv5 = 1.0 / geo[5];
+    if (nv > 0) {
+      poly_transform_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, s>>>(
+          (const double*)u.xy, (double*)px, (double*)py, nv, inv0, inv1, inv3, inv5);
+      GM_LAUNCH_CHECK();
+    }
+    if (np_ > 0) {
+      poly_rows_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
+          (const double*)py, (const int64_t*)u.rings, (const int64_t*)u.polys, np_, height,
+          (int)row_begin, (int)row_end, (int*)miny, (int*)maxy);
+      GM_LAUNCH_CHECK();
+    }
+    if (stripe_call) {
+      GM_CUDA(cudaMemsetAsync(n_active, 0, sizeof(int), s));
+      if (np_ > 0) {
+        poly_active_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, s>>>(
+            (const int*)miny, (const int*)maxy, (const int64_t*)u.rings, (const int64_t*)u.polys, np_,
+            (int*)active, (int*)n_active);
+        GM_LAUNCH_CHECK();
+      }
+    }
+    if (q) {
+      memcpy(q->geo, geo, sizeof(q->geo));
+      q->height = height; q->width = width; q->row_begin = row_begin; q->row_end = row_end;
+      GM_CUDA(cudaEventCreateWithFlags(&q->ready, cudaEventDisableTiming));
+      GM_CUDA(cudaEventRecord(q->ready, s));
+      std::lock_guard<std::mutex> guard(resident->lock);
+      if (resident->prepared.size() >= 4) resident->prepared.erase(resident->prepared.begin());
+      resident->prepared.push_back(q);
+      u.shared = q;
+      adopt(*q);
+    }
   }
   u.dev.px = (const double*)u.px; u.dev.py = (const double*)u.py;
-  u.dev.ring_offsets = (const int64_t*)u.rings; u.dev.poly_offsets = (const int64_t*)u.polys;
   u.dev.miny = (const int*)u.miny; u.dev.maxy = (const int*)u.maxy;
-  u.dev.n_polygons = np_; u.dev.height = height; u.dev.width = width; u.dev.cap = cap;
-  u.dev.error = (int*)u.error;
+  if (stripe_call) { u.dev.active = (const int*)u.active; u.dev.n_active = (const int*)u.n_active; }
   return 0;
 }
 
@@ -2428,6 +2551,7 @@ static size_t scan_smem(int cap, int warps) {
 }
 
 static int check_overflow(PolyUpload& u, cudaStream_t s) {
+  if (u.deferred_error) return 0;     // gm_zonal_finalize_device reads the soup's flag
   int flag = 0;
   GM_CUDA(cudaMemcpyAsync(&flag, u.error, sizeof(int), cudaMemcpyDeviceToHost, s));
   GM_CUDA(cudaStreamSynchronize(s));
@@ -2774,7 +2898,7 @@ __global__ void zonal_pack_kernel(const GmZonalPartial* __restrict__ partial, co
   if (p >= n) return;
   const GmZonalPartial r = partial[p];
   sums[p] = (double)r.count; sums[n + p] = (double)cells[p]; sums[2 * n + p] = r.sum;
-  extremes[p] = r.vmin; extremes[n + p] = -r.vmax;
+  extremes[p] = r.count > 0 ? r.vmin : DBL_MAX; extremes[n + p] = r.count > 0 ? -r.vmax : DBL_MAX;
 }
 
 __global__ void zonal_unpack_kernel(const double* __restrict__ sums, const double* __restrict__ extremes, int64_t n,
@@ -2815,6 +2939,10 @@ static int run_zonal_partials_device(PolyUpload& u, const Staged& raster, const 
   GM_TRY(cudaMallocAsync(&dpartial, sizeof(GmZonalPartial) * np_, s));
   GM_TRY(cudaMallocAsync(&dwork, sizeof(int) * (size_t)(np_ + 2), s));
   GM_TRY(cudaMemsetAsync(dwork, 0, 2 * sizeof(int), s));
+  // polygons without rows in this stripe are never visited: count 0 (zonal_pack_kernel turns
+  // that into the neutral extremes)
+  GM_TRY(cudaMemsetAsync(dpartial, 0, sizeof(GmZonalPartial) * np_, s));
+  GM_TRY(cudaMemsetAsync(darea, 0, sizeof(long long) * np_, s));
   if (thresholds && upload(&dthr, thresholds, sizeof(float) * np_, s)) { cleanup(); return 1; }
   const size_t smem_scan = scan_smem(u.dev.cap, PG_WARPS);
   if (smem_scan > 48 * 1024)
@@ -2880,8 +3008,12 @@ extern "C" int gm_polygons_upload(const GmPolygons* polys, void** handle) {
   int rc = upload(&r->xy, polys->xy, sizeof(double) * 2 * r->n_vertices, s);
   if (!rc) rc = upload(&r->rings, polys->ring_offsets, sizeof(int64_t) * (r->n_rings + 1), s);
   if (!rc) rc = upload(&r->polys, polys->poly_offsets, sizeof(int64_t) * (r->n_polygons + 1), s);
+  if (!rc && (cudaMalloc((void**)&r->error, sizeof(int)) != cudaSuccess ||
+              cudaMemsetAsync(r->error, 0, sizeof(int), s) != cudaSuccess))
+    rc = fail("gm_polygons_upload: no memory for the overflow flag");
   if (!rc && cudaStreamSynchronize(s) != cudaSuccess) rc = fail("gm_polygons_upload: copy failed");
   if (rc) {
+    if (r->error) cudaFree(r->error);
     void* all[] = {r->xy, r->rings, r->polys};
     for (void* p : all) if (p) cudaFreeAsync(p, s);
     delete r;
@@ -2895,6 +3027,8 @@ extern "C" int gm_polygons_free(void* handle) {
   if (!handle) return 0;
   ResidentPolygons* r = static_cast<ResidentPolygons*>(handle);
   cudaStream_t s = resolve_stream(nullptr);
+  r->prepared.clear();
+  if (r->error) cudaFree(r->error);
   void* all[] = {r->xy, r->rings, r->polys};
   for (void* p : all) if (p) cudaFreeAsync(p, s);
   delete r;
@@ -2988,7 +3122,7 @@ extern "C" int gm_zonal_stats(const GmArray* raster, const void* nodata, int has
   Staged in;
   PolyUpload u;
   int rc = in.open_input(*raster, s);
-  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s);
+  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s, false, true);
   if (!rc) {
 #define GM_Z(T) run_zonal<T>(u, in, nodata, has_nodata, stat, q, thresholds, out, covered, partial, s)
     switch (raster->dtype) {
@@ -3024,7 +3158,7 @@ extern "C" int gm_zonal_partials_device(const GmArray* raster, const void* nodat
   Staged in;
   PolyUpload u;
   int rc = in.open_input(*raster, s);
-  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s);
+  if (!rc) rc = prepare_polygons(polys, geo, H, W, row_begin, row_end, u, s, true);
   if (!rc) {
     GM_RASTER_DISPATCH(raster->dtype,
                        run_zonal_partials_device<T>(u, in, nodata, has_nodata, thresholds, sums, extremes, stat, s),
@@ -3037,11 +3171,16 @@ extern "C" int gm_zonal_partials_device(const GmArray* raster, const void* nodat
 }
 
 extern "C" int gm_zonal_finalize_device(const double* sums, const double* extremes, int64_t n_polygons,
-                                        int stat, float* out, int64_t* covered, void* stream) {
+                                        int stat, float* out, int64_t* covered, const GmPolygons* polys,
+                                        void* stream) {
   if (ensure_init()) return 1;
   if (!sums || !extremes || !out || !covered) return fail("gm_zonal_finalize_device: null argument");
   if (n_polygons == 0) return 0;
   cudaStream_t s = resolve_stream(stream);
+  // the stripe pass on a resident soup left its crossing-overflow flag on the device: it comes
+  // back with the results, under the one synchronisation of this call
+  ResidentPolygons* resident = polys ? static_cast<ResidentPolygons*>(const_cast<void*>(polys->resident)) : nullptr;
+  int overflow = 0;
   void *dout = nullptr, *dcov = nullptr;
   GM_CUDA(cudaMallocAsync(&dout, sizeof(float) * n_polygons, s));
   GM_CUDA(cudaMallocAsync(&dcov, sizeof(long long) * n_polygons, s));
@@ -3051,9 +3190,15 @@ extern "C" int gm_zonal_finalize_device(const double* sums, const double* extrem
   if (e == cudaSuccess) count_launch();
   if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, sizeof(float) * n_polygons, cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(covered, dcov, sizeof(long long) * n_polygons, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && resident && resident->error)
+    e = cudaMemcpyAsync(&overflow, resident->error, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFreeAsync(dout, s);
   cudaFreeAsync(dcov, s);
   if (e != cudaSuccess) return fail(std::string("gm_zonal_finalize_device: ") + cudaGetErrorString(e));
+  if (overflow) {
+    cudaMemsetAsync(resident->error, 0, sizeof(int), s);
+    return fail("polygons: more than 4096 edge crossings (or 8 horizontal edges) on one scanline");
+  }
   return 0;
 }

@@ -729,12 +729,15 @@ def _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, th
             kept["geo"] = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox(stripe_bbox, shape[1], shape[2]))
             kept["nodata"] = _native.scalar_ptr(0 if s is None else s, local.dtype)
             kept["has_nodata"] = int(s is not None)
-            kept["polys"] = soup.as_struct()
+            # resident soup: the stripe pass keeps its preparation (pixel-space vertices, row
+            # ranges, the ids of the polygons with rows here) and does not synchronise
+            kept["polys"] = soup.to_device().as_struct()
         soup._stripe_call = kept
     sums, extremes = kept["sums"], kept["extremes"]
-    sums.zero_()
-    if statistic in ("min", "max"):
-        extremes.fill_(float(np.finfo(np.float64).max))
+    if not has_rows:      # (a stripe pass writes every entry of both vectors)
+        sums.zero_()
+        if statistic in ("min", "max"):
+            extremes.fill_(float(np.finfo(np.float64).max))
     if has_rows:
         thresholds = None
         if threshold_values is not None:
@@ -758,7 +761,8 @@ def _zonal_striped_device(soup, local, no_data_value, stripe_bbox, statistic, th
     # (the result buffers are reused by the next call on this soup: copy what must outlive it)
     out, covered = kept["out"], kept["covered"]
     _native.check(lib.gm_zonal_finalize_device(sums.data_ptr(), extremes.data_ptr(), n, _STAT_CODES[statistic],
-                                               out.ctypes.data, covered.ctypes.data, stream))
+                                               out.ctypes.data, covered.ctypes.data,
+                                               ctypes.byref(kept["polys"]) if has_rows else None, stream))
     _trace("finalise + download")
     return out.copy(), np.nonzero(covered == 0)[0].tolist()
 

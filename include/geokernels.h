@@ -305,13 +305,18 @@ int  gm_segment_order_stat(const void* values, int32_t dtype, const int64_t* off
  * (geometry/aggregate.py:311-316) is formed from them.  `sums` / `extremes` are DEVICE
  * pointers (e.g. torch tensors); `out` / `covered` are host buffers.  `stat` (GmStat, or -1 for
  * everything) lets the stripe pass compute only what the statistic needs: the sums for
- * sum / mean / count, one extreme for min / max.                                             */
+ * sum / mean / count, one extreme for min / max.  With a resident soup (gm_polygons_upload) the
+ * stripe pass keeps what it derives from the soup for this grid (pixel-space vertices, row
+ * ranges, the ids of the polygons with rows in the stripe) for the next call and does not
+ * synchronise: its crossing-overflow flag is read back by gm_zonal_finalize_device, which takes
+ * the same `polys` (NULL: nothing deferred).                                                  */
 int  gm_zonal_partials_device(const GmArray* raster, const void* nodata, int has_nodata,
                               const GmPolygons* polys, const double geo[6],
                               const float* thresholds, int64_t row_begin, int64_t row_end,
                               double* sums, double* extremes, int stat, void* stream);
 int  gm_zonal_finalize_device(const double* sums, const double* extremes, int64_t n_polygons,
-                              int stat, float* out, int64_t* covered, void* stream);
+                              int stat, float* out, int64_t* covered, const GmPolygons* polys,
+                              void* stream);
 
 #ifdef __cplusplus
 }
