@@ -643,6 +643,32 @@ def run_temporal(ctx):
 # ----------------------------------------------------------------------------
 
 
+def host_link_ceiling(torch, dist, world, h2d, d2h, steps):
+    """Seconds for `steps` rounds of bare page-locked copies of the end-to-end leg's bytes (h2d up,
+    d2h down, on two streams so that they overlap as in the chunk pipeline), every rank at once."""
+    up_host = torch.empty(h2d, dtype=torch.uint8).pin_memory()
+    down_host = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    up_dev = torch.empty(h2d, dtype=torch.uint8, device="cuda")
+    down_dev = torch.empty(d2h, dtype=torch.uint8, device="cuda")
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def round_trip():
+        with torch.cuda.stream(a):
+            up_dev.copy_(up_host, non_blocking=True)
+        with torch.cuda.stream(b):
+            down_host.copy_(down_dev, non_blocking=True)
+
+    round_trip()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        round_trip()
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -680,7 +706,7 @@ def run_b200(args):
     # inputs; every step uploads both rasters (pinned H2D) and downloads the result
     h2d = ints.nbytes + floats.nbytes
     d2h = pixels  # one bool per pixel
-    e2e_s = float("nan")
+    e2e_s = link_s = float("nan")
     e2e_checksum = None
     if not args.profile:
         result = view.get_data(**request)  # warm-up: tokens, page-locking, NVRTC, pools
@@ -696,6 +722,7 @@ def run_b200(args):
         e2e_checksum = int(result["values"].sum())
         d2h = result["values"].nbytes
         del result
+        link_s = host_link_ceiling(torch, dist, world, h2d, d2h, args.e2e_steps)
 
     # ---- kernel-resident measurement: compile once, launch K times -------------
     graph, name = view.get_compute_graph(**request)
@@ -730,10 +757,10 @@ def run_b200(args):
         del inputs, leaf_payloads, out
     assert e2e_checksum is None or e2e_checksum == checksum, "e2e result differs from the resident result"
 
-    t = torch.tensor([elapsed_ms, e2e_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed_ms, e2e_s, link_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_s = float(t[0]), float(t[1])
+    elapsed_ms, e2e_s, link_s = float(t[0]), float(t[1]), float(t[2])
 
     striped = {}
     if "stencils" in args.legs:
@@ -765,6 +792,14 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                     "per_rank_link_gb_s": (h2d + d2h) * args.e2e_steps / e2e_s / 1e9,
+                    # the same bytes per step as bare cudaMemcpyAsync calls (page-locked buffers, upload
+                    # and download on two streams, all ranks at once): what the box's host side gives
+                    # N ranks together, i.e. the ceiling of `value` above
+                    "host_link_ceiling": {
+                        "per_rank_gb_s": (h2d + d2h) * args.e2e_steps / link_s / 1e9,
+                        "aggregate_gb_s": world * (h2d + d2h) * args.e2e_steps / link_s / 1e9,
+                        "as_gpixel_s": world * pixels * args.e2e_steps / link_s / 1e9,
+                        "e2e_fraction_of_ceiling": link_s / e2e_s},
                     "rank0_host_binding": binding},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -567,6 +567,28 @@ def _order_stat_call(soup, payload, no_data_value, bbox, threshold_values, stati
     return out, covered
 
 
+_HELPERS = {}
+
+
+def _helper_pool():
+    """One helper thread per process for the boundary work of the striped order statistics."""
+    pool = _HELPERS.get("pool")
+    if pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        pool = _HELPERS["pool"] = ThreadPoolExecutor(max_workers=1, thread_name_prefix="gm-boundary")
+    return pool
+
+
+def _side_stream(device):
+    import torch
+
+    key = ("stream", device)
+    if key not in _HELPERS:
+        _HELPERS[key] = torch.cuda.Stream(device=device)
+    return _HELPERS[key]
+
+
 def _rank_soups(soup, bbox, height, world, rank):
     """This rank's share of the order statistics, cached on the soup: the polygons it owns that
     lie inside its stripe and the ones that cross into the next stripe, each as ids + a soup of
@@ -641,33 +663,57 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
     def thresholds_of(ids):
         return None if threshold_values is None else np.asarray(threshold_values)[ids]
 
-    # boundary rows first (asynchronous under NCCL): my first rows go north, the southern
-    # neighbour's first rows come here; the select of the inner polygons runs meanwhile
+    # boundary rows: my first rows go north, the southern neighbour's first rows come here, and the
+    # polygons that cross into the next stripe are selected on the strip made of both.  Under NCCL
+    # all of that runs on a helper thread with its own stream WHILE this thread selects the inner
+    # polygons: the exchange, the few hundred boundary polygons and their three launches hide
+    # behind the stripe's own select (the library calls release the GIL).
     link = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
-    ops, recv = [], None
-    if rank > 0 and halo[rank - 1] > 0:
-        send = tensor[:, :int(halo[rank - 1])].to(link).contiguous()
-        ops.append(dist.P2POp(dist.isend, send, rank - 1, group))
-    if rank < world - 1 and halo[rank] > 0:
-        recv = torch.empty((1, int(halo[rank]), tensor.shape[2]), dtype=tensor.dtype, device=link)
-        ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
-    pending = dist.batch_isend_irecv(ops) if ops else []
+
+    def boundary(ready=None, device=None):
+        if device is not None:           # helper thread: its own device context and stream
+            torch.cuda.set_device(device)
+            side = _side_stream(device)
+            side.wait_event(ready)       # the stripe as the caller's stream left it
+            with torch.cuda.stream(side), _native.use_stream(side.cuda_stream):
+                return boundary()
+        ops, recv = [], None
+        if rank > 0 and halo[rank - 1] > 0:
+            send = tensor[:, :int(halo[rank - 1])].to(link).contiguous()
+            ops.append(dist.P2POp(dist.isend, send, rank - 1, group))
+        if rank < world - 1 and halo[rank] > 0:
+            recv = torch.empty((1, int(halo[rank]), tensor.shape[2]), dtype=tensor.dtype, device=link)
+            ops.append(dist.P2POp(dist.irecv, recv, rank + 1, group))
+        for work in (dist.batch_isend_irecv(ops) if ops else []):
+            work.wait()
+        if recv is None or not len(near_ids):
+            if link == "cuda" and ops:
+                torch.cuda.current_stream().synchronize()    # my rows have left before they may change
+            return None
+        k = int(keep[rank])
+        strip = torch.cat([tensor[:, r1 - r0 - k:], recv.to(tensor.device)], dim=1).contiguous()
+        strip_bbox = (x1, y2 - (r1 + int(halo[rank])) * dy, x2, y2 - (r1 - k) * dy)
+        if strip.is_cuda:
+            torch.cuda.current_stream().synchronize()   # the strip is complete before the library reads it
+        return _order_stat_call(near_soup, _as_payload(strip), no_data_value, strip_bbox,
+                                thresholds_of(near_ids), statistic, percentile)
+
+    helper = None
+    if link == "cuda" and tensor is not None and tensor.is_cuda:
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        if _native.current_stream() not in (None, torch.cuda.current_stream().cuda_stream):
+            _native.synchronize()      # the library's stream holds work on the stripe: let it finish
+        helper = _helper_pool().submit(boundary, ready, tensor.device.index)
     _trace("boundary rows posted")
     if r1 > r0 and len(inside_ids):
         got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
                                     statistic, percentile)
         mine[0, inside_ids], mine[1, inside_ids] = got, cov > 0
     _trace("select inside the stripe")
-    for work in pending:
-        work.wait()
-    if recv is not None and len(near_ids):
-        k = int(keep[rank])
-        strip = torch.cat([tensor[:, r1 - r0 - k:], recv.to(tensor.device)], dim=1).contiguous()
-        strip_bbox = (x1, y2 - (r1 + int(halo[rank])) * dy, x2, y2 - (r1 - k) * dy)
-        if strip.is_cuda:
-            torch.cuda.current_stream().synchronize()   # the strip is complete before the library reads it
-        got, cov = _order_stat_call(near_soup, _as_payload(strip), no_data_value, strip_bbox,
-                                    thresholds_of(near_ids), statistic, percentile)
+    strip_result = helper.result() if helper is not None else boundary()
+    if strip_result is not None:
+        got, cov = strip_result
         mine[0, near_ids], mine[1, near_ids] = got, cov > 0
     _trace("select on the boundary strip")
     block = stage_in.to(dev, non_blocking=True)
