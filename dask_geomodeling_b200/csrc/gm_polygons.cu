@@ -1202,7 +1202,7 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
                     const float* __restrict__ thresholds, int stat, double q,
                     const long long* __restrict__ area, const long long* __restrict__ big_offset,
                     typename KeyOf<T>::type* __restrict__ big_keys, int smem_capacity,
-                    float* __restrict__ out, const int* __restrict__ work) {
+                    float* __restrict__ out, const int* __restrict__ work, int* __restrict__ too_big) {
   typedef typename KeyOf<T>::type K;
   extern __shared__ __align__(16) unsigned char sel_smem[];
   const int nw = SEL_THREADS / 32;
@@ -1218,6 +1218,10 @@ zonal_select_kernel(const PolyDev P, const T* __restrict__ raster, T nodata, int
   for (int item = blockIdx.x; item < n_listed; item += gridDim.x) {
     const int64_t p = work[2 + item];
     const long long a = area[p];
+    if (a > smem_capacity && big_keys == nullptr) {   // optimistic launch without global key segments:
+      if (threadIdx.x == 0) *too_big = 1;             // the host repeats the listed polygons with them
+      continue;
+    }
     K* keys = a <= smem_capacity ? smem_keys : big_keys + big_offset[p];
     if (threadIdx.x == 0) cursor = 0;
     __syncthreads();
@@ -2655,6 +2659,7 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
   int n_listed = 0;
   std::vector<int> listed;
   bool area_done = false;
+  bool selected = false;      // the listed polygons are done and `out` is on the host already
   if (order_stat) {
     GM_TRY(cudaMallocAsync(&dlist, sizeof(int) * (size_t)(np_ + 2), s));
     scratch_list = dlist;
@@ -2708,12 +2713,36 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
           u.dev, (long long*)darea, (const int*)dlist);
       GM_TRY(cudaGetLastError());
       count_launch();
+      // The deferred polygons are selected right away by the block-per-polygon kernel with their
+      // keys in shared memory (the whole budget), its grid sized without knowing the list's
+      // length: results, counts, the list and a "some polygon did not fit" flag come back under
+      // ONE synchronisation.  Only when the flag is up does the host lay out global key segments
+      // and repeat the listed polygons (below).
+      {
+        typedef typename KeyOf<T>::type K;
+        const size_t shead = (scan_smem(u.dev.cap, SEL_THREADS / 32) + 15) / 16 * 16;
+        const int capacity = (int)((200 * 1024 - shead) / sizeof(K));
+        const size_t smem_sel = shead + (size_t)capacity * sizeof(K);
+        GM_TRY(cudaFuncSetAttribute(zonal_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+        GM_TRY(cudaMallocAsync(&dtotal, sizeof(int), s));
+        GM_TRY(cudaMemsetAsync(dtotal, 0, sizeof(int), s));
+        zonal_select_kernel<T><<<poly_grid(np_ < 1024 ? np_ : 1024), SEL_THREADS, smem_sel, s>>>(
+            u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, stat, q,
+            (const long long*)darea, nullptr, (K*)nullptr, capacity, (float*)dout, (const int*)dlist,
+            (int*)dtotal);
+        GM_TRY(cudaGetLastError());
+        count_launch();
+      }
       const int64_t head = np_ < 4096 ? np_ : 4096;
       std::vector<int> front(head + 2);
+      int too_big = 0;
       GM_TRY(cudaMemcpyAsync(front.data(), dlist, sizeof(int) * (head + 2), cudaMemcpyDeviceToHost, s));
       GM_TRY(cudaMemcpyAsync(area, darea, sizeof(long long) * np_, cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaMemcpyAsync(&too_big, dtotal, sizeof(int), cudaMemcpyDeviceToHost, s));
+      GM_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * np_, cudaMemcpyDeviceToHost, s));
       GM_TRY(cudaStreamSynchronize(s));
       area_done = true;
+      selected = !too_big;
       cudaFreeAsync(dbig, s);
       cudaFreeAsync(dstate, s);
       cudaFreeAsync(dcounters, s);
@@ -2793,7 +2822,7 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       GM_TRY(cudaMemcpyAsync(out, dout, sizeof(float) * np_, cudaMemcpyDeviceToHost, s));
     }
   }
-  if (order_stat && out) {
+  if (order_stat && out && !selected) {
     typedef typename KeyOf<T>::type K;
     if (!dout) GM_TRY(cudaMallocAsync(&dout, sizeof(float) * np_, s));
     if (n_listed > 0) {
@@ -2806,16 +2835,23 @@ static int run_zonal(PolyUpload& u, const Staged& raster, const void* nodata, in
       const size_t smem_sel = head + (size_t)capacity * sizeof(K);
       GM_TRY(cudaFuncSetAttribute(zonal_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
       // global key segments for the polygons that do not fit shared memory
-      std::vector<long long> offsets(np_, 0);
+      // (only polygons that exceed the shared-memory capacity read their offset: none -> no table)
       long long total = 0;
       for (int p : listed)
-        if (area[p] > capacity) { offsets[p] = total; total += area[p]; }
-      if (upload(&doff, offsets.data(), sizeof(long long) * np_, s)) { cleanup(); return 1; }
+        if (area[p] > capacity) total += area[p];
+      if (total > 0) {
+        std::vector<long long> offsets(np_, 0);
+        total = 0;
+        for (int p : listed)
+          if (area[p] > capacity) { offsets[p] = total; total += area[p]; }
+        if (upload(&doff, offsets.data(), sizeof(long long) * np_, s)) { cleanup(); return 1; }
+        GM_TRY(cudaStreamSynchronize(s));     // `offsets` is pageable and leaves scope here
+      }
       GM_TRY(cudaMallocAsync(&dbig, sizeof(K) * (size_t)(total > 0 ? total : 1), s));
       zonal_select_kernel<T><<<poly_grid(n_listed), SEL_THREADS, smem_sel, s>>>(
           u.dev, (const T*)raster.dev, nd, has_nodata, (const float*)dthr, stat, q,
           (const long long*)darea, (const long long*)doff, (K*)dbig, (int)capacity, (float*)dout,
-          (const int*)dlist);
+          (const int*)dlist, nullptr);
       GM_TRY(cudaGetLastError());
       count_launch();
     }
