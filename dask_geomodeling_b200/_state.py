@@ -19,3 +19,28 @@ def device_resident(flag=True):
         yield
     finally:
         _local.keep = previous
+
+
+class RowWindow(object):
+    """Target of stencil calls that each compute a row window of ONE output raster: the first call
+    allocates the full (bands, full_rows, width) output, every call writes its rows at ``r0``
+    (raster/spatial.py `_call_stencil`; single-band rasters only -- arrays are contiguous)."""
+
+    def __init__(self, full_rows):
+        self.full_rows = int(full_rows)
+        self.r0 = 0
+        self.out = None
+
+
+def row_window():
+    return getattr(_local, "row_window", None)
+
+
+@contextlib.contextmanager
+def into_row_window(target):
+    previous = row_window()
+    _local.row_window = target
+    try:
+        yield target
+    finally:
+        _local.row_window = previous

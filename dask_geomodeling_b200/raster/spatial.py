@@ -72,6 +72,22 @@ def _call_stencil(values, out_shape, out_dtype, launch):
         values = _native.DeviceArray.from_host(values)
     if not on_device:
         values = np.ascontiguousarray(values)
+    target = _state.row_window() if on_device and out_shape[0] == 1 else None
+    if target is not None:
+        # a row window of a larger output (parallel.stencil_haloed computes the interior of a
+        # stripe while its halo rows travel): the full raster is allocated once, this call
+        # writes rows [r0, r0 + rows)
+        if target.out is None:
+            target.out = _native.DeviceArray((1, target.full_rows, out_shape[2]), out_dtype)
+        full = target.out
+        if full.dtype != np.dtype(out_dtype) or full.shape[2] != out_shape[2] or \
+                target.r0 < 0 or target.r0 + out_shape[1] > full.shape[1]:
+            raise ValueError("stencil row window does not fit its output raster")
+        out = _native.DeviceArray(out_shape, out_dtype, owner=full,
+                                  ptr=full.ptr + target.r0 * out_shape[2] * np.dtype(out_dtype).itemsize)
+        src, dst = _native.as_gm_array(values), _native.as_gm_array(out)
+        _native.check(launch(lib, ctypes.byref(src), ctypes.byref(dst), _native.current_stream()))
+        return out
     out = (_native.DeviceArray(out_shape, out_dtype) if on_device
            else _native.pinned_empty(out_shape, out_dtype))
     src, dst = _native.as_gm_array(values), _native.as_gm_array(out)

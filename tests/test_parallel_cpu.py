@@ -92,6 +92,42 @@ def test_exchange_halo_three_ranks():
     spawn(_halo_worker, 3, world=3)
 
 
+def _box_max(data, size):
+    """A window-invariant stencil with the blocks' calling convention: the input carries a margin
+    of size // 2 cells that the output drops."""
+    from scipy import ndimage
+
+    r = size // 2
+    out = ndimage.maximum_filter(np.asarray(data["values"]), size=(1, size, size))[:, r:-r, r:-r]
+    return {"values": out, "no_data_value": data["no_data_value"]}
+
+
+def _overlap_worker(rank, world, halo):
+    import torch
+
+    rng = np.random.default_rng(9)
+    full = rng.normal(size=(1, 61, 23)).astype("f4")
+    fill = -1e30
+    r0, r1 = parallel.stripe_rows(full.shape[1], world)[rank]
+    stored = parallel.pad_columns(parallel.exchange_halo(torch.from_numpy(full[:, r0:r1].copy()), halo, fill), halo, fill)
+    expected = _box_max({"values": np.pad(full, ((0, 0), (halo, halo), (halo, halo)), constant_values=fill),
+                         "no_data_value": fill}, 2 * halo + 1)["values"][:, r0:r1]
+    for overlap in (False, True):
+        stored[:, :halo] = 7.0       # stale halo rows: the exchange must refresh them
+        stored[:, -halo:] = 7.0
+        if rank == 0:
+            stored[:, :halo] = fill
+        if rank == world - 1:
+            stored[:, -halo:] = fill
+        got = parallel.stencil_haloed(_box_max, stored, fill, halo, halo, 2 * halo + 1, overlap=overlap)
+        np.testing.assert_array_equal(np.asarray(got["values"]), expected)
+
+
+@pytest.mark.parametrize("halo,world", [(1, 2), (5, 2), (3, 3)])
+def test_stencil_on_a_stored_stripe_with_overlapped_exchange(halo, world):
+    spawn(_overlap_worker, halo, world=world)
+
+
 def _thin_stripe_worker(rank, world):
     import torch
 

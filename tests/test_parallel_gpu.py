@@ -123,6 +123,34 @@ def _stencil_worker(rank, world):
     delta = np.abs(np.asarray(got["values"]).astype(int) - expected[:, r0:r1].astype(int))
     assert delta.max() <= 1 and (delta > 0).mean() <= 1e-3
 
+    # a stripe STORED with its halo (one band): the exchange overlapped with the interior rows
+    # (three row windows written into one output) equals the one-call result bit for bit, and
+    # the oracle
+    band = local[:1].contiguous()
+    cases = [(raster.MovingMax.process, 5, 5, (11,), lambda: R.moving_max(whole(5)[:1], nodata, 11)[0]),
+             (raster.HillShade.process, 1, 1, (dict(resolution=(1.0, 1.0), altitude=45.0, azimuth=315.0, fill=0),), None),
+             (raster.Smooth.process, lw, 5, (dict(smooth_mode="exact", fill=0, size=[5.0, 5.0], margin=(lw, 5)),),
+              lambda: R.smooth(whole(5)[:1], nodata, (5.0, 5.0), 0, "exact")[0])]
+    for process, halo_rows, halo_cols, extra, oracle in cases:
+        pitch = 4 if process is raster.MovingMax.process else 1
+        stored = parallel.pad_columns(parallel.exchange_halo(band, halo_rows, nodata), halo_cols, nodata, pitch)
+        if process is raster.MovingMax.process:
+            extra = extra + (stored.shape[2] - (w + 2 * halo_cols),)
+        with _native.smooth_arithmetic("exact"):
+            plain = np.asarray(parallel.stencil_haloed(process, stored, nodata, halo_rows, halo_cols, *extra,
+                                                       overlap=False)["values"])
+            stored[:, :halo_rows] = 0.0          # stale halo rows: the exchange must refresh them
+            stored[:, -halo_rows:] = 0.0
+            if rank == 0:
+                stored[:, :halo_rows] = nodata
+            if rank == world - 1:
+                stored[:, -halo_rows:] = nodata
+            over = parallel.stencil_haloed(process, stored, nodata, halo_rows, halo_cols, *extra, overlap=True)
+        assert over["values"].shape == (1, r1 - r0, w)
+        np.testing.assert_array_equal(np.asarray(over["values"]), plain)
+        if oracle is not None:
+            np.testing.assert_array_equal(plain, oracle()[:, r0:r1])
+
 
 def test_stencils_with_halo_exchange():
     spawn(_stencil_worker)
