@@ -174,6 +174,17 @@ def test_sink_init(source, root):
         RasterFileSink(source, "http://example.com/x")
 
 
+def test_strict_file_paths(source, root, tmp_path_factory):
+    from dask_geomodeling_b200 import utils
+
+    outside = str(tmp_path_factory.mktemp("elsewhere") / "x")
+    assert utils.safe_abspath(outside) == outside          # absolute paths pass by default
+    with config.set({"geomodeling.strict-file-paths": True}):
+        assert utils.safe_file_url("inside/a.tif") == "file://" + os.path.join(root, "inside", "a.tif")
+        with pytest.raises(IOError):
+            RasterFileSink(source, outside)
+
+
 def test_sink_process(source, root, request_kwargs):
     path = os.path.join(root, "sink")
     assert RasterFileSink(source, path).get_data(**request_kwargs) is None
