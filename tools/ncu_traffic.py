@@ -109,7 +109,7 @@ PER_LAUNCH = {
     "moving_max_block_kernel": "moving_max_block_kernel<float",
     "hillshade_quad_kernel": "hillshade_quad_kernel<float",
 }
-# zonal statistics: one CALL = everything between two poly_transform launches
+# zonal statistics: one CALL = the launches from one call's first kernel to the next call's
 PER_CALL = {
     "zonal_mean": "zonal_reduce_warp_kernel<float, 1>",
     "zonal_max": "zonal_reduce_warp_kernel<float, 4>",
@@ -148,11 +148,19 @@ def main(src, dst):
             traffic[key] = {"dram_bytes_per_launch": statistics.median(e["bytes"] for e in big),
                             "kernel_duration_s_under_ncu": statistics.median(e["ns"] for e in big) / 1e9,
                             "launches_counted": len(big), "source": source}
-        calls, current = [], None
+        # a call starts with its preparation (first call on a soup and grid) or, when a resident
+        # soup kept that, with the first kernel of the statistic itself
+        FIRST = ("zonal_reduce_warp_kernel", "zonal_select_bracket_kernel")
+        calls, current, opened_by_prepare = [], None, False
         for e in ours:
-            if "poly_transform_kernel" in e["name"]:
+            starts = "poly_transform_kernel" in e["name"]
+            if any(f in e["name"] for f in FIRST):
+                starts = not (opened_by_prepare and current is not None
+                              and not any(any(f in x["name"] for f in FIRST) for x in current))
+            if starts:
                 current = []
                 calls.append(current)
+                opened_by_prepare = "poly_transform_kernel" in e["name"]
             if current is not None and ("zonal" in e["name"] or "poly_" in e["name"]):
                 current.append(e)
         for key, fragment in PER_CALL.items():
