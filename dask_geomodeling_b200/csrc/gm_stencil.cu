@@ -99,20 +99,28 @@ template <typename T> struct Lowest { static __host__ __device__ T value() { ret
 // resolution into float32, then the shading in float32 exactly in the order of
 // the reference expression; the result is truncated to uint8.
 template <typename T> struct HillArith;
+// add2 / sub2: acc + 2 x and acc - 2 x.  Doubling is exact in binary floating point, so ONE fused
+// multiply-add rounds exactly like the reference's separate product and sum.
 template <> struct HillArith<float> {
   typedef float acc;
   static __device__ __forceinline__ float div(float v, double res) { return v / (float)res; }
   static __device__ __forceinline__ float mul(float v, double inv) { return v * (float)inv; }
+  static __device__ __forceinline__ float add2(float acc_, float x) { return __fmaf_rn(2.0f, x, acc_); }
+  static __device__ __forceinline__ float sub2(float acc_, float x) { return __fmaf_rn(-2.0f, x, acc_); }
 };
 template <> struct HillArith<double> {
   typedef double acc;
   static __device__ __forceinline__ float div(double v, double res) { return (float)(v / res); }
   static __device__ __forceinline__ float mul(double v, double inv) { return (float)(v * inv); }
+  static __device__ __forceinline__ double add2(double acc_, double x) { return __fma_rn(2.0, x, acc_); }
+  static __device__ __forceinline__ double sub2(double acc_, double x) { return __fma_rn(-2.0, x, acc_); }
 };
 template <typename T> struct HillArith {  // integer rasters: arithmetic wraps in T, division in double
   typedef T acc;
   static __device__ __forceinline__ float div(T v, double res) { return (float)((double)v / res); }
   static __device__ __forceinline__ float mul(T v, double inv) { return (float)((double)v * inv); }
+  static __device__ __forceinline__ T add2(T acc_, T x) { return (T)(acc_ + (T)2 * x); }
+  static __device__ __forceinline__ T sub2(T acc_, T x) { return (T)(acc_ - (T)2 * x); }
 };
 
 constexpr int HS_WARPS = 8;
@@ -139,7 +147,8 @@ template <> __device__ __forceinline__ int64_t shfl_down_any<int64_t>(int64_t v,
 // grey level on 4e-5 of the pixels for this form; the parity tests allow 1e-3.
 constexpr int HQ_COLS = 124;   // output columns per warp
 constexpr int HQ_ROWS = 64;
-constexpr int HQ_AHEAD = 4;    // source rows fetched per batch (16 loads in flight per lane)
+constexpr int HQ_AHEAD = 3;    // source rows fetched per batch (12 loads in flight per lane); a multiple of 3
+static_assert(HQ_AHEAD % 3 == 0, "the ring of three row sets must close over a batch");
 
 template <typename T, bool EXACT_INVERSE>
 __global__ void __launch_bounds__(32 * HS_WARPS, 4)
@@ -175,10 +184,11 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
     w[4] = shfl_down_any<A>(w[0], 1);
     w[5] = shfl_down_any<A>(w[1], 1);
   };
-  A a[6], m[6];
-  load_row(y0, a);
-  load_row(y0 + 1, m);
-  const A two = (A)2;
+  // three live source rows in a ring of three register sets: a batch of HQ_AHEAD rows (a multiple
+  // of 3) returns every set to its role, so no row is ever moved between registers
+  A ring[3][6];
+  load_row(y0, ring[0]);
+  load_row(y0 + 1, ring[1]);
   const bool lane_writes = lane < 31 && x0 < W;
   const bool whole_quad = dst_aligned && x0 + 3 < W;
   uint8_t* o = dst + (int64_t)b * out_plane + (int64_t)y0 * W + x0;
@@ -193,7 +203,9 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
 #pragma unroll
     for (int i = 0; i < HQ_AHEAD; ++i) {
       const int r = r0 + i;
-      A c[6];
+      A (&a)[6] = ring[i % 3];
+      A (&m)[6] = ring[(i + 1) % 3];
+      A (&c)[6] = ring[(i + 2) % 3];
 #pragma unroll
       for (int j = 0; j < 4; ++j) c[j] = clean(next[i][j]);
       c[4] = shfl_down_any<A>(c[0], 1);
@@ -202,8 +214,9 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         // s0 s1 s2 = a[j..j+2] ; s3 . s5 = m[j], m[j+2] ; s6 s7 s8 = c[j..j+2]
-        const A gy = ((((a[j] + two * a[j + 1]) + a[j + 2]) - c[j]) - two * c[j + 1]) - c[j + 2];
-        const A gx = ((((a[j] + two * m[j]) + c[j]) - a[j + 2]) - two * m[j + 2]) - c[j + 2];
+        // gy = ((((s0 + 2 s1) + s2) - s6) - 2 s7) - s8 ; gx = ((((s0 + 2 s3) + s6) - s2) - 2 s5) - s8
+        const A gy = HillArith<T>::sub2((HillArith<T>::add2(a[j], a[j + 1]) + a[j + 2]) - c[j], c[j + 1]) - c[j + 2];
+        const A gx = HillArith<T>::sub2((HillArith<T>::add2(a[j], m[j]) + c[j]) - a[j + 2], m[j + 2]) - c[j + 2];
         float fy, fx;
         if (EXACT_INVERSE) {
           fy = HillArith<T>::mul((T)gy, inv_yres);
@@ -231,8 +244,6 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
             if (x0 + j < W) q[j] = (uint8_t)(packed >> (8 * j));
         }
       }
-#pragma unroll
-      for (int j = 0; j < 6; ++j) { a[j] = m[j]; m[j] = c[j]; }
     }
   }
 }
