@@ -409,10 +409,12 @@ def run_stencils(ctx):
         whole = make_dem(torch, 0, n, n, 99, nodata)
     px = n * n
     for name, label, halo_rows, halo_cols, process, extra, bpp, kernel in ops:
-        pitch = 4 if name == "movingmax" else 1     # 16-byte row pitch: tiles staged by TMA
+        pitch = 4 if name in ("movingmax", "hillshade") else 1     # 16-byte row pitch: TMA tiles / quad loads
         stored = parallel.pad_columns(parallel.exchange_halo(dem, halo_rows, nodata), halo_cols, nodata, pitch)
         if name == "movingmax":
             extra = extra + (stored.shape[2] - (n + 2 * halo_cols),)
+        if name == "hillshade":
+            extra = (dict(extra[0], pad=stored.shape[2] - (n + 2 * halo_cols)),)
         stored_whole = None
         if whole is not None:
             stored_whole = parallel.pad_columns(

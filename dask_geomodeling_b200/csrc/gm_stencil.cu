@@ -153,12 +153,14 @@ static_assert(HQ_AHEAD % 3 == 0, "the ring of three row sets must close over a b
 template <typename T, bool EXACT_INVERSE>
 __global__ void __launch_bounds__(32 * HS_WARPS, 4)
 hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T nodata, int has_nodata,
-                      T fill, int bands, int H, int W, double xres, double yres,
+                      T fill, int bands, int H, int W, int SW, int quad_loads, double xres, double yres,
                       double inv_xres, double inv_yres, int dst_aligned,
                       float sin_alt, float cos_alt_zsf, float cos_az, float sin_az, float square_zsf) {
+  // SW: columns of a source row (W + 2, or more when the window was padded to a 16-byte pitch);
+  // quad_loads: 4-byte cells on that pitch -- a lane fetches its four columns with ONE 16-byte
+  // load (they start at a multiple of four) instead of four loads 16 bytes apart
   typedef typename HillArith<T>::acc A;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int SW = W + 2;
   const int64_t in_plane = (int64_t)(H + 2) * SW, out_plane = (int64_t)H * W;
   const int strips_x = (W + HQ_COLS - 1) / HQ_COLS;
   const int strips_y = (H + HQ_ROWS - 1) / HQ_ROWS;
@@ -177,10 +179,22 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
 #pragma unroll
   for (int j = 0; j < 4; ++j) col[j] = min(x0 + j, last_col);
   auto clean = [&](T v) -> A { return (A)((has_nodata && v == nodata) ? fill : v); };
-  auto load_row = [&](int row, A (&w)[6]) {
+  const bool quad = sizeof(T) == 4 && quad_loads && x0 + 3 <= last_col;
+  auto fetch = [&](int row, T (&v)[4]) {
     const T* p = base + (int64_t)min(row, last_row) * SW;
+    if (sizeof(T) == 4 && quad) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + x0));
+      memcpy(&v[0], &q, 16);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = clean(__ldg(p + col[j]));
+      for (int j = 0; j < 4; ++j) v[j] = __ldg(p + col[j]);
+    }
+  };
+  auto load_row = [&](int row, A (&w)[6]) {
+    T v[4];
+    fetch(row, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = clean(v[j]);
     w[4] = shfl_down_any<A>(w[0], 1);
     w[5] = shfl_down_any<A>(w[1], 1);
   };
@@ -195,11 +209,7 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
   for (int r0 = 0; r0 < rows; r0 += HQ_AHEAD) {
     T next[HQ_AHEAD][4];
 #pragma unroll
-    for (int i = 0; i < HQ_AHEAD; ++i) {
-      const T* p = base + (int64_t)min(y0 + r0 + i + 2, last_row) * SW;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) next[i][j] = __ldg(p + col[j]);
-    }
+    for (int i = 0; i < HQ_AHEAD; ++i) fetch(y0 + r0 + i + 2, next[i]);
 #pragma unroll
     for (int i = 0; i < HQ_AHEAD; ++i) {
       const int r = r0 + i;
@@ -1300,7 +1310,7 @@ template <typename T> static T cast_fill(double fill) { return (T)fill; }
 
 template <typename T>
 static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int has_nodata,
-                         double fill, int bands, int H, int W, double xres, double yres,
+                         double fill, int bands, int H, int W, int SW, double xres, double yres,
                          double alt_deg, double az_deg, cudaStream_t s) {
   const double alt = alt_deg * (M_PI / 180.0), az = az_deg * (M_PI / 180.0);
   // math.radians(x) = x * (pi / 180) in CPython
@@ -1313,10 +1323,11 @@ static int run_hillshade(const Staged& in, Staged& out, const void* nodata, int 
   const int64_t qstrips = (int64_t)bands * qx * qy;
   const unsigned qblocks = (unsigned)((qstrips + HS_WARPS - 1) / HS_WARPS);
   const int aligned = ((uintptr_t)out.dev % 4 == 0) && (W % 4 == 0);
+  const int quad_loads = sizeof(T) == 4 && SW % 4 == 0 && (uintptr_t)in.dev % 16 == 0;
 #define GM_HQ(EXACT)                                                                                \
   hillshade_quad_kernel<T, EXACT><<<qblocks, 32 * HS_WARPS, 0, s>>>(                                \
       (const T*)in.dev, (uint8_t*)out.dev, has_nodata ? read_scalar<T>(nodata) : T(0), has_nodata,   \
-      cast_fill<T>(fill), bands, H, W, xres, yres, 1.0 / xres, 1.0 / yres, aligned,                  \
+      cast_fill<T>(fill), bands, H, W, SW, quad_loads, xres, yres, 1.0 / xres, 1.0 / yres, aligned,  \
       (float)sin(alt), (float)(cos(alt) * zsf), (float)cos(az), (float)sin(az), (float)(zsf * zsf))
   if (exact) GM_HQ(true); else GM_HQ(false);
 #undef GM_HQ
@@ -1506,10 +1517,13 @@ extern "C" int gm_hillshade(const GmArray* src, GmArray* dst, const void* nodata
   return with_staged(src, dst, stream, [&](Staged& in, Staged& out, cudaStream_t s) -> int {
     const int bands = (int)dst->shape[0], H = (int)dst->shape[1], W = (int)dst->shape[2];
     if (dst->dtype != GM_U8) return fail("gm_hillshade: output must be uint8");
-    if (src->shape[0] != bands || src->shape[1] != H + 2 || src->shape[2] != W + 2)
+    // columns beyond W + 2 are pitch padding (ignored): with a 16-byte row pitch a lane reads its
+    // four source columns with one load
+    if (src->shape[0] != bands || src->shape[1] != H + 2 || src->shape[2] < W + 2)
       return fail("gm_hillshade: source must carry a 1 pixel halo");
     GM_DISPATCH_NUMERIC(src->dtype, run_hillshade<T>(in, out, nodata, has_nodata, fill, bands, H, W,
-                                                     xres, yres, altitude_deg, azimuth_deg, s));
+                                                     (int)src->shape[2], xres, yres, altitude_deg,
+                                                     azimuth_deg, s));
   });
 }
 

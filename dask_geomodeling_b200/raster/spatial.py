@@ -276,8 +276,15 @@ class HillShade(BaseSingle):
             return [(self.store, request)]
         x1, y1, x2, y2 = request["bbox"]
         resolution = ((x2 - x1) / request["width"], (y2 - y1) / request["height"])
+        # 4-byte rasters: a few more columns on the right make a row of the window a whole number
+        # of 16-byte groups -- a lane of the kernel then reads its four columns with one load
+        pad = (-enlarged["width"]) % 4 if np.dtype(self.store.dtype).itemsize == 4 else 0
+        if pad:
+            ex1, ey1, ex2, ey2 = enlarged["bbox"]
+            enlarged["bbox"] = (ex1, ey1, ex2 + pad * resolution[0], ey2)
+            enlarged["width"] += pad
         kwargs = dict(resolution=resolution, altitude=self.altitude, azimuth=self.azimuth,
-                      fill=self.fill)
+                      fill=self.fill, pad=pad)
         return [(self.store, enlarged), (kwargs, None)]
 
     @staticmethod
@@ -289,7 +296,7 @@ class HillShade(BaseSingle):
         xres, yres = process_kwargs["resolution"]
         holder, nodata_ptr, has_nodata = _nodata_arg(source, data["no_data_value"])
         out = _call_stencil(
-            source, (t, h - 2, w - 2), np.uint8,
+            source, (t, h - 2, w - 2 - int(process_kwargs.get("pad", 0))), np.uint8,
             lambda lib, src, dst, stream: lib.gm_hillshade(
                 src, dst, nodata_ptr, has_nodata, float(process_kwargs["fill"]), float(xres),
                 float(yres), float(process_kwargs["altitude"]), float(process_kwargs["azimuth"]),

@@ -209,7 +209,9 @@ int  gm_resample_nn(const GmArray* src, GmArray* dst, const void* nodata,
                     double col0, double col_step, double row0, double row_step,
                     void* stream);
 
-/* stencils (raster/spatial.py): src carries the halo the reference requests */
+/* stencils (raster/spatial.py): src carries the halo the reference requests.  gm_hillshade and
+ * gm_moving_max accept rows with extra columns on the right (src.shape[2] >= dst.shape[2] + halo):
+ * on a 16-byte row pitch HillShade reads four columns per load and MovingMax stages tiles by TMA */
 int  gm_hillshade(const GmArray* src, GmArray* dst, const void* nodata, int has_nodata,
                   double fill, double xres, double yres, double altitude_deg,
                   double azimuth_deg, void* stream);            /* :353-417 */

@@ -1,6 +1,7 @@
 """Stencil kernels (Dilate, MovingMax, Smooth, HillShade) against the oracle, which
 calls the same scipy.ndimage routines the reference calls."""
 import numpy as np
+from datetime import datetime as Datetime
 import pytest
 
 from dask_geomodeling_b200 import raster, workloads
@@ -78,6 +79,27 @@ def test_smooth_arithmetic_modes(mode, ulps, dtype):
         assert delta.max() <= ulps * np.spacing(np.float32(np.abs(expected).max()))
     if mode == "fma" and dtype == "f4":
         assert (delta > 0).mean() < 0.05
+
+
+@pytest.mark.parametrize("width", [101, 102, 130, 253])
+def test_hillshade_on_a_padded_row_pitch(width):
+    """Rows padded to whole 16-byte groups (what HillShade.get_sources_and_requests asks its store
+    for): the quad-load path gives the very bytes of the unpadded call, and the block's own
+    request equals the oracle on the unpadded window."""
+    values, nodata = dem((2, 70, width), 5, dtype="f4")
+    kwargs = dict(resolution=(0.5, 0.5), altitude=45.0, azimuth=315.0, fill=0)
+    plain = raster.HillShade.process({"values": values, "no_data_value": nodata}, kwargs)
+    pad = (-width) % 4
+    padded = np.pad(values, ((0, 0), (0, 0), (0, pad)), constant_values=nodata)
+    got = raster.HillShade.process({"values": padded, "no_data_value": nodata}, dict(kwargs, pad=pad))
+    assert got["values"].shape == (2, 68, width - 2)
+    np.testing.assert_array_equal(np.asarray(got["values"]), np.asarray(plain["values"]))
+    src = raster.MemorySource(values, nodata, "EPSG:28992", 0.5, (0.0, 35.0), time_first=0, time_delta=1000)
+    block = raster.HillShade(src)
+    request = dict(mode="vals", bbox=(0.5, 0.5, 0.5 * (width - 1), 34.5), width=width - 2, height=68,
+                   projection="EPSG:28992", start=Datetime(1970, 1, 1), stop=Datetime(1970, 1, 1, 0, 0, 1))
+    through_block = block.get_data(**request)
+    np.testing.assert_array_equal(through_block["values"], np.asarray(plain["values"]))
 
 
 @pytest.mark.parametrize("fill", [0, 7.5])
