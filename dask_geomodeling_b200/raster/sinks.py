@@ -1,9 +1,10 @@
-"""Raster sinks: tiles of a view written as GeoTIFF files, merged into a VRT
-(reference: raster/sinks.py:18-204).
+"""Raster sinks: tiles of a view written as GeoTIFF files and merged into a VRT
+(interface of the reference's raster/sinks.py:18-204: ``RasterFileSink(source, url)``,
+``RasterFileSink.merge_files(path, target)``, ``to_file(source, url, tile_size, **request)``).
 
-The tile values come out of the CUDA path (``RasterTiler`` cuts the request, every tile is
-evaluated on the device and downloaded once); encoding them is host work
-(``dask_geomodeling_b200/geotiff.py``: 256 x 256 deflate tiles on a thread pool, no GDAL).
+The tile values come out of the CUDA path -- ``RasterTiler`` cuts the request, every tile is
+evaluated on the device and downloaded once -- and are encoded on the host by
+``dask_geomodeling_b200/geotiff.py`` (256 x 256 deflate tiles on a thread pool, no GDAL).
 """
 import glob
 import os
@@ -18,109 +19,102 @@ from .parallelize import RasterTiler
 __all__ = ["RasterFileSink", "to_file"]
 
 
+def _tile_path(directory_url, name):
+    directory = utils.safe_abspath(directory_url)
+    os.makedirs(directory, exist_ok=True)
+    return os.path.join(directory, name + ".tif")
+
+
 class RasterFileSink(BaseSingle):
-    """Write raster data to GeoTIFF files in a specified directory.
-
-    Use RasterFileSink.merge_files to merge tiles into a VRT file.
-
-    Args:
-      source (RasterBlock): The raster block the data is coming from.
-      url (str): The target directory to put the files in. If relative, it is taken relative to
-        the geomodeling.root setting.
-    """
+    """Write the 'vals' response of ``source`` as one GeoTIFF per request into the directory
+    ``url`` (relative paths start at the ``geomodeling.root`` setting).  The file is named after
+    the request's token, so the tiles of a ``RasterTiler`` land next to each other; requests in
+    other modes pass through.  ``merge_files`` turns such a directory into a VRT."""
 
     def __init__(self, source, url):
         if not isinstance(source, RasterBlock):
             raise TypeError("'{}' object is not allowed".format(type(source)))
         super().__init__(source, utils.safe_file_url(url))
 
-    @property
-    def url(self):
-        return self.args[1]
+    url = property(lambda self: self.args[1])
 
     def get_sources_and_requests(self, **request):
-        if request["mode"] != "vals":
-            return [(self.store, request), ({}, None)]
-        process_kwargs = {
-            "url": self.url,
-            "hash": tokenize(request)[:7],
-            "bbox": request["bbox"],
-            "projection": request["projection"],
-        }
-        return [(self.store, request), (process_kwargs, None)]
+        target = {}
+        if request["mode"] == "vals":
+            target = {"url": self.url, "hash": tokenize(request)[:7],
+                      "bbox": request["bbox"], "projection": request["projection"]}
+        return [(self.store, request), (target, None)]
 
     @staticmethod
     def process(data, process_kwargs):
-        if not process_kwargs:
-            return data    # non-vals mode: forward data as-is
+        if not process_kwargs:            # time / meta requests: nothing to write
+            return data
         if data is None or "values" not in data:
             return None
-        values = data["values"]
+        values, no_data_value = data["values"], data["no_data_value"]
         if _native.is_device(values):
             values = np.asarray(values)
-        no_data_value = data["no_data_value"]
         if values.ndim != 3 or values.shape[0] != 1:
             raise ValueError("Expected a single-band raster (shape (1, H, W)), got shape {}".format(values.shape))
-        band_data = values[0]
-        if no_data_value is not None and np.all(band_data == no_data_value):
-            return None    # nothing but no data: no file
-        height, width = band_data.shape
-        path = utils.safe_abspath(process_kwargs["url"])
-        os.makedirs(path, exist_ok=True)
-        x1, y1, x2, y2 = process_kwargs["bbox"]
-        geo_transform = (x1, (x2 - x1) / width, 0, y2, 0, -(y2 - y1) / height)
-        geotiff.write_geotiff(os.path.join(path, process_kwargs["hash"] + ".tif"), band_data, geo_transform,
+        band = values[0]
+        if no_data_value is not None and (band == no_data_value).all():
+            return None                   # an empty tile leaves no file behind
+        rows, cols = band.shape
+        west, south, east, north = process_kwargs["bbox"]
+        geo_transform = (west, (east - west) / cols, 0, north, 0, (south - north) / rows)
+        geotiff.write_geotiff(_tile_path(process_kwargs["url"], process_kwargs["hash"]), band, geo_transform,
                               process_kwargs["projection"], no_data_value)
         return None
 
     @staticmethod
     def merge_files(path, target):
-        """Merge GeoTIFF files (the output of this Block) into a VRT file.
+        """Write the VRT ``target`` over all ``*.tif`` files in the directory ``path``."""
+        directory, vrt = utils.safe_abspath(path), utils.safe_abspath(target)
+        if os.path.exists(vrt):
+            raise IOError("Target '{}' already exists".format(vrt))
+        tiles = glob.glob(os.path.join(directory, "*.tif"))
+        if not tiles:
+            raise IOError("No source .tif files found in '{}'".format(directory))
+        geotiff.write_vrt(vrt, tiles)
 
-        Args:
-          path (str): The source directory containing .tif files.
-          target (str): The target .vrt file path.
-        """
-        path = utils.safe_abspath(path)
-        target = utils.safe_abspath(target)
-        if os.path.exists(target):
-            raise IOError("Target '{}' already exists".format(target))
-        source_paths = glob.glob(os.path.join(path, "*.tif"))
-        if len(source_paths) == 0:
-            raise IOError("No source .tif files found in '{}'".format(path))
-        geotiff.write_vrt(target, source_paths)
+
+def _complete_request(source, request):
+    """``to_file`` request with the reference's defaults: the source's projection, the envelope
+    of its geometry and its own cell size where the caller gave none."""
+    request = dict(request, mode="vals")
+    missing = "Cannot determine the {} from the source raster. Please provide {}."
+    if "projection" not in request:
+        if source.projection is None:
+            raise ValueError(missing.format("projection", "a 'projection' argument"))
+        request["projection"] = source.projection
+    if "bbox" not in request:
+        footprint = source.geometry
+        if footprint is None:
+            raise ValueError(missing.format("extent", "a 'bbox' argument"))
+        if hasattr(footprint, "GetEnvelope"):          # an OGR geometry: (x1, x2, y1, y2)
+            west, east, south, north = footprint.GetEnvelope()
+        else:
+            west, south, east, north = footprint.bounds
+        request["bbox"] = (west, south, east, north)
+    if not ("width" in request and "height" in request):
+        grid = source.geo_transform
+        if grid is None:
+            raise ValueError(missing.format("pixel size", "'width' and 'height' arguments"))
+        west, south, east, north = request["bbox"]
+        request["width"] = int(round((east - west) / abs(float(grid[1]))))
+        request["height"] = int(round((north - south) / abs(float(grid[5]))))
+    return request
 
 
 def to_file(source, url, tile_size, **request):
-    """Export data from a RasterBlock to disk: tiled GeoTIFFs merged into a VRT at ``url``
-    (reference raster/sinks.py:148-204; same defaults for projection, bbox, width and height)."""
-    request["mode"] = "vals"
-    if "projection" not in request:
-        if source.projection is None:
-            raise ValueError("Cannot determine the projection from the source raster. "
-                             "Please provide a 'projection' argument.")
-        request["projection"] = source.projection
-    if "bbox" not in request:
-        if source.geometry is None:
-            raise ValueError("Cannot determine the extent from the source raster. "
-                             "Please provide a 'bbox' argument.")
-        if hasattr(source.geometry, "GetEnvelope"):
-            x1, x2, y1, y2 = source.geometry.GetEnvelope()
-        else:
-            x1, y1, x2, y2 = source.geometry.bounds
-        request["bbox"] = x1, y1, x2, y2
-    if "width" not in request or "height" not in request:
-        if source.geo_transform is None:
-            raise ValueError("Cannot determine the pixel size from the source raster. "
-                             "Please provide 'width' and 'height' arguments.")
-        geo_transform = source.geo_transform
-        x1, y1, x2, y2 = request["bbox"]
-        request["width"] = int(round((x2 - x1) / abs(float(geo_transform[1]))))
-        request["height"] = int(round((y2 - y1) / abs(float(geo_transform[5]))))
-    path = utils.safe_abspath(url)
-    if os.path.isdir(path):
-        path = os.path.join(path, "output.vrt")
-    tiles_dir = os.path.join(os.path.split(path)[0], "tiles")
-    sink = RasterFileSink(source, tiles_dir)
-    RasterTiler(sink, tile_size).get_data(**request)
-    RasterFileSink.merge_files(tiles_dir, path)
+    """Export ``source`` to disk: GeoTIFF tiles of at most ``tile_size`` cells in a ``tiles``
+    directory next to the VRT ``url`` that mosaics them (``url`` may be a directory: the VRT is
+    then ``output.vrt`` inside it).  ``bbox``, ``projection``, ``width`` and ``height`` default to
+    the source's own extent, projection and cell size; ``start`` / ``stop`` select the frame."""
+    request = _complete_request(source, request)
+    vrt = utils.safe_abspath(url)
+    if os.path.isdir(vrt):
+        vrt = os.path.join(vrt, "output.vrt")
+    tiles = os.path.join(os.path.dirname(vrt), "tiles")
+    RasterTiler(RasterFileSink(source, tiles), tile_size).get_data(**request)
+    RasterFileSink.merge_files(tiles, vrt)
