@@ -103,6 +103,62 @@ def test_zonal_stats(dtype, statistic):
         np.testing.assert_array_equal(got[0], expected)
 
 
+@pytest.mark.parametrize("resident", [False, True])
+@pytest.mark.parametrize("dtype", ["f4", "i2"])
+def test_stripe_partials_and_finalisation(dtype, resident):
+    """The stripe entry points of the multi-GPU path in ONE process: the raster is cut in three row
+    stripes, every stripe is reduced by gm_zonal_partials_device (only the polygons with rows in
+    the stripe are visited; a resident soup keeps its preparation between calls and leaves the
+    overflow flag to the finalisation), the partial vectors are added / minimised as the
+    all-reduces would, gm_zonal_finalize_device forms the statistic: equal to the oracle on the
+    whole raster, call after call."""
+    import ctypes
+
+    from dask_geomodeling_b200 import _native
+    from dask_geomodeling_b200.geometry.aggregate import _STAT_CODES, _frame_descriptor
+
+    h, w = 150, 130
+    rng = np.random.default_rng(21)
+    nodata = R.dtype_max(dtype)
+    frame = (rng.uniform(0, 100, (h, w)) if dtype == "f4" else rng.integers(0, 100, (h, w))).astype(dtype)
+    frame[rng.random((h, w)) < 0.1] = nodata
+    polys = random_polygons(60, 150, seed=8, concave=True)
+    polys.append([[(300.0, 300.0), (310.0, 300.0), (310.0, 310.0)]])      # outside the raster
+    n = len(polys)
+    soup = utils.PolygonSoup(to_geometries(polys))
+    if resident:
+        soup.to_device()
+    lib = _native.lib()
+    holder, nodata_ptr = _native.scalar_ptr(nodata, frame.dtype)
+    bounds = [(0, 47), (47, 48), (48, 150)]                               # a one-row stripe in the middle
+    stripes = [_native.DeviceArray.from_host(np.ascontiguousarray(frame[np.newaxis, a:b])) for a, b in bounds]
+    sums_dev = _native.DeviceArray((3 * n,), "f8")
+    extremes_dev = _native.DeviceArray((2 * n,), "f8")
+    out, covered = np.empty(n, "f4"), np.empty(n, "i8")
+    for statistic in ("mean", "sum", "count", "min", "max", "mean"):
+        expected, no_cells = oracle_zonal(frame, nodata, polys, (0, 0, w, h), statistic)
+        sums, extremes = np.zeros(3 * n), np.full(2 * n, np.finfo("f8").max)
+        for (a, b), stripe in zip(bounds, stripes):
+            geo = (ctypes.c_double * 6)(*utils.GeoTransform.from_bbox((0, h - b, w, h - a), b - a, w))
+            polys_struct = soup.as_struct()
+            desc = _frame_descriptor(stripe, 0)
+            _native.check(lib.gm_zonal_partials_device(
+                ctypes.byref(desc), nodata_ptr, 1, ctypes.byref(polys_struct), geo, None, 0, b - a,
+                sums_dev.ptr, extremes_dev.ptr, _STAT_CODES[statistic], _native.current_stream()))
+            sums += np.asarray(sums_dev)
+            extremes = np.minimum(extremes, np.asarray(extremes_dev))
+        totals = _native.DeviceArray.from_host(sums)
+        lowest = _native.DeviceArray.from_host(extremes)
+        _native.check(lib.gm_zonal_finalize_device(
+            totals.ptr, lowest.ptr, n, _STAT_CODES[statistic], out.ctypes.data, covered.ctypes.data,
+            ctypes.byref(polys_struct), _native.current_stream()))
+        assert np.nonzero(covered == 0)[0].tolist() == no_cells
+        if statistic in ("sum", "mean"):
+            np.testing.assert_allclose(out, expected, rtol=1e-6, equal_nan=True)
+        else:
+            np.testing.assert_array_equal(out, expected)
+
+
 @pytest.mark.parametrize("kind", ["uniform", "few_values", "constant", "wide_range"])
 @pytest.mark.parametrize("statistic", ["median", "p90", "p1.5"])
 def test_zonal_order_statistics_convex_float32(kind, statistic):
