@@ -82,15 +82,19 @@ def _bounds(soup, geometries):
 def _prepared(polygons):
     """Geometry objects, CSR soup and bounding boxes of a polygon list, built once per list
     object (the list is an argument of the block, i.e. it lives as long as the view)."""
+    # the list must not be edited in place afterwards; a sample of its elements' identities
+    # (first, last, 30 in between) catches the edits that keep its length
+    n = len(polygons)
+    sample = tuple(id(polygons[i]) for i in sorted(set(np.linspace(0, n - 1, 32).astype(int).tolist()))) if n else ()
     hit = _PREPARED.get(id(polygons))
-    if hit is not None and hit[0] is polygons and len(hit[1]) == len(polygons):
+    if hit is not None and hit[0] is polygons and len(hit[1]) == n and hit[4] == sample:
         return hit[1], hit[2], hit[3]
     geometries = [_as_geometry(p) for p in polygons]
     soup = utils.PolygonSoup(geometries)
     bounds = _bounds(soup, geometries)
     if len(_PREPARED) >= 8:
         _PREPARED.pop(next(iter(_PREPARED)))
-    _PREPARED[id(polygons)] = (polygons, geometries, soup, bounds)
+    _PREPARED[id(polygons)] = (polygons, geometries, soup, bounds, sample)
     return geometries, soup, bounds
 
 
