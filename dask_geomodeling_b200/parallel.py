@@ -285,6 +285,22 @@ def _as_payload(tensor):
     return tensor.numpy()
 
 
+def _visible_to_library(tensor):
+    """The library launches on its own (non-blocking) stream unless the caller put it on torch's
+    (`_native.use_stream`): what torch has queued for `tensor` -- halo rows that just landed, pads --
+    must be complete before a kernel of the library reads it."""
+    if not getattr(tensor, "is_cuda", False):
+        return
+    import torch
+
+    from . import _native
+
+    mine = _native.current_stream()
+    current = torch.cuda.current_stream(tensor.device)
+    if mine is None or int(mine) != int(current.cuda_stream):
+        current.synchronize()
+
+
 def stencil_striped(process, local, no_data_value, halo_rows, halo_cols, *process_args, group=None):
     """Run a stencil block's ``process`` (Smooth, MovingMax, Dilate, HillShade) on a row
     stripe of a raster that is sharded over the ranks.
@@ -297,6 +313,7 @@ def stencil_striped(process, local, no_data_value, halo_rows, halo_cols, *proces
     haloed = pad_columns(haloed, halo_cols, no_data_value)
     from .core import fusion
 
+    _visible_to_library(haloed)
     with fusion.device_resident():
         return process({"values": _as_payload(haloed), "no_data_value": no_data_value}, *process_args)
 
@@ -324,6 +341,7 @@ def stencil_haloed(process, haloed, no_data_value, halo_rows, halo_cols, *proces
     if not (overlap and world > 1 and halo_rows > 0 and haloed.shape[0] == 1 and rows >= 4 * halo_rows
             and hasattr(haloed, "is_cuda")):
         refresh_halo(haloed, halo_rows, halo_cols, group)
+        _visible_to_library(haloed)
         with fusion.device_resident():
             return process({"values": _as_payload(haloed), "no_data_value": no_data_value}, *process_args)
     if not getattr(haloed, "_stripes_checked", False):     # once per stored stripe, not per step
@@ -333,6 +351,7 @@ def stencil_haloed(process, haloed, no_data_value, halo_rows, halo_cols, *proces
         except AttributeError:
             pass
     h = halo_rows
+    _visible_to_library(haloed)
     works, landing = _post_halo(haloed, h, group)
     target = _state.RowWindow(rows)
     pieces = []
@@ -345,6 +364,7 @@ def stencil_haloed(process, haloed, no_data_value, halo_rows, halo_cols, *proces
     with fusion.device_resident(), _state.into_row_window(target):
         window(h, rows + h, h)                  # interior: needs no neighbour row
         _land_halo(haloed, works, landing)
+        _visible_to_library(haloed)
         window(0, 3 * h, 0)                     # the first and the last `h` output rows
         window(rows - h, rows + 2 * h, rows - h)
     result = dict(pieces[0])
