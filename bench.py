@@ -132,6 +132,14 @@ class NvmlSampler(object):
         pynvml.nvmlInit()
         self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
         self.period = period
+        # the first queries of a process take tens to hundreds of milliseconds on a fresh box
+        # (a 1000-step run once ended with ONE sample): pay that here, before the thread starts
+        for _ in range(2):
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            try:
+                pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
         self.sm, self.reasons = [], set()
         self.running = True
         self.thread = threading.Thread(target=self._loop, daemon=True)
@@ -155,6 +163,10 @@ class NvmlSampler(object):
                 pass
             time.sleep(self.period)
 
+    def mark(self):
+        """The timed region starts here (samples before it were taken under the warm-up load)."""
+        self.marked = len(self.sm)
+
     def stop(self):
         self.running = False
         self.thread.join(timeout=2)
@@ -163,7 +175,8 @@ class NvmlSampler(object):
         except Exception:
             sm_max = None
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "samples_in_timed_region": len(self.sm) - getattr(self, "marked", 0), "source": "nvml"}
 
 
 class SmiSampler(object):
@@ -188,6 +201,9 @@ class SmiSampler(object):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
+    def mark(self):
+        self.marked = len(self.samples)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -211,7 +227,8 @@ class SmiSampler(object):
                 if flag.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": len(self.samples) - getattr(self, "marked", 0), "source": "nvidia-smi"}
 
 
 def make_sampler(index):
@@ -740,11 +757,21 @@ def run_b200(args):
         leaf_types = [(p["values"].dtype, p["no_data_value"]) for p in leaf_payloads]
         compiled = _program.CompiledProgram([fusion.build_expression(plan)], leaf_types)
         out = _native.DeviceArray((1, size, size), compiled.results[0].dtype)
-        for _ in range(warmup):
-            compiled.launch(inputs, [out])
-        ctx.barrier()
+        # The clock sampler runs from the warm-up on: the warm-up is stretched to >= 60 ms of the
+        # SAME launches (a 20-step timed region lasts 6.5 ms, one NVML query about a millisecond),
+        # so that the median clock and the throttle reasons describe the load the timed region
+        # runs under; `samples_in_timed_region` says how many fell inside it.
         sampler = make_sampler(local_rank) if rank == 0 else None
-        time.sleep(0.005)          # the sampler thread is running before the first timed launch
+        t_load = time.perf_counter()
+        done = 0
+        while done < warmup or (time.perf_counter() - t_load < 0.06 and done < 4096):
+            for _ in range(16):
+                compiled.launch(inputs, [out])
+            stream.synchronize()
+            done += 16
+        ctx.barrier()
+        if sampler is not None:
+            sampler.mark()
         launches_before = _native.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record(stream)
