@@ -2404,6 +2404,11 @@ struct ResidentPolygons {
   int* error = nullptr;       // crossing-overflow flag of calls whose check is deferred
   std::mutex lock;
   std::vector<std::shared_ptr<PreparedPolygons>> prepared;   // most recent last, <= 4
+  // the grid of the last call that found nothing prepared: an entry is only built (with plain,
+  // device-synchronising allocations) when the SAME grid comes again -- a sweep of ever new
+  // request windows over one soup keeps the stream-ordered per-call path
+  struct Seen { double geo[6]; int height, width; int64_t rows[2]; };
+  std::vector<Seen> seen;     // the last 8 such grids
 };
 
 struct PolyUpload {
@@ -2493,13 +2498,29 @@ static int prepare_polygons(const GmPolygons* polys, const double* geo, int heig
     }
   }
   if (!u.shared) {
+    bool build = false;     // keep what this call prepares?
+    if (keep) {
+      std::lock_guard<std::mutex> guard(resident->lock);
+      ResidentPolygons::Seen now;
+      memcpy(now.geo, geo, sizeof(now.geo));
+      now.height = height; now.width = width; now.rows[0] = row_begin; now.rows[1] = row_end;
+      for (size_t i = 0; i < resident->seen.size() && !build; ++i) {
+        const ResidentPolygons::Seen& o = resident->seen[i];
+        build = memcmp(o.geo, now.geo, sizeof(now.geo)) == 0 && o.height == height && o.width == width &&
+                o.rows[0] == row_begin && o.rows[1] == row_end;
+      }
+      if (!build) {
+        if (resident->seen.size() >= 8) resident->seen.erase(resident->seen.begin());
+        resident->seen.push_back(now);
+      }
+    }
     // (plain cudaMalloc for arrays that outlive the call: stream-ordered frees of another
     //  stream's pool blocks are not wanted here)
     auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t {
-      return keep ? cudaMalloc(ptr, bytes) : cudaMallocAsync(ptr, bytes, s);
+      return build ? cudaMalloc(ptr, bytes) : cudaMallocAsync(ptr, bytes, s);
     };
     std::shared_ptr<PreparedPolygons> q;
-    if (keep) q = std::make_shared<PreparedPolygons>();
+    if (build) q = std::make_shared<PreparedPolygons>();
     void *px = nullptr, *py = nullptr, *miny = nullptr, *maxy = nullptr, *active = nullptr, *n_active = nullptr;
     cudaError_t e = alloc(&px, sizeof(double) * (nv > 0 ? nv : 1));
     if (e == cudaSuccess) e = alloc(&py, sizeof(double) * (nv > 0 ? nv : 1));

@@ -309,7 +309,8 @@ int  gm_segment_order_stat(const void* values, int32_t dtype, const int64_t* off
  * everything) lets the stripe pass compute only what the statistic needs: the sums for
  * sum / mean / count, one extreme for min / max.  With a resident soup (gm_polygons_upload) the
  * stripe pass keeps what it derives from the soup for this grid (pixel-space vertices, row
- * ranges, the ids of the polygons with rows in the stripe) for the next call and does not
+ * ranges, the ids of the polygons with rows in the stripe) from the second call on the same grid
+ * on (a sweep of ever new windows stays on the stream-ordered per-call path) and does not
  * synchronise: its crossing-overflow flag is read back by gm_zonal_finalize_device, which takes
  * the same `polys` (NULL: nothing deferred).                                                  */
 int  gm_zonal_partials_device(const GmArray* raster, const void* nodata, int has_nodata,
