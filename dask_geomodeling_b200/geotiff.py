@@ -81,8 +81,10 @@ def _geo_keys(projection):
     return directory, ascii_params
 
 
-def write_geotiff(path, values, geo_transform, projection, no_data_value=None, compress=True, tile=TILE):
-    """Write ``values`` ((h, w) or (bands, h, w)) as a tiled GeoTIFF; see the module docstring."""
+def write_geotiff(path, values, geo_transform, projection, no_data_value=None, compress=True, tile=TILE,
+                  bigtiff=None):
+    """Write ``values`` ((h, w) or (bands, h, w)) as a tiled GeoTIFF; see the module docstring.
+    ``bigtiff``: None = when the file would pass 4 GB (GDAL's BIGTIFF=IF_NEEDED), True / False = forced."""
     values = np.asarray(values)
     if values.ndim == 2:
         values = values[np.newaxis]
@@ -107,7 +109,7 @@ def write_geotiff(path, values, geo_transform, projection, no_data_value=None, c
 
     n_tiles = bands * tiles_y * tiles_x
     chunks = list(_pool().map(encode, range(n_tiles))) if n_tiles > 1 else [encode(0)]
-    big = sum(len(c) for c in chunks) + 16 * n_tiles + 4096 > 0xFFFF0000
+    big = sum(len(c) for c in chunks) + 16 * n_tiles + 4096 > 0xFFFF0000 if bigtiff is None else bool(bigtiff)
 
     tags = [
         (256, _LONG, [width]), (257, _LONG, [height]),

@@ -67,6 +67,22 @@ def test_bands_wkt_and_geographic(tmp_path):
     assert tif._geo_key(1024) == 2 and tif._geo_key(2048) == 4326
 
 
+def test_bigtiff_layout(tmp_path):
+    """The 64-bit layout (files past 4 GB) forced on a small raster: offsets and counts are 8-byte
+    words, the directory has 20-byte entries; our reader and libtiff read it back."""
+    values = np.arange(300 * 520, dtype="f4").reshape(300, 520)
+    path = str(tmp_path / "big.tif")
+    geotiff.write_geotiff(path, values, GT, "EPSG:28992", -9999.0, bigtiff=True)
+    with open(path, "rb") as f:
+        assert struct.unpack("<2sHHH", f.read(8)) == (b"II", 43, 8, 0)
+    tif = geotiff.GeoTiff(path)
+    assert tif._big and tif.geo_transform == GT and tif.no_data_value == -9999.0
+    np.testing.assert_array_equal(tif.read()[0], values)
+    np.testing.assert_array_equal(tif.read_window(0, 1, 250, 300, 500, 520)[0], values[250:, 500:])
+    with PIL_Image.open(path) as image:
+        np.testing.assert_array_equal(np.asarray(image), values)
+
+
 def test_reads_files_of_other_writers(tmp_path):
     """Strips, big-endian order, the horizontal predictor and chunky samples do not come out of
     our writer: a strip file written by Pillow and hand-made files cover the reader."""
