@@ -240,8 +240,9 @@ hillshade_quad_kernel(const T* __restrict__ src, uint8_t* __restrict__ dst, T no
         float inv_len;
         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_len) : "f"(__fmaf_rn(square_zsf, xx_plus_yy, 1.0f)));
         const float cang = num * inv_len;
-        const int grey = (int)(255.0f * cang);
-        const unsigned out = (cang <= 0.0f) ? 0u : ((unsigned)grey & 0xffu);
+        // np.where(cang <= 0, 0, 255 * cang).astype(uint8): the unsigned conversion truncates and
+        // sends negative products (and NaN) to 0 by itself -- no compare / select
+        const unsigned out = __float2uint_rz(255.0f * cang) & 0xffu;
         packed |= out << (8 * j);
       }
       if (lane_writes && r < rows) {
