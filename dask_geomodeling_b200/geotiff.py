@@ -9,7 +9,7 @@ there is small and fully specified by TIFF 6.0 + the GeoTIFF 1.1 key directory:
   256 x 256 tiles, Adobe-deflate (code 8), ModelPixelScale + ModelTiepoint, a GeoKey directory with
   the EPSG code, the ``GDAL_NODATA`` ASCII tag (42113); BigTIFF when the file passes 4 GB.
 * ``GeoTiff``: header of a TIFF / BigTIFF (both byte orders; strips or tiles; uncompressed or
-  deflate; horizontal predictor; chunky or planar samples) and ``read_window``, which inflates only
+  deflate / LZW; horizontal predictor; chunky or planar samples) and ``read_window``, which inflates only
   the tiles a request touches.
 * ``write_vrt`` / ``Mosaic``: the VRT ``gdal.BuildVRT`` makes of equally-gridded tiles
   (`raster/sinks.py:126-145`) and its reader (sources pasted by their ``DstRect``).
@@ -173,6 +173,42 @@ def write_geotiff(path, values, geo_transform, projection, no_data_value=None, c
     os.replace(tmp, path)    # a reader never sees half a file
 
 
+def _lzw_decode(data):
+    """TIFF's LZW (compression 5): MSB-first codes of 9..12 bits, ClearCode 256, EndOfInformation
+    257, the code width grows one entry early.  Pure Python -- a slow path for files of other
+    writers (GDAL's own default is uncompressed, the sink of this package writes deflate)."""
+    table = [bytes([i]) for i in range(256)] + [b"", b""]
+    out = bytearray()
+    bits = value = 0
+    width, previous = 9, None
+    for byte in data:
+        value = (value << 8) | byte
+        bits += 8
+        while bits >= width:
+            bits -= width
+            code = (value >> bits) & ((1 << width) - 1)
+            if code == 257:
+                return bytes(out)
+            if code == 256:
+                del table[258:]
+                width, previous = 9, None
+                continue
+            if previous is None:
+                entry = table[code]
+            elif code < len(table):
+                entry = table[code]
+                table.append(previous + entry[:1])
+            else:
+                entry = previous + previous[:1]
+                table.append(entry)
+            out += entry
+            previous = entry
+            if len(table) >= (1 << width) - 1 and width < 12:
+                width += 1
+        value &= (1 << bits) - 1
+    return bytes(out)
+
+
 class GeoTiff(object):
     """Header of a (Big)TIFF file; pixels are read per window."""
 
@@ -203,8 +239,8 @@ class GeoTiff(object):
             raise NotImplementedError("TIFF samples of {} bits".format(t.get(258)))
         self.dtype = np.dtype("{}{}".format(kind, bits // 8))
         self.compression = int(t.get(259, [1])[0])
-        if self.compression not in (1, 8, 32946):
-            raise NotImplementedError("TIFF compression scheme {} (only none and deflate)".format(self.compression))
+        if self.compression not in (1, 5, 8, 32946):
+            raise NotImplementedError("TIFF compression scheme {} (only none, LZW and deflate)".format(self.compression))
         self.predictor = int(t.get(317, [1])[0])
         if self.predictor not in (1, 2):
             raise NotImplementedError("TIFF predictor {}".format(self.predictor))
@@ -327,7 +363,9 @@ class GeoTiff(object):
         with open(f_path, "rb") as f:
             f.seek(offset)
             raw = f.read(count)
-        if self.compression != 1:
+        if self.compression == 5:
+            raw = _lzw_decode(raw)
+        elif self.compression != 1:
             raw = zlib.decompress(raw)
         block = np.frombuffer(raw, dtype=self.dtype.newbyteorder(self._e),
                               count=rows * self.block_w * samples).reshape(rows, self.block_w, samples)

@@ -130,9 +130,25 @@ def test_reads_files_of_other_writers(tmp_path):
     assert tif.geo_transform is None and tif.projection is None
 
 
+@pytest.mark.parametrize("dtype,mode", [("u1", None), ("i4", "I"), ("f4", "F")])
+def test_reads_lzw_files(tmp_path, dtype, mode):
+    """LZW strips written by libtiff (Pillow): smooth data (long matches, the table fills and is
+    cleared) and noise (mostly literals, code widths up to 12 bits)."""
+    rng = np.random.default_rng(4)
+    y, x = np.mgrid[0:333, 0:411]
+    for name, values in (("smooth", ((x // 7 + y // 5) % 200).astype(dtype)),
+                         ("noise", rng.integers(0, 250, (333, 411)).astype(dtype))):
+        path = str(tmp_path / (name + ".tif"))
+        PIL_Image.fromarray(values, mode=mode).save(path, compression="tiff_lzw")
+        tif = geotiff.GeoTiff(path)
+        assert tif.compression == 5 and tif.dtype == np.dtype(dtype)
+        np.testing.assert_array_equal(tif.read()[0], values)
+        np.testing.assert_array_equal(tif.read_window(0, 1, 300, 333, 7, 400)[0], values[300:, 7:400])
+
+
 def test_unsupported_files_raise(tmp_path):
     path = str(tmp_path / "c.tif")
-    PIL_Image.fromarray(np.zeros((4, 4), "u1")).save(path, compression="tiff_lzw")
+    PIL_Image.fromarray(np.zeros((4, 4), "u1")).save(path, compression="packbits")
     with pytest.raises(NotImplementedError):
         geotiff.GeoTiff(path)
     with open(path, "wb") as f:
