@@ -9,7 +9,7 @@ there is small and fully specified by TIFF 6.0 + the GeoTIFF 1.1 key directory:
   256 x 256 tiles, Adobe-deflate (code 8), ModelPixelScale + ModelTiepoint, a GeoKey directory with
   the EPSG code, the ``GDAL_NODATA`` ASCII tag (42113); BigTIFF when the file passes 4 GB.
 * ``GeoTiff``: header of a TIFF / BigTIFF (both byte orders; strips or tiles; uncompressed or
-  deflate / LZW; horizontal predictor; chunky or planar samples) and ``read_window``, which inflates only
+  deflate / LZW; horizontal and floating-point predictors; chunky or planar samples) and ``read_window``, which inflates only
   the tiles a request touches.
 * ``write_vrt`` / ``Mosaic``: the VRT ``gdal.BuildVRT`` makes of equally-gridded tiles
   (`raster/sinks.py:126-145`) and its reader (sources pasted by their ``DstRect``).
@@ -81,10 +81,29 @@ def _geo_keys(projection):
     return directory, ascii_params
 
 
+def _predict(block, predictor):
+    """Forward predictor of one (rows, width) block of little-endian samples -> bytes."""
+    if predictor == 2:       # horizontal differencing of the samples' bit patterns
+        words = block.view(np.dtype("<u{}".format(block.dtype.itemsize)))
+        out = words.copy()
+        out[:, 1:] = words[:, 1:] - words[:, :-1]
+        return out.tobytes()
+    # floating-point predictor (TIFF Technical Note 3): byte planes, most significant first, then
+    # byte-wise horizontal differencing over the whole row
+    rows, width = block.shape
+    planes = block.astype(block.dtype.newbyteorder(">")).view("u1").reshape(rows, width, block.dtype.itemsize)
+    line = np.ascontiguousarray(planes.transpose(0, 2, 1)).reshape(rows, -1)
+    out = line.copy()
+    out[:, 1:] = line[:, 1:] - line[:, :-1]
+    return out.tobytes()
+
+
 def write_geotiff(path, values, geo_transform, projection, no_data_value=None, compress=True, tile=TILE,
-                  bigtiff=None):
+                  bigtiff=None, predictor=1):
     """Write ``values`` ((h, w) or (bands, h, w)) as a tiled GeoTIFF; see the module docstring.
-    ``bigtiff``: None = when the file would pass 4 GB (GDAL's BIGTIFF=IF_NEEDED), True / False = forced."""
+    ``bigtiff``: None = when the file would pass 4 GB (GDAL's BIGTIFF=IF_NEEDED), True / False = forced.
+    ``predictor``: 1 = none (what the reference's sink asks for), 2 = horizontal differencing,
+    3 = floating-point predictor (float rasters)."""
     values = np.asarray(values)
     if values.ndim == 2:
         values = values[np.newaxis]
@@ -97,6 +116,8 @@ def write_geotiff(path, values, geo_transform, projection, no_data_value=None, c
         raise ValueError("Unsupported dtype '{}' for GeoTIFF".format(values.dtype))
     bands, height, width = values.shape
     tiles_x, tiles_y = -(-width // tile), -(-height // tile)
+    if predictor not in (1, 2, 3) or (predictor == 3 and dtype.kind != "f"):
+        raise ValueError("predictor {} does not apply to dtype '{}'".format(predictor, values.dtype))
 
     def encode(index):
         band, rest = divmod(index, tiles_y * tiles_x)
@@ -104,7 +125,7 @@ def write_geotiff(path, values, geo_transform, projection, no_data_value=None, c
         block = np.zeros((tile, tile), dtype=dtype)
         part = values[band, ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile]
         block[:part.shape[0], :part.shape[1]] = part
-        raw = block.tobytes()
+        raw = block.tobytes() if predictor == 1 else _predict(block, predictor)
         return zlib.compress(raw, 6) if compress else raw
 
     n_tiles = bands * tiles_y * tiles_x
@@ -122,6 +143,8 @@ def write_geotiff(path, values, geo_transform, projection, no_data_value=None, c
     ]
     if bands > 1:
         tags.append((338, _SHORT, [0] * (bands - 1)))
+    if predictor != 1:
+        tags.append((317, _SHORT, [predictor]))
     p, a, _, q, _, d = [float(x) for x in geo_transform]
     tags.append((33550, _DOUBLE, [abs(a), abs(d), 0.0]))
     tags.append((33922, _DOUBLE, [0.0, 0.0, 0.0, p, q, 0.0]))
@@ -242,7 +265,7 @@ class GeoTiff(object):
         if self.compression not in (1, 5, 8, 32946):
             raise NotImplementedError("TIFF compression scheme {} (only none, LZW and deflate)".format(self.compression))
         self.predictor = int(t.get(317, [1])[0])
-        if self.predictor not in (1, 2):
+        if self.predictor not in (1, 2, 3) or (self.predictor == 3 and self.dtype.kind != "f"):
             raise NotImplementedError("TIFF predictor {}".format(self.predictor))
         self.planar = int(t.get(284, [1])[0]) if self.bands > 1 else 2
         if 322 in t:
@@ -367,6 +390,12 @@ class GeoTiff(object):
             raw = _lzw_decode(raw)
         elif self.compression != 1:
             raw = zlib.decompress(raw)
+        if self.predictor == 3:   # floating-point predictor: undo the byte differencing and the byte planes
+            size = self.dtype.itemsize
+            line = np.frombuffer(raw, dtype="u1", count=rows * self.block_w * samples * size)
+            line = np.cumsum(line.reshape(rows, -1, samples), axis=1, dtype="u1").reshape(rows, size, -1)
+            block = np.ascontiguousarray(line.transpose(0, 2, 1)).view(self.dtype.newbyteorder(">"))
+            return block.reshape(rows, self.block_w, samples).astype(self.dtype)
         block = np.frombuffer(raw, dtype=self.dtype.newbyteorder(self._e),
                               count=rows * self.block_w * samples).reshape(rows, self.block_w, samples)
         if self.predictor == 2:    # horizontal differencing, on the samples' bit patterns

@@ -67,6 +67,28 @@ def test_bands_wkt_and_geographic(tmp_path):
     assert tif._geo_key(1024) == 2 and tif._geo_key(2048) == 4326
 
 
+@pytest.mark.parametrize("dtype,predictor", [("i2", 2), ("u1", 2), ("f4", 2), ("f4", 3), ("f8", 3)])
+def test_predictors(tmp_path, dtype, predictor):
+    """Horizontal differencing and the floating-point predictor (what GDAL writes with PREDICTOR=2 / 3):
+    written here, read back here and -- where Pillow has an image mode -- by libtiff."""
+    y, x = np.mgrid[0:300, 0:270]
+    values = (np.sin(x / 30.0) * 100 + y * 0.25).astype(dtype)
+    path = str(tmp_path / "p.tif")
+    geotiff.write_geotiff(path, values, GT, "EPSG:28992", None, predictor=predictor)
+    plain = str(tmp_path / "q.tif")
+    geotiff.write_geotiff(plain, values, GT, "EPSG:28992", None)
+    assert os.path.getsize(path) < os.path.getsize(plain)         # the predictor pays on smooth data
+    tif = geotiff.GeoTiff(path)
+    assert tif.predictor == predictor
+    np.testing.assert_array_equal(tif.read()[0], values)
+    np.testing.assert_array_equal(tif.read_window(0, 1, 250, 300, 200, 270)[0], values[250:, 200:])
+    if dtype != "f8":
+        with PIL_Image.open(path) as image:
+            np.testing.assert_array_equal(np.asarray(image), values)
+    with pytest.raises(ValueError):
+        geotiff.write_geotiff(path, values.astype("i4"), GT, "EPSG:28992", None, predictor=3)
+
+
 def test_bigtiff_layout(tmp_path):
     """The 64-bit layout (files past 4 GB) forced on a small raster: offsets and counts are 8-byte
     words, the directory has 20-byte entries; our reader and libtiff read it back."""
