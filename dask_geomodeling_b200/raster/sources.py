@@ -91,6 +91,7 @@ def source_window(geo_transform, bbox, height, width, src_h, src_w):
     col0, col_step, row0, row_step = window_geometry(geo_transform, bbox, height, width)
     c_lo, c_hi = _window(width, col0, col_step, src_w)
     r_lo, r_hi = _window(height, row0, row_step, src_h)
+    r_lo, c_lo = min(r_lo, src_h), min(c_lo, src_w)      # a request beyond the source: empty window
     return r_lo, max(r_hi, r_lo), c_lo, max(c_hi, c_lo)
 
 

@@ -139,3 +139,44 @@ def test_fused_group_with_an_ndarray_operand():
     extra = []
     fusion.build_expression(fusion.optimize(graph, name)[name][1], 1, extra)
     assert extra == []
+
+
+def test_source_window_covers_what_a_request_reads():
+    """`raster.sources.source_window` (the part of a file that RasterFileSource decodes): every
+    source cell the nearest-neighbour formula addresses inside the source lies in the window, which
+    never reaches beyond the first / last addressed cell by more than the clipping to the source."""
+    from dask_geomodeling_b200.raster.sources import source_window, window_geometry
+
+    rng = np.random.default_rng(12)
+    src_h, src_w = 600, 530
+    gt = utils.GeoTransform((1000.0, 2.5, 0, 2000.0, 0, -2.5))
+    for _ in range(200):
+        x1, y1 = rng.uniform(700, 2400), rng.uniform(300, 2100)
+        w, h = rng.uniform(3, 900), rng.uniform(3, 900)
+        width, height = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        bbox = (x1, y1, x1 + w, y1 + h)
+        r_lo, r_hi, c_lo, c_hi = source_window(gt, bbox, height, width, src_h, src_w)
+        col0, col_step, row0, row_step = window_geometry(gt, bbox, height, width)
+        cols = np.floor(col0 + np.arange(width) * col_step).astype(int)
+        rows = np.floor(row0 + np.arange(height) * row_step).astype(int)
+        cols, rows = cols[(cols >= 0) & (cols < src_w)], rows[(rows >= 0) & (rows < src_h)]
+        assert 0 <= r_lo <= r_hi <= src_h and 0 <= c_lo <= c_hi <= src_w
+        if len(cols):
+            assert c_lo <= cols.min() and cols.max() < c_hi
+        if len(rows):
+            assert r_lo <= rows.min() and rows.max() < r_hi
+        span_c = np.floor([col0, col0 + (width - 1) * col_step]).astype(int)
+        span_r = np.floor([row0, row0 + (height - 1) * row_step]).astype(int)
+        assert c_lo >= min(max(span_c.min(), 0), src_w) and c_hi <= max(min(span_c.max() + 1, src_w), c_lo)
+        assert r_lo >= min(max(span_r.min(), 0), src_h) and r_hi <= max(min(span_r.max() + 1, src_h), r_lo)
+
+
+def test_prepared_geometry_cache_notices_replaced_elements():
+    from dask_geomodeling_b200.geometry import sources
+
+    polygons = [[(i, 0.0), (i + 1.0, 0.0), (i + 1.0, 1.0)] for i in range(100)]
+    first = sources._prepared(polygons)
+    assert sources._prepared(polygons)[1] is first[1]            # same list: same soup
+    polygons[0] = [(50.0, 50.0), (51.0, 50.0), (51.0, 51.0)]       # an end element is always sampled
+    again = sources._prepared(polygons)
+    assert again[1] is not first[1] and again[2][0].tolist() == [50.0, 50.0, 51.0, 51.0]
