@@ -786,10 +786,18 @@ def _zonal_order_striped(soup, local, no_data_value, bbox, height, rows, statist
             _native.synchronize()      # the library's stream holds work on the stripe: let it finish
         helper = _helper_pool().submit(boundary, ready, tensor.device.index)
     _trace("boundary rows posted")
-    if r1 > r0 and len(inside_ids):
-        got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
-                                    statistic, percentile)
-        mine[0, inside_ids], mine[1, inside_ids] = got, cov > 0
+    try:
+        if r1 > r0 and len(inside_ids):
+            got, cov = _order_stat_call(inside_soup, local, no_data_value, stripe_bbox, thresholds_of(inside_ids),
+                                        statistic, percentile)
+            mine[0, inside_ids], mine[1, inside_ids] = got, cov > 0
+    except BaseException:
+        if helper is not None:      # never leave the helper's send / recv behind a raised error
+            try:
+                helper.result()
+            except BaseException:
+                pass
+        raise
     _trace("select inside the stripe")
     strip_result = helper.result() if helper is not None else boundary()
     if strip_result is not None:
